@@ -1,0 +1,429 @@
+// Earth Mover's Distance (auction-style approximate matching) for sm_100a.
+//
+// Replaces approxmatch / matchcost / matchcostgrad{1,2} (reference: PytorchEMD/cuda/emd_kernel.cu:29-161,
+// 204-246, 290-358; Python side pointnet2/emd.py:7-21).  Algorithm unchanged: 10 temperature levels
+// (-4^7 ... -4^-1, 0), three O(n*m) passes per level.
+//
+// Mapping differences:
+//   reference                                       here
+//   ---------                                       ----
+//   <<<32,512>>> on the legacy default stream:      one thread-block CLUSTER per cloud (1/2/4/8 CTAs
+//   32 CTAs total, clouds serialised per CTA        picked so the grid covers >= 2 waves of 148 SMs);
+//                                                   rows are split across the cluster, the four
+//                                                   remain/ratio vectors are exchanged through L2 and
+//                                                   ordered by barrier.cluster (release/acquire)
+//   tile re-staged for every 512-row group          each thread owns up to 8 rows in registers, a tile
+//                                                   of the other cloud is staged once per pass
+//   match (b*m*n fp32) read-modify-written 10x,     pdr_emd_cost: `match` never exists -- the cost
+//   then re-read by matchcost (~88 B / pair)        sum(d^2 * w) is accumulated in the third pass
+//                                                   (12(n+m) B / cloud of HBM traffic);
+//                                                   pdr_emd_approxmatch: first level stores, later
+//                                                   levels accumulate (no memset, one read fewer)
+//   __expf with the denormal fix-up sequence        ex2.approx.ftz on a pre-scaled level (the values
+//   (FSETP + 2 predicated FMUL per pair)            that differ are < 2^-126 and vanish against the
+//                                                   1e-9 regulariser); -DPDR_EMD_EXACT_EXPF restores it
+// Per-row accumulation order (sequential over the other cloud's index) is the reference's.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pdr {
+namespace {
+
+constexpr int kEmdThreads = 256;
+constexpr int kEmdTile = 1024;
+constexpr int kEmdMaxCluster = 8;
+constexpr int kEmdSlots = 8;  // per-cloud partial-cost slots in the workspace
+
+__device__ __forceinline__ float emd_exp(float level_scaled, float d) {
+#ifdef PDR_EMD_EXACT_EXPF
+  return __expf(level_scaled * d);  // level_scaled == level
+#else
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(level_scaled * d));  // level_scaled == level*log2(e)
+  return r;
+#endif
+}
+
+__device__ __forceinline__ void sync_all(int cs) {
+  if (cs > 1) cg::this_cluster().sync();
+  else __syncthreads();
+}
+
+// Stage tile [p0, p0+cnt) of a cloud with its per-point weight from the L2-resident workspace.
+__device__ __forceinline__ void stage(float4 *s, const float *__restrict__ pts, const float *w, int p0,
+                                      int cnt) {
+  for (int i = threadIdx.x; i < cnt; i += kEmdThreads) {
+    const float *p = pts + (size_t)(p0 + i) * 3;
+    s[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldcg(w + p0 + i));
+  }
+}
+
+template <int R, bool WRITE_MATCH, bool ACC_COST>
+__global__ void __launch_bounds__(kEmdThreads)
+emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float *__restrict__ xyz2_all,
+           float *__restrict__ match_all, float *temp_all, float *__restrict__ cost_out) {
+  __shared__ float4 tile[kEmdTile];
+  __shared__ float s_cost[kEmdThreads / 32];
+  const int cloud = blockIdx.x / cs, rank = blockIdx.x % cs, tid = threadIdx.x;
+  const float *xyz1 = xyz1_all + (size_t)cloud * n * 3;
+  const float *xyz2 = xyz2_all + (size_t)cloud * m * 3;
+  float *match = WRITE_MATCH ? match_all + (size_t)cloud * n * m : nullptr;
+  float *remainL = temp_all + (size_t)cloud * (2 * (size_t)(n + m) + kEmdSlots);
+  float *remainR = remainL + n, *ratioL = remainR + m, *ratioR = ratioL + n, *slots = ratioR + m;
+
+  const int rp1 = (n + cs - 1) / cs, rp2 = (m + cs - 1) / cs;
+  const int kb = min(n, rank * rp1), ke = min(n, kb + rp1);
+  const int lb = min(m, rank * rp2), le = min(m, lb + rp2);
+
+  float multiL, multiR;  // emd_kernel.cu:31-38 (integer division)
+  if (n >= m) { multiL = 1.f; multiR = (float)(n / m); } else { multiL = (float)(m / n); multiR = 1.f; }
+  for (int k = kb + tid; k < ke; k += kEmdThreads) __stcg(remainL + k, multiL);
+  for (int l = lb + tid; l < le; l += kEmdThreads) __stcg(remainR + l, multiR);
+  sync_all(cs);
+
+  float cost_acc = 0.f;
+  for (int j = 7; j >= -2; --j) {
+    float level = -powf(4.0f, (float)j);
+    if (j == -2) level = 0.f;
+#ifndef PDR_EMD_EXACT_EXPF
+    level *= 1.4426950408889634f;
+#endif
+    // ---- pass 1: ratioL[k] = remainL[k] / (1e-9 + sum_l e(k,l) * remainR[l]) ---------------------
+    for (int g = kb; g < ke; g += kEmdThreads * R) {
+      float x[R], y[R], z[R], acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int k = min(g + r * kEmdThreads + tid, n - 1);
+        x[r] = __ldg(xyz1 + k * 3); y[r] = __ldg(xyz1 + k * 3 + 1); z[r] = __ldg(xyz1 + k * 3 + 2);
+        acc[r] = 1e-9f;
+      }
+      for (int l0 = 0; l0 < m; l0 += kEmdTile) {
+        const int cnt = min(kEmdTile, m - l0);
+        __syncthreads();
+        stage(tile, xyz2, remainR, l0, cnt);
+        __syncthreads();
+#pragma unroll 2
+        for (int l = 0; l < cnt; ++l) {
+          const float4 p = tile[l];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float d = dist2_ref(__fsub_rn(p.x, x[r]), __fsub_rn(p.y, y[r]), __fsub_rn(p.z, z[r]));
+            acc[r] = __fmaf_rn(emd_exp(level, d), p.w, acc[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int k = g + r * kEmdThreads + tid;
+        if (k < ke) __stcg(ratioL + k, __ldcg(remainL + k) / acc[r]);
+      }
+    }
+    sync_all(cs);
+    // ---- pass 2: columns.  sumr = remainR[l] * sum_k e * ratioL[k] ---------------------------------
+    for (int g = lb; g < le; g += kEmdThreads * R) {
+      float x[R], y[R], z[R], acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int l = min(g + r * kEmdThreads + tid, m - 1);
+        x[r] = __ldg(xyz2 + l * 3); y[r] = __ldg(xyz2 + l * 3 + 1); z[r] = __ldg(xyz2 + l * 3 + 2);
+        acc[r] = 0.f;
+      }
+      for (int k0 = 0; k0 < n; k0 += kEmdTile) {
+        const int cnt = min(kEmdTile, n - k0);
+        __syncthreads();
+        stage(tile, xyz1, ratioL, k0, cnt);
+        __syncthreads();
+#pragma unroll 2
+        for (int k = 0; k < cnt; ++k) {
+          const float4 p = tile[k];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float d = dist2_ref(__fsub_rn(x[r], p.x), __fsub_rn(y[r], p.y), __fsub_rn(z[r], p.z));
+            acc[r] = __fmaf_rn(emd_exp(level, d), p.w, acc[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int l = g + r * kEmdThreads + tid;
+        if (l < le) {
+          const float rr = __ldcg(remainR + l);
+          const float sumr = acc[r] * rr;
+          const float consumption = fminf(rr / (sumr + 1e-9f), 1.0f);
+          __stcg(ratioR + l, consumption * rr);
+          __stcg(remainR + l, fmaxf(0.0f, rr - sumr));
+        }
+      }
+    }
+    sync_all(cs);
+    // ---- pass 3: w = e * ratioL[k] * ratioR[l]; match += w; remainL[k] -= sum_l w; cost += d^2 w --
+    for (int g = kb; g < ke; g += kEmdThreads * R) {
+      float x[R], y[R], z[R], acc[R], rl[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int kr = g + r * kEmdThreads + tid;
+        const int k = min(kr, n - 1);
+        x[r] = __ldg(xyz1 + k * 3); y[r] = __ldg(xyz1 + k * 3 + 1); z[r] = __ldg(xyz1 + k * 3 + 2);
+        rl[r] = kr < ke ? __ldcg(ratioL + k) : 0.f;  // rows this CTA does not own contribute w = 0
+        acc[r] = 0.f;
+      }
+      for (int l0 = 0; l0 < m; l0 += kEmdTile) {
+        const int cnt = min(kEmdTile, m - l0);
+        __syncthreads();
+        stage(tile, xyz2, ratioR, l0, cnt);
+        __syncthreads();
+#pragma unroll 2
+        for (int l = 0; l < cnt; ++l) {
+          const float4 p = tile[l];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float d = dist2_ref(__fsub_rn(p.x, x[r]), __fsub_rn(p.y, y[r]), __fsub_rn(p.z, z[r]));
+            const float w = emd_exp(level, d) * rl[r] * p.w;
+            acc[r] += w;
+            if (ACC_COST) cost_acc = __fmaf_rn(d, w, cost_acc);
+            if (WRITE_MATCH) {
+              const int k = g + r * kEmdThreads + tid;
+              if (k < ke) {
+                float *mp = match + (size_t)(l0 + l) * n + k;
+                *mp = (j == 7) ? w : *mp + w;
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int k = g + r * kEmdThreads + tid;
+        if (k < ke) __stcg(remainL + k, fmaxf(0.0f, __ldcg(remainL + k) - acc[r]));
+      }
+    }
+    sync_all(cs);
+  }
+  if (ACC_COST) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
+    if ((tid & 31) == 0) s_cost[tid >> 5] = cost_acc;
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.f;
+      for (int w = 0; w < kEmdThreads / 32; ++w) a += s_cost[w];
+      __stcg(slots + rank, a);
+    }
+    sync_all(cs);
+    if (rank == 0 && tid == 0) {
+      float a = 0.f;
+      for (int r = 0; r < cs; ++r) a += __ldcg(slots + r);
+      cost_out[cloud] = a;
+    }
+  }
+}
+
+// matchcost forward: cost[b] = sum_{k,l} d^2(k,l) * match[l][k]   (emd_kernel.cu:204-246)
+__global__ void __launch_bounds__(256)
+matchcost_kernel(int n, int m, const float *__restrict__ xyz1_all, const float *__restrict__ xyz2_all,
+                 const float *__restrict__ match_all, float *__restrict__ partial, int nblk) {
+  __shared__ float4 tile[kEmdTile];
+  __shared__ float s_red[8];
+  const int cloud = blockIdx.y;
+  const float *xyz1 = xyz1_all + (size_t)cloud * n * 3;
+  const float *xyz2 = xyz2_all + (size_t)cloud * m * 3;
+  const float *match = match_all + (size_t)cloud * n * m;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const bool on = k < n;
+  const int kk = on ? k : n - 1;
+  const float x1 = __ldg(xyz1 + kk * 3), y1 = __ldg(xyz1 + kk * 3 + 1), z1 = __ldg(xyz1 + kk * 3 + 2);
+  float sub = 0.f;
+  for (int l0 = 0; l0 < m; l0 += kEmdTile) {
+    const int cnt = min(kEmdTile, m - l0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      const float *p = xyz2 + (size_t)(l0 + i) * 3;
+      tile[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    }
+    __syncthreads();
+    if (on) {
+#pragma unroll 4
+      for (int l = 0; l < cnt; ++l) {
+        const float4 p = tile[l];
+        const float d = dist2_ref(__fsub_rn(p.x, x1), __fsub_rn(p.y, y1), __fsub_rn(p.z, z1));
+        sub = __fmaf_rn(d, __ldg(match + (size_t)(l0 + l) * n + k), sub);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sub += __shfl_xor_sync(0xffffffffu, sub, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sub;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += s_red[w];
+    partial[(size_t)cloud * nblk + blockIdx.x] = a;
+  }
+}
+
+__global__ void sum_partials_kernel(int b, int nblk, const float *__restrict__ partial, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  float a = 0.f;
+  for (int k = 0; k < nblk; ++k) a += partial[(size_t)i * nblk + k];
+  out[i] = a;
+}
+
+// matchcost backward (emd_kernel.cu:290-358):
+//   grad1[k] = grad_cost * 2 * sum_l match[l][k] * (xyz1[k] - xyz2[l])
+//   grad2[l] = grad_cost * 2 * sum_k match[l][k] * (xyz2[l] - xyz1[k])
+template <bool FOR_XYZ1>
+__global__ void __launch_bounds__(256)
+matchcost_grad_kernel(int n, int m, const float *__restrict__ grad_cost, const float *__restrict__ xyz1_all,
+                      const float *__restrict__ xyz2_all, const float *__restrict__ match_all,
+                      float *__restrict__ grad_all) {
+  __shared__ float4 tile[kEmdTile];
+  const int cloud = blockIdx.y;
+  const int na = FOR_XYZ1 ? n : m, nb = FOR_XYZ1 ? m : n;
+  const float *A = (FOR_XYZ1 ? xyz1_all : xyz2_all) + (size_t)cloud * na * 3;
+  const float *B = (FOR_XYZ1 ? xyz2_all : xyz1_all) + (size_t)cloud * nb * 3;
+  const float *match = match_all + (size_t)cloud * n * m;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  const bool on = a < na;
+  const int aa = on ? a : na - 1;
+  const float ax = __ldg(A + aa * 3), ay = __ldg(A + aa * 3 + 1), az = __ldg(A + aa * 3 + 2);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int b0 = 0; b0 < nb; b0 += kEmdTile) {
+    const int cnt = min(kEmdTile, nb - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      const float *p = B + (size_t)(b0 + i) * 3;
+      tile[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    }
+    __syncthreads();
+    if (on) {
+      for (int t = 0; t < cnt; ++t) {
+        const float4 p = tile[t];
+        const float w = FOR_XYZ1 ? __ldg(match + (size_t)(b0 + t) * n + a)    // match[l][k], k = a
+                                 : __ldg(match + (size_t)a * n + (b0 + t));    // match[l][k], l = a
+        gx += (ax - p.x) * w; gy += (ay - p.y) * w; gz += (az - p.z) * w;
+      }
+    }
+  }
+  if (on) {
+    const float g = 2.f * __ldg(grad_cost + cloud);
+    float *o = grad_all + ((size_t)cloud * na + a) * 3;
+    o[0] = gx * g; o[1] = gy * g; o[2] = gz * g;
+  }
+}
+
+int pick_cluster(int b, int n, int m) {
+  const int big = n > m ? n : m;
+  int cs = 1;
+  while (cs < kEmdMaxCluster && (long long)b * cs < 2 * kNumSMs && big / (cs * 2) >= 128) cs *= 2;
+  return cs;
+}
+
+template <bool WRITE_MATCH, bool ACC_COST>
+int launch_emd(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp,
+               float *cost, cudaStream_t stream) {
+  const int cs = pick_cluster(b, n, m);
+  const int big = n > m ? n : m;
+  const int rp = ceil_div(big, cs);
+  const int R = ceil_div(rp, kEmdThreads);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)b * cs);
+  cfg.blockDim = dim3(kEmdThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+#define PDR_EMD_LAUNCH(RR) \
+  e = cudaLaunchKernelEx(&cfg, emd_kernel<RR, WRITE_MATCH, ACC_COST>, n, m, cs, xyz1, xyz2, match, temp, cost)
+  if (R <= 1) PDR_EMD_LAUNCH(1);
+  else if (R <= 2) PDR_EMD_LAUNCH(2);
+  else if (R <= 4) PDR_EMD_LAUNCH(4);
+  else PDR_EMD_LAUNCH(8);
+#undef PDR_EMD_LAUNCH
+  if (e != cudaSuccess) {
+    set_error("emd_kernel launch (cluster %d): %s", cs, cudaGetErrorString(e));
+    return PDR_ERR_CUDA;
+  }
+  return check_launch("emd_kernel");
+}
+
+int emd_check(const char *op, int b, int n, int m, const void *temp, size_t temp_bytes) {
+  PDR_REQUIRE(b >= 0 && n >= 1 && m >= 1, "%s: bad sizes b=%d n=%d m=%d", op, b, n, m);
+  PDR_REQUIRE((long long)b * kEmdMaxCluster < (1ll << 31), "%s: b too large", op);
+  const size_t need = pdr_emd_workspace_bytes(b, n, m);
+  if (b > 0 && (!temp || temp_bytes < need)) {
+    set_error("%s: workspace %zu B < %zu B", op, temp_bytes, need);
+    return PDR_ERR_WORKSPACE;
+  }
+  return PDR_OK;
+}
+
+}  // namespace
+}  // namespace pdr
+
+using namespace pdr;
+
+extern "C" size_t pdr_emd_workspace_bytes(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0) return 0;
+  const size_t per_cloud = 2 * ((size_t)n + m) + kEmdSlots;
+  const size_t mc = (size_t)ceil_div(n, 256);  // matchcost partials share the same scratch
+  return (size_t)b * (per_cloud > mc ? per_cloud : mc) * sizeof(float);
+}
+
+extern "C" int pdr_emd_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match,
+                                   void *temp, size_t temp_bytes, void *stream) {
+  int rc = emd_check("emd_approxmatch", b, n, m, temp, temp_bytes);
+  if (rc) return rc;
+  if (b == 0) return PDR_OK;
+  PDR_REQUIRE(xyz1 && xyz2 && match, "emd_approxmatch: null pointer");
+  return launch_emd<true, false>(b, n, m, xyz1, xyz2, match, (float *)temp, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int pdr_emd_cost(int b, int n, int m, const float *xyz1, const float *xyz2, float *cost, void *temp,
+                            size_t temp_bytes, void *stream) {
+  int rc = emd_check("emd_cost", b, n, m, temp, temp_bytes);
+  if (rc) return rc;
+  if (b == 0) return PDR_OK;
+  PDR_REQUIRE(xyz1 && xyz2 && cost, "emd_cost: null pointer");
+  return launch_emd<false, true>(b, n, m, xyz1, xyz2, nullptr, (float *)temp, cost, (cudaStream_t)stream);
+}
+
+extern "C" int pdr_emd_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match,
+                                 float *cost, void *temp, size_t temp_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = emd_check("emd_matchcost", b, n, m, temp, temp_bytes);
+  if (rc) return rc;
+  PDR_REQUIRE(b <= 65535, "emd_matchcost: b > 65535");
+  if (b == 0) return PDR_OK;
+  PDR_REQUIRE(xyz1 && xyz2 && match && cost, "emd_matchcost: null pointer");
+  const int nblk = ceil_div(n, 256);
+  float *partial = (float *)temp;  // (b, nblk) per-CTA partial sums, added in index order below
+  matchcost_kernel<<<dim3(nblk, b), 256, 0, stream>>>(n, m, xyz1, xyz2, match, partial, nblk);
+  rc = check_launch("matchcost_kernel");
+  if (rc) return rc;
+  sum_partials_kernel<<<ceil_div(b, 128), 128, 0, stream>>>(b, nblk, partial, cost);
+  return check_launch("sum_partials_kernel");
+}
+
+extern "C" int pdr_emd_matchcost_backward(int b, int n, int m, const float *grad_cost, const float *xyz1,
+                                          const float *xyz2, const float *match, float *grad1, float *grad2,
+                                          void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PDR_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "emd_matchcost_backward: bad sizes");
+  if (b == 0) return PDR_OK;
+  PDR_REQUIRE(grad_cost && xyz1 && xyz2 && match && grad1 && grad2, "emd_matchcost_backward: null pointer");
+  matchcost_grad_kernel<true><<<dim3(ceil_div(n, 256), b), 256, 0, stream>>>(n, m, grad_cost, xyz1, xyz2, match, grad1);
+  int rc = check_launch("matchcost_grad_kernel<1>");
+  if (rc) return rc;
+  matchcost_grad_kernel<false><<<dim3(ceil_div(m, 256), b), 256, 0, stream>>>(n, m, grad_cost, xyz1, xyz2, match, grad2);
+  return check_launch("matchcost_grad_kernel<2>");
+}

@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing for the sampling path: one process per GPU, shapes sharded across ranks, no
+collective during the T reverse steps, ONE all_gather of the generated clouds (and of the per-shape
+metrics) at the end over NCCL/NVLink.
+
+Replaces the reference's Popen fan-out + filesystem gather (pointnet2/generate_samples_distributed.py:
+26-97,188-201) and the per-step nn.DataParallel scatter/gather (pointnet2/completion_eval.py:113-118).
+Sharding follows the reference's contiguous-range rule (mvp_dataloader/mvp_dataset.py:152-198).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous [start, stop) of `total` shapes owned by `rank`; the first `total % world` ranks get one
+    extra shape."""
+    base, rem = divmod(total, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend=None):
+    """Join the process group described by RANK/WORLD_SIZE/MASTER_ADDR/MASTER_PORT (torchrun).  Returns
+    (rank, world_size, local_rank).  No-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def all_gather_shapes(local, counts=None):
+    """Concatenate per-rank tensors (n_r, ...) along dim 0 on every rank.  Ranks may hold different n_r
+    (pass `counts`, the list of n_r, or let it be exchanged first)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    if counts is None:
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        ns = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(ns, n)
+        counts = [int(v.item()) for v in ns]
+    mx = max(counts)
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], dim=0)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad.contiguous())
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def sample_sharded(sample_fn, total_shapes, rank, world_size):
+    """Run `sample_fn(start, stop) -> (n_local, N, 3)` on this rank's shard and gather everything."""
+    start, stop = shard_range(total_shapes, rank, world_size)
+    local = sample_fn(start, stop)
+    counts = [shard_range(total_shapes, r, world_size) for r in range(world_size)]
+    return all_gather_shapes(local, counts=[b - a for a, b in counts])

@@ -1,0 +1,251 @@
+"""``PointNet2CloudCondition``: the dual-path conditional PointNet++ denoiser eps_theta(x_t, t, c)
+(reference: pointnet2/models/pointnet2_with_pcld_condition.py).
+
+Same constructor (the ``pointnet_config`` dict), same ``forward(pointcloud, condition, ts, label,
+use_retained_condition_feature)`` / ``reset_cond_features()`` contract, same parameter names.
+
+Structure differs from the reference: the condition branch (SA_modules_condition, FP_modules_condition,
+global PointNet) depends only on the condition cloud, never on x_t, so it is evaluated as one block
+(`encode_condition`) and retained for the remaining 999 steps, instead of being interleaved with the
+x_t branch level by level (reference :383-447).  The arithmetic per module is unchanged.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from .pnet import Pnet2Stage
+from .pointnet2_modules import FeatureMapModule, Swish
+from .pointnet2_ssg_sem import PointNet2SemSegSSG, calc_t_emb, swish  # noqa: F401  (re-exported)
+
+
+class ConditionState:
+    """What is retained between denoising steps for one batch of condition clouds."""
+
+    __slots__ = ("l_uvw", "encoder", "decoder", "global_feature")
+
+    def __init__(self, l_uvw, encoder, decoder, global_feature):
+        self.l_uvw, self.encoder, self.decoder, self.global_feature = l_uvw, encoder, decoder, global_feature
+
+
+class PointNet2CloudCondition(PointNet2SemSegSSG):
+    def _build_model(self):
+        hp = self.hparams
+        for flag in ("concate_partial_with_noisy_input", "use_position_encoding"):
+            if hp.get(flag, False):
+                raise NotImplementedError("pointnet_config['%s']=True is not used by any shipped config and is "
+                                          "not supported by the B200 path" % flag)
+        self._cond_state = None
+        self.attention_setting = hp.get("attention_setting", None)
+        self.FeatureMapper_attention_setting = copy.deepcopy(self.attention_setting)
+        if self.FeatureMapper_attention_setting is not None:
+            self.FeatureMapper_attention_setting["use_attention_module"] = (
+                self.FeatureMapper_attention_setting["add_attention_to_FeatureMapper_module"])
+        self.global_attention_setting = hp.get("global_attention_setting", None)
+        self.bn = hp.get("bn", True)
+        self.scale_factor = 1
+        self.record_neighbor_stats = hp["record_neighbor_stats"]
+        if hp["include_class_condition"]:
+            self.class_emb = nn.Embedding(hp["num_class"], hp["class_condition_dim"])
+
+        in_fea_dim = hp["in_fea_dim"]
+        partial_in_fea_dim = hp.get("partial_in_fea_dim", in_fea_dim)
+        self.attach_position_to_input_feature = hp["attach_position_to_input_feature"]
+        if self.attach_position_to_input_feature:
+            in_fea_dim += 3
+            partial_in_fea_dim += 3
+        self.partial_in_fea_dim = partial_in_fea_dim
+        self.include_abs_coordinate = hp["include_abs_coordinate"]
+        self.pooling = hp.get("pooling", "max")
+        self.network_activation = hp.get("activation", "relu")
+        assert self.network_activation in ("relu", "swish")
+        self.network_activation_function = nn.ReLU(True) if self.network_activation == "relu" else Swish()
+        self.include_local_feature = hp.get("include_local_feature", True)
+        self.include_global_feature = hp.get("include_global_feature", False)
+
+        self.global_feature_dim = None
+        if self.include_global_feature:
+            g_arch = hp["pnet_global_feature_architecture"]
+            self.global_feature_dim = g_arch[1][-1]
+            self.global_pnet = Pnet2Stage(g_arch[0], g_arch[1], bn=self.bn,
+                                          remove_last_activation=hp.get("global_feature_remove_last_activation", True))
+
+        t_dim = hp["t_dim"]
+        self.fc_t1 = nn.Linear(t_dim, 4 * t_dim)
+        self.fc_t2 = nn.Linear(4 * t_dim, 4 * t_dim)
+        self.activation = swish
+
+        mapper_kw = dict(use_xyz=hp["model.use_xyz"], include_abs_coordinate=self.include_abs_coordinate,
+                         include_center_coordinate=hp.get("include_center_coordinate", False), bn=self.bn,
+                         bn_first=hp["bn_first"], bias=hp["bias"], res_connect=hp["res_connect"],
+                         activation=self.network_activation, attention_setting=self.FeatureMapper_attention_setting)
+        arch = hp["architecture"]
+        enc_map_dim = dec_map_dim = None
+        if self.include_local_feature:
+            c_arch = hp["condition_net_architecture"]
+            m_arch = hp["feature_mapper_architecture"]
+            c_feat = c_arch["feature_dim"]
+            self.SA_modules_condition = self.build_SA_model(
+                c_arch["npoint"], c_arch["radius"], c_arch["nsample"], c_feat, c_arch["mlp_depth"],
+                partial_in_fea_dim, False, False, neighbor_def=c_arch["neighbor_definition"],
+                activation=self.network_activation, bn=self.bn, attention_setting=self.attention_setting)
+            enc_map_dim = m_arch["encoder_feature_map_dim"]
+            self.encoder_feature_map = nn.ModuleList()
+            for i, out_dim in enumerate(enc_map_dim):
+                first_conv = hp["bn_first"] and i == 0
+                in_dim = partial_in_fea_dim if (i == 0 and not first_conv) else c_feat[i]
+                query_dim = in_fea_dim if i == 0 else arch["feature_dim"][i]
+                self.encoder_feature_map.append(FeatureMapModule(
+                    [in_dim] + [out_dim] * m_arch["encoder_mlp_depth"], m_arch["encoder_radius"][i],
+                    m_arch["encoder_nsample"][i], first_conv=first_conv, first_conv_in_channel=partial_in_fea_dim,
+                    neighbor_def=m_arch["neighbor_definition"], query_feature_dim=query_dim, **mapper_kw))
+
+        enc_extra = enc_map_dim if self.include_local_feature else None
+        self.SA_modules = self.build_SA_model(
+            arch["npoint"], arch["radius"], arch["nsample"], arch["feature_dim"], arch["mlp_depth"],
+            in_fea_dim + (enc_map_dim[0] if self.include_local_feature else 0), hp["include_t"],
+            hp["include_class_condition"], include_global_feature=self.include_global_feature,
+            global_feature_dim=self.global_feature_dim, additional_fea_dim=enc_extra,
+            neighbor_def=arch["neighbor_definition"], activation=self.network_activation, bn=self.bn,
+            attention_setting=self.attention_setting, global_attention_setting=self.global_attention_setting)
+
+        if self.include_local_feature:
+            c_dec = c_arch["decoder_feature_dim"]
+            assert c_dec[-1] == c_feat[-1]
+            self.FP_modules_condition = self.build_FP_model(
+                c_dec, c_arch["decoder_mlp_depth"], c_feat, partial_in_fea_dim, False, False,
+                use_knn_FP=c_arch.get("use_knn_FP", False), K=c_arch.get("K", 3),
+                include_grouper=c_arch.get("include_grouper", False), radius=c_arch["radius"],
+                nsample=c_arch["nsample"], neighbor_def=c_arch["neighbor_definition"],
+                activation=self.network_activation, bn=self.bn, attention_setting=self.attention_setting)
+            dec_map_dim = m_arch["decoder_feature_map_dim"]
+            self.decoder_feature_map = nn.ModuleList()
+            for i, out_dim in enumerate(dec_map_dim):
+                self.decoder_feature_map.append(FeatureMapModule(
+                    [c_dec[i]] + [out_dim] * m_arch["decoder_mlp_depth"], m_arch["decoder_radius"][i],
+                    m_arch["decoder_nsample"][i], first_conv=False, first_conv_in_channel=0,
+                    neighbor_def=m_arch["neighbor_definition"],
+                    query_feature_dim=arch["decoder_feature_dim"][i], **mapper_kw))
+
+        dec = arch["decoder_feature_dim"]
+        assert dec[-1] == arch["feature_dim"][-1]
+        self.FP_modules = self.build_FP_model(
+            dec, arch["decoder_mlp_depth"], arch["feature_dim"], in_fea_dim, hp["include_t"],
+            hp["include_class_condition"], include_global_feature=self.include_global_feature,
+            global_feature_dim=self.global_feature_dim,
+            additional_fea_dim=dec_map_dim[1:] if self.include_local_feature else None,
+            use_knn_FP=arch.get("use_knn_FP", False), K=arch.get("K", 3),
+            include_grouper=arch.get("include_grouper", False), radius=arch["radius"], nsample=arch["nsample"],
+            neighbor_def=arch["neighbor_definition"], activation=self.network_activation, bn=self.bn,
+            attention_setting=self.attention_setting, global_attention_setting=self.global_attention_setting)
+
+        # refinement / upsampling head width (reference :238-244; mutates hparams like the reference)
+        factor = hp.get("point_upsample_factor", 1)
+        if factor > 1:
+            if hp.get("include_displacement_center_to_final_output", False):
+                factor -= 1
+            hp["out_dim"] = int(hp["out_dim"] * (factor + 1))
+        head_in = dec[0] + 3 + (dec_map_dim[0] if self.include_local_feature else 0)
+        self.fc_lyaer = self._build_head(head_in, copy.deepcopy(self.network_activation_function), bn=self.bn)
+
+    # -- retained condition state -------------------------------------------------------------------
+    def reset_cond_features(self):
+        self._cond_state = None
+
+    # attribute views kept for callers that poke at the reference's fields
+    @property
+    def l_uvw(self):
+        return self._cond_state.l_uvw if self._cond_state else None
+
+    @property
+    def encoder_cond_features(self):
+        return self._cond_state.encoder if self._cond_state else None
+
+    @property
+    def decoder_cond_features(self):
+        return self._cond_state.decoder if self._cond_state else None
+
+    @property
+    def global_feature(self):
+        return self._cond_state.global_feature if self._cond_state else None
+
+    def encode_condition(self, condition):
+        """Everything that depends on the condition cloud only.  condition (B,M,3+partial feats)."""
+        uvw = condition[:, :, 0:3].contiguous() / self.scale_factor
+        n_in = self.partial_in_fea_dim - (3 if self.attach_position_to_input_feature else 0)
+        global_feature = None
+        if self.include_global_feature:
+            g_in = torch.cat([uvw, condition[:, :, 3:3 + n_in]], dim=2) if n_in > 0 else uvw
+            global_feature = self.global_pnet(g_in.transpose(1, 2))
+        l_uvw, enc, dec = None, None, None
+        if self.include_local_feature:
+            if self.attach_position_to_input_feature:
+                condition = torch.cat([condition, uvw], dim=2)
+            _, feats = self._break_up_pc(condition)
+            rec, pool = self.record_neighbor_stats, self.pooling
+            l_uvw, enc = [uvw], [feats]
+            for sa in self.SA_modules_condition:
+                u, f = sa(l_uvw[-1], enc[-1], t_emb=None, condition_emb=None, subset=True,
+                          record_neighbor_stats=rec, pooling=pool)
+                l_uvw.append(u)
+                enc.append(f)
+            dec = list(enc)
+            for i in range(len(self.FP_modules_condition) - 1, -1, -1):
+                dec[i] = self.FP_modules_condition[i](l_uvw[i], l_uvw[i + 1], enc[i], dec[i + 1], t_emb=None,
+                                                      condition_emb=None, record_neighbor_stats=rec, pooling=pool)
+        return ConditionState(l_uvw, enc, dec, global_feature)
+
+    def forward(self, pointcloud, condition, ts=None, label=None, use_retained_condition_feature=False):
+        """pointcloud (B,N,3), condition (B,M,3+C), ts (B,), label (B,) long -> (B,N,out_dim)."""
+        if self.include_global_feature or self.include_local_feature:
+            assert condition is not None
+        with torch.no_grad():
+            if self.attach_position_to_input_feature:
+                pointcloud = torch.cat([pointcloud, pointcloud[:, :, 0:3] / self.scale_factor], dim=2)
+            xyz, features = self._break_up_pc(pointcloud)
+            xyz = xyz / self.scale_factor
+
+        t_emb = self.embed_t(ts)
+        class_emb = (self.class_emb(label) if (label is not None and self.hparams["include_class_condition"])
+                     else None)
+
+        if use_retained_condition_feature and self._cond_state is not None:
+            cs = self._cond_state
+        else:
+            cs = self.encode_condition(condition)
+            if use_retained_condition_feature:
+                cs.global_feature = None if cs.global_feature is None else cs.global_feature.detach().clone()
+                self._cond_state = cs
+
+        if self.include_global_feature:
+            condition_emb = cs.global_feature
+            second_condition_emb = class_emb if self.hparams["include_class_condition"] else None
+        else:
+            condition_emb = class_emb if self.hparams["include_class_condition"] else None
+            second_condition_emb = None
+        emb = dict(t_emb=t_emb, condition_emb=condition_emb, second_condition_emb=second_condition_emb)
+        rec, pool = self.record_neighbor_stats, self.pooling
+
+        def transfer(mapper, level, feats_at_level):
+            mapped = mapper(cs.l_uvw[level], feats_at_level, l_xyz[level], subset=False,
+                            record_neighbor_stats=rec, pooling=pool, features_at_new_xyz=l_features[level])
+            return torch.cat([mapped, l_features[level]], dim=1)
+
+        l_xyz, l_features = [xyz], [features]
+        for i, sa in enumerate(self.SA_modules):
+            inp = transfer(self.encoder_feature_map[i], i, cs.encoder[i]) if self.include_local_feature \
+                else l_features[i]
+            li_xyz, li_features = sa(l_xyz[i], inp, subset=True, record_neighbor_stats=rec, pooling=pool, **emb)
+            l_xyz.append(li_xyz)
+            l_features.append(li_features)
+
+        for lvl in range(len(self.FP_modules), 0, -1):
+            inp = transfer(self.decoder_feature_map[lvl], lvl, cs.decoder[lvl]) if self.include_local_feature \
+                else l_features[lvl]
+            l_features[lvl - 1] = self.FP_modules[lvl - 1](l_xyz[lvl - 1], l_xyz[lvl], l_features[lvl - 1], inp,
+                                                           record_neighbor_stats=rec, pooling=pool, **emb)
+
+        out_feature = transfer(self.decoder_feature_map[0], 0, cs.decoder[0]) if self.include_local_feature \
+            else l_features[0]
+        out_feature = torch.cat([out_feature, xyz.transpose(1, 2)], dim=1)
+        return self.fc_lyaer(out_feature).transpose(1, 2)

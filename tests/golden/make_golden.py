@@ -1,0 +1,137 @@
+"""Generate the committed golden fixtures by running the REFERENCE's own Python (imported from
+/root/reference, never copied) on CPU, with its native modules (`pointnet2_ops._ext`,
+`pytorch3d.ops.knn`, `emd_cuda`) bound to the CPU oracle (oracle/cpu_oracle.py).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Outputs (small, committed): tests/golden/*.pt, tests/golden/state_dict_keys.json
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("PDR_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, ROOT)
+
+from oracle import cpu_oracle as O  # noqa: E402
+from tests import common as C  # noqa: E402
+
+
+def bind_reference_to_oracle():
+    """sys.modules shims so that the unmodified reference Python runs on the CPU oracle."""
+    import point_diffusion_refinement_b200.dropin as dropin
+    ext = types.ModuleType("oracle_ext")
+    for name in ("furthest_point_sampling", "gather_points", "ball_query", "group_points", "three_nn",
+                 "three_interpolate"):
+        setattr(ext, name, getattr(O, name))
+    ext.three_nn = lambda u, k: list(O.three_nn(u, k))
+    knn = types.ModuleType("oracle_knn")
+    knn.knn_points, knn.knn_gather = O.knn_points, O.knn_gather
+    knn.Pointclouds = type("Pointclouds", (), {})
+    emd = types.ModuleType("oracle_emd")
+    emd.approxmatch_forward, emd.matchcost_forward = O.approxmatch_forward, O.matchcost_forward
+    dropin.install(ext=ext, knn_module=knn, emd_module=emd)
+    for p in (os.path.join(REF, "pointnet2"), REF, os.path.join(REF, "pointnet2_ops_lib")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def main():
+    bind_reference_to_oracle()
+    from pointnet2.models.pointnet2_with_pcld_condition import PointNet2CloudCondition as RefNet
+    from pointnet2.models.pointnet2_ssg_sem import PointNet2SemSegSSG as RefSSG
+    import pointnet2.util as ref_util  # reference util.py (schedule)
+    import pointnet2.util_fastdpmv2 as ref_fast
+    from point_diffusion_refinement_b200 import configs
+
+    out = {}
+    # ---- 1. state_dict contract of the shipped DDPM config -------------------------------------------
+    torch.manual_seed(0)
+    net = RefNet(configs.ddpm_pointnet_config()).eval()
+    keys = {k: list(v.shape) for k, v in net.state_dict().items()}
+    refine = RefNet(configs.refine_pointnet_config(8)).eval()
+    keys_refine = {k: list(v.shape) for k, v in refine.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_keys.json"), "w") as f:
+        json.dump({"ddpm": keys, "refine_x8": keys_refine}, f, indent=0, sort_keys=True)
+    print("ddpm params: %.3f M in %d tensors" % (sum(np.prod(s) for s in keys.values()) / 1e6, len(keys)))
+
+    # ---- 2. one eps_theta call, tiny pyramid (CPU-test sized), cold and warm --------------------------
+    for tag, cfg, B, N, M in (("tiny", configs.tiny_pointnet_config(), 2, 256, 384),
+                              ("full", configs.ddpm_pointnet_config(), 2, 2048, 3072)):
+        net = RefNet(cfg).eval()
+        C.fill_parameters_(net, seed=1)
+        x, cond, ts, label = C.denoiser_inputs(B, N, M, seed=3)
+        with torch.no_grad():
+            cold = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+            x2 = x + 0.05 * cold
+            warm = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+            net.reset_cond_features()
+            plain = net(x, cond, ts=ts, label=label, use_retained_condition_feature=False)
+        assert torch.equal(plain, cold)
+        torch.save({"cfg": tag, "B": B, "N": N, "M": M, "param_seed": 1, "input_seed": 3,
+                    "eps_cold": cold.clone(), "eps_warm": warm.clone()},
+                   os.path.join(HERE, "denoiser_%s.pt" % tag))
+        print(tag, "eps cold/warm abs-mean", cold.abs().mean().item(), warm.abs().mean().item())
+
+    # refinement net (include_t False, upsample x2 head)
+    cfg = configs.tiny_pointnet_config()
+    cfg["include_t"] = False
+    cfg["point_upsample_factor"] = 2
+    cfg["include_displacement_center_to_final_output"] = False
+    net = RefNet(cfg).eval()
+    C.fill_parameters_(net, seed=2)
+    x, cond, ts, label = C.denoiser_inputs(2, 256, 384, seed=4)
+    with torch.no_grad():
+        disp = net(x, cond, ts=None, label=label)
+    torch.save({"disp": disp.clone(), "param_seed": 2, "input_seed": 4}, os.path.join(HERE, "refiner_tiny.pt"))
+
+    # ---- 3. unconditional PointNet2SemSegSSG with three_nn / three_interpolate decoder ----------------
+    ssg_cfg = C.ssg_config()
+    net = RefSSG(ssg_cfg).eval()
+    C.fill_parameters_(net, seed=5)
+    g = torch.Generator().manual_seed(6)
+    pc = torch.randn(2, 256, 3, generator=g)
+    with torch.no_grad():
+        y = net(pc, ts=torch.tensor([10.0, 500.0]), label=torch.tensor([1, 7]))
+    torch.save({"out": y.clone(), "keys": {k: list(v.shape) for k, v in net.state_dict().items()}},
+               os.path.join(HERE, "ssg_tiny.pt"))
+
+    # ---- 4. schedules -------------------------------------------------------------------------------
+    dh = ref_util.calc_diffusion_hyperparams(**configs.DIFFUSION_CONFIG)
+    sched = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in dh.items()}
+    fast = {}
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self  # reference calls .cuda() on schedule tensors
+    try:
+        for length, schedule in ((50, "quadratic"), (20, "linear")):
+            eta = ref_fast.get_VAR_noise(length, configs.DIFFUSION_CONFIG, schedule)
+            taus = ref_fast._precompute_VAR_steps(dh, eta)
+            steps = ref_fast.get_STEP_step(length, configs.DIFFUSION_CONFIG, schedule)
+            fast["%d_%s" % (length, schedule)] = {"eta": torch.from_numpy(np.asarray(eta)),
+                                                  "taus": torch.tensor(taus, dtype=torch.float64),
+                                                  "steps": steps}
+    finally:
+        torch.Tensor.cuda = real_cuda
+    torch.save({"ddpm": sched, "fast": fast}, os.path.join(HERE, "schedules.pt"))
+
+    # ---- 5. reference-owned known answers ------------------------------------------------------------
+    # (a) PytorchEMD/test_emd_loss.py:6-19: 2x2 clouds, optimal assignment cost 0.71 -> /max(n,m) = 0.355
+    # (b) ChamferDistancePytorch/unit_test.py:14-35: chamfer vs float64 brute force, rand(4,100,3) x rand(4,200,3)
+    g = torch.Generator().manual_seed(7)
+    p1, p2 = torch.rand(4, 100, 3, generator=g), torch.rand(4, 200, 3, generator=g)
+    P = ((p1.double()[:, :, None, :] - p2.double()[:, None, :, :]) ** 2).sum(-1)
+    torch.save({"p1": p1, "p2": p2, "dist1": P.min(2)[0].float(), "dist2": P.min(1)[0].float(),
+                "idx1": P.min(2)[1].int(), "idx2": P.min(1)[1].int()}, os.path.join(HERE, "chamfer_f64.pt"))
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
