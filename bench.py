@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the hot path on B200, one JSON line on stdout (rank 0).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): conditional DDPM reverse
+sampling, B = 32 shapes per GPU, 2048-point output, 3072-point mirrored partial condition (4 channels),
+random-init PointNet2CloudCondition (9.76 M parameters, shipped DDPM config), T = 1000.
+A *step* is one pass of the hot path over one batch: eps_theta(x_t, t, c) with retained condition
+features + the posterior update with fresh device noise.  metric = shapes/s of the full T=1000 chain
+= (world * B) / (T * seconds per step); steps are warm steps (the one cold step per chain, which also
+encodes the condition cloud, is timed separately and reported as `cold_ms`).
+`e2e` runs util.sampling() -- the public API -- from pinned HOST buffers (condition, labels, x_T copied
+H2D, result copied D2H inside the timed region) for `--e2e-steps` reverse steps, cold step included.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_CHAIN = 1000
+N_POINTS, M_COND = 2048, 3072
+WORKLOAD = "ddpm_reverse_step B=32/gpu N=2048 cond=3072x4 T=1000 PointNet2CloudCondition(9.76M, random init)"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--batch", type=int, default=32, help="shapes per GPU")
+    p.add_argument("--e2e-steps", type=int, default=50)
+    p.add_argument("--cpu-batch", type=int, default=2, help="shapes per step of the CPU arm (bounded sample)")
+    p.add_argument("--no-tf32", action="store_true", help="fp32 SIMT GEMMs instead of TF32 tensor cores")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic inputs and model
+# ------------------------------------------------------------------------------------------------------
+def make_inputs(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    uvw = torch.rand(B, M_COND, 3, generator=g) * 2 - 1
+    flag = torch.ones(B, M_COND, 1)
+    flag[:, M_COND // 2:] = -1
+    cond = torch.cat([uvw, flag], dim=2)
+    label = torch.arange(B) % 16
+    xT = torch.randn(B, N_POINTS, 3, generator=g)
+    return cond, label, xT
+
+
+def make_net(device):
+    from point_diffusion_refinement_b200 import configs
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    torch.manual_seed(0)
+    return PointNet2CloudCondition(configs.ddpm_pointnet_config()).eval().to(device)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks during the timed region (profiling recipe)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# per-kernel accounting: which of OUR kernels dominates the step, and its roofline
+# ------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name, a):
+    """Algorithmic HBM bytes of one C-ABI call from its integer arguments (per-kernel table)."""
+    def num(v):
+        v = getattr(v, "value", v)
+        return int(v) if isinstance(v, (int, float)) else 0
+    i = [num(v) for v in a[:6]]
+    if name == "pdr_furthest_point_sampling":
+        b, n, m = i[:3]
+        return b * (12 * n + 4 * m)
+    if name == "pdr_ball_query":
+        b, n, m = i[:3]
+        ns = num(a[4])
+        return b * (12 * (n + m) + 4 * m * (ns + 1))
+    if name == "pdr_group_points":
+        b, c, n, npt, ns = i[:5]
+        return b * (4 * npt * ns + 4 * c * npt * ns + 4 * c * min(n, npt * ns))
+    if name == "pdr_gather_points":
+        b, c, n, m = i[:4]
+        return b * (4 * m + 8 * c * m)
+    if name == "pdr_knn_points":
+        b, p1, p2, k = i[:4]
+        return b * (12 * (p1 + p2) + 12 * p1 * k)
+    if name == "pdr_affine_noise_update":
+        return 12 * i[0]
+    return None
+
+
+class KernelAccounting:
+    """Wraps point_diffusion_refinement_b200._lib.call with CUDA events on the launching stream."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        from point_diffusion_refinement_b200 import _lib
+        self._lib, self._orig = _lib, _lib.call
+        mods = [m for n, m in sys.modules.items() if n.startswith("point_diffusion_refinement_b200") and hasattr(m, "call")]
+        self._mods = mods
+
+        def wrapped(name, *args):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self._orig(name, *args)
+            e.record()
+            self.records.append((name, args, s, e))
+
+        for m in mods:
+            m.call = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        for m in self._mods:
+            m.call = self._orig
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, args, s, e in self.records:
+            ms = s.elapsed_time(e)
+            d = agg.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+            d["calls"] += 1
+            d["ms"] += ms
+            b = algorithmic_bytes(name, args)
+            d["bytes"] += b or 0
+        return agg
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the same step through the package's host modules bound to the CPU oracle
+# ------------------------------------------------------------------------------------------------------
+def cpu_step_seconds(batch, steps, warmup):
+    """Seconds per warm DDPM step on the host cores (oracle port: C/OpenMP ops + CPU torch for the MLPs)."""
+    from tests import common as C
+    from point_diffusion_refinement_b200 import configs
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    torch.manual_seed(0)
+    net = PointNet2CloudCondition(configs.ddpm_pointnet_config()).eval()
+    cond, label, x = make_inputs(batch, seed=1)
+    ts = torch.full((batch,), 999.0)
+    with C.package_bound_to_oracle(), torch.no_grad():
+        eps = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)  # cold
+        for _ in range(max(warmup - 1, 0)):
+            eps = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eps = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+            x = (x - 0.01 * eps) * 1.0001 + 0.01 * torch.randn_like(x)
+        dt = (time.perf_counter() - t0) / steps
+    return dt
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    dt = cpu_step_seconds(args.cpu_batch, args.steps, args.warmup)
+    value = args.cpu_batch / (T_CHAIN * dt)
+    sample = "%d shapes/step x %d warm steps of the same denoise step (oracle C/OpenMP ops + CPU torch MLPs)" % (
+        args.cpu_batch, args.steps)
+    line = {"impl": "reference", "metric": "ddpm_shapes_per_sec_T1000", "value": value, "unit": "shapes/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "the reference has no CPU implementation of these ops "
+                       "(AT_ASSERT CPU not supported); this arm is the oracle port on the host cores"},
+            "cpu_baseline": {"value": value, "unit": "shapes/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    from point_diffusion_refinement_b200 import _lib, util
+    from point_diffusion_refinement_b200 import dist as pdist
+    _lib.lib()  # fail loudly if the CUDA library is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        pdist.init_from_env(backend="nccl")
+    tf32 = not args.no_tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.benchmark = True
+
+    B = args.batch
+    net = make_net(dev)
+    cond_h, label_h, xT_h = [t.pin_memory() for t in make_inputs(B, seed=100 + rank)]
+    cond, label, x = cond_h.to(dev), label_h.to(dev), xT_h.to(dev)
+    dh = util.calc_diffusion_hyperparams(T=T_CHAIN, beta_0=1e-4, beta_T=0.02)
+    rng = util.DeviceNoise(seed=1234 + rank)
+    ts = torch.empty((B,), dtype=torch.float32, device=dev)
+    Alpha = dh["Alpha"].numpy(); Abar = dh["Alpha_bar"].numpy(); Sigma = dh["Sigma"].numpy()
+
+    def one_step(t):
+        nonlocal x
+        ts.fill_(float(t))
+        eps = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+        inv = 1.0 / float(Alpha[t]) ** 0.5
+        c = (1.0 - float(Alpha[t])) / (1.0 - float(Abar[t])) ** 0.5
+        rng.affine_update(x, eps.contiguous(), inv, -c * inv, float(Sigma[t]))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.no_grad():
+        # cold step (encodes the condition cloud), timed on its own
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); one_step(T_CHAIN - 1); e1.record(); torch.cuda.synchronize()
+        cold_ms = e0.elapsed_time(e1)
+        t = T_CHAIN - 2
+        for _ in range(max(args.warmup, 3)):
+            one_step(t); t -= 1
+        # ---- timed region: exactly K warm steps ------------------------------------------------------
+        clocks = ClockSampler(local_rank)
+        sync()
+        clocks.start()
+        launches0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            one_step(t); t -= 1
+        e1.record()
+        sync()
+        clock_info = clocks.stop()
+        launches = _lib.launch_count - launches0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_per_step = ms.item() / args.steps
+
+        # ---- which of our kernels dominates, and its roofline (one extra, untimed, instrumented step) --
+        with KernelAccounting() as acct:
+            one_step(t); t -= 1
+            agg = acct.summary()
+        net.reset_cond_features()
+
+        # ---- e2e through the public API with host buffers ----------------------------------------------
+        e2e = None
+        if not args.no_e2e:
+            Ke = min(args.e2e_steps, T_CHAIN - 1)
+            out_h = torch.empty((B, N_POINTS, 3), dtype=torch.float32).pin_memory()
+
+            def chain():
+                c = cond_h.to(dev, non_blocking=True); l = label_h.to(dev, non_blocking=True)
+                xT = xT_h.to(dev, non_blocking=True)
+                r = util.sampling(net, (B, N_POINTS, 3), dh, label=l, condition=c, verbose=False,
+                                  print_every_n_steps=0, use_a_precomputed_XT=True, step=Ke, XT=xT, seed=rank)
+                out_h.copy_(r, non_blocking=True)
+                return r
+
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                chain()                       # warm-up of the API path
+                sync()
+                t0 = time.perf_counter()
+                e0.record(); r = chain(); e1.record()
+                sync()
+                wall = time.perf_counter() - t0
+            ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+                _ = pdist.all_gather_shapes(r)        # the one collective of the path (final gather)
+            chain_s = ems.item() / 1e3
+            h2d = cond_h.numel() * 4 + label_h.numel() * 8 + xT_h.numel() * 4
+            e2e = {"value": world * B / (chain_s * T_CHAIN / Ke), "unit": "shapes/s",
+                   "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": out_h.numel() * 4 / Ke,
+                   "chain_steps": Ke, "chain_ms": chain_s * 1e3,
+                   "note": "util.sampling(use_a_precomputed_XT, step=%d): %d reverse steps incl. the cold one, "
+                           "pinned-host condition/label/x_T in, generated cloud out; scaled by T/steps" % (Ke, Ke)}
+
+    if rank != 0:
+        return
+    value = world * B / (T_CHAIN * ms_per_step / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    own_ms = sum(d["ms"] for d in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1]["ms"]) if agg else (None, None)
+    roofline = None
+    if top[0]:
+        d = top[1]
+        per_launch_ms = d["ms"] / d["calls"]
+        achieved = (d["bytes"] / d["calls"]) / (per_launch_ms * 1e-3) / 1e9 if d["bytes"] else None
+        roofline = {"kernel": top[0], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json (burst)" if peaks else "fallback 6.65 TB/s",
+                    "launches_per_step": d["calls"], "ms_per_launch": per_launch_ms,
+                    "share_of_step": d["ms"] / ms_per_step,
+                    "own_kernels_share_of_step": own_ms / ms_per_step,
+                    "per_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        dt = cpu_step_seconds(args.cpu_batch, 2, 1)
+        cpu_baseline = {"value": args.cpu_batch / (T_CHAIN * dt), "unit": "shapes/s", "cores": cores, "kind": "port",
+                        "sample": "%d shapes x 2 warm steps of the same denoise step on the host "
+                                  "(oracle C/OpenMP ops + CPU torch MLPs); %.2f s/step" % (args.cpu_batch, dt)}
+    line = {
+        "metric": "ddpm_shapes_per_sec_T1000", "value": value, "unit": "shapes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if tf32 else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "T": T_CHAIN, "step": "one warm reverse step "
+                   "(eps_theta + posterior update, device Philox noise)", "cold_ms": cold_ms,
+                   "l2": "per-step activation working set (>1 GB at B=32) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": "dp%d: shapes sharded by rank, no collective inside the chain, one final all_gather" % world},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info, "e2e": e2e,
+        "gpu_launches": launches,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

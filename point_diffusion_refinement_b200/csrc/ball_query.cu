@@ -101,7 +101,7 @@ extern "C" int pdr_ball_query(int b, int n, int m, float radius, int nsample, co
   const size_t staged_bytes = found_bytes + (size_t)n * 3 * sizeof(float);
   if (staged_bytes <= 200 * 1024) {
     auto kern = ball_query_kernel<true>;
-    if (staged_bytes > 48 * 1024) {
+    if (staged_bytes + 2048 > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) { set_error("ball_query: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
     }

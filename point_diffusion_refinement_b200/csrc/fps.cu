@@ -182,7 +182,7 @@ int launch_onchip(int b, int n, int m, int bs, int log2bs, const float *xyz, int
                   cudaStream_t stream) {
   const size_t smem = (size_t)n * 3 * sizeof(float);
   auto kern = fps_onchip_kernel<PPT, XYZ_REGS>;
-  if (smem > 48 * 1024) {
+  if (smem + 2048 > 48 * 1024) {  // static __shared__ counts against the 48 KiB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("fps: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));

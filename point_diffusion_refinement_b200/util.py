@@ -138,7 +138,7 @@ def sampling(net, size, diffusion_hyperparams, print_every_n_steps=100, label=0,
         for t in range(start_iter, -1, -1):
             if verbose:
                 print("t%d x max %.2f min %.2f" % (t, x.max(), x.min()))
-            if t % print_every_n_steps == 0 and print_every_n_steps > 0:
+            if print_every_n_steps > 0 and t % print_every_n_steps == 0:
                 print("reverse step: %d" % t, flush=True)
             ts.fill_(float(t))
             if condition is None:

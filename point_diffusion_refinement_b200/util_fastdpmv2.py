@@ -88,8 +88,12 @@ def _precompute_VAR_steps(diffusion_hyperparams, user_defined_eta):
     Gamma_bar = _gamma_bar(user_defined_eta)
     T_user = len(Gamma_bar)
     assert Gamma_bar[0] <= Alpha_bar[0] and Gamma_bar[-1] >= Alpha_bar[-1]
-    # python floats: the fp32 schedule endpoints promoted to float64, as 0-d fp32 arrays were by the
-    # value-based casting of the numpy 1.x the reference ran under
+    # The reference passes 0-d fp32 arrays here (Beta[0].cpu().numpy(), :295-297), so its Stirling formula
+    # runs in whatever precision the installed numpy promotes fp32-with-python-float to: a fp32/fp64
+    # mixture under the numpy 1.x it was written for, pure fp32 under numpy >= 2 -- where the result is so
+    # noisy (+-0.9 step, last tau 0.497) that the reference's own `assert abs(tau) < 0.1` (:353) fails.
+    # We evaluate it in float64 on the fp32 schedule endpoints, which reproduces the reference run with
+    # a float64 `Beta` (tests/golden/schedules.pt: "taus_f64") and always satisfies that assert.
     b0, bT = float(Beta[0]), float(Beta[-1])
     ab = Alpha_bar.numpy()
     steps = []

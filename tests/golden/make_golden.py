@@ -113,10 +113,13 @@ def main():
     try:
         for length, schedule in ((50, "quadratic"), (20, "linear")):
             eta = ref_fast.get_VAR_noise(length, configs.DIFFUSION_CONFIG, schedule)
-            taus = ref_fast._precompute_VAR_steps(dh, eta)
+            taus = ref_fast._precompute_VAR_steps(dh, eta)          # as it runs under this numpy (fp32 Stirling)
+            dh64 = dict(dh, Beta=dh["Beta"].double())               # same fp32 endpoints, float64 Stirling
+            taus64 = ref_fast._precompute_VAR_steps(dh64, eta)
             steps = ref_fast.get_STEP_step(length, configs.DIFFUSION_CONFIG, schedule)
             fast["%d_%s" % (length, schedule)] = {"eta": torch.from_numpy(np.asarray(eta)),
-                                                  "taus": torch.tensor(taus, dtype=torch.float64),
+                                                  "taus_as_run_here": torch.tensor(taus, dtype=torch.float64),
+                                                  "taus_f64": torch.tensor(taus64, dtype=torch.float64),
                                                   "steps": steps}
     finally:
         torch.Tensor.cuda = real_cuda

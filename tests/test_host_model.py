@@ -1,0 +1,118 @@
+"""CPU: host-side logic against fixtures produced by the reference's own Python (tests/golden/
+make_golden.py).  The package's native entry points are bound to the CPU oracle for these tests only."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from tests import common as C
+
+
+@pytest.fixture(scope="module")
+def keys(golden_dir):
+    return json.load(open(golden_dir + "/state_dict_keys.json"))
+
+
+def test_state_dict_contract(keys):
+    """Reference checkpoints load key for key (generate_samples.py:178-179)."""
+    from point_diffusion_refinement_b200 import configs
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    net = PointNet2CloudCondition(configs.ddpm_pointnet_config())
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == keys["ddpm"]
+    assert sum(p.numel() for p in net.parameters()) == 9758959 or abs(sum(p.numel() for p in net.parameters()) - 9.759e6) < 2e3
+    net = PointNet2CloudCondition(configs.refine_pointnet_config(8))
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == keys["refine_x8"]
+    assert net.fc_lyaer[-1].out_channels == 27       # 3 * (8 + 1) displacement channels
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_denoiser_matches_reference_python(oracle, golden_dir, tag):
+    from point_diffusion_refinement_b200 import configs
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    gold = torch.load(golden_dir + "/denoiser_%s.pt" % tag)
+    cfg = configs.tiny_pointnet_config() if tag == "tiny" else configs.ddpm_pointnet_config()
+    net = C.fill_parameters_(PointNet2CloudCondition(cfg).eval(), seed=gold["param_seed"])
+    x, cond, ts, label = C.denoiser_inputs(gold["B"], gold["N"], gold["M"], seed=gold["input_seed"])
+    with C.package_bound_to_oracle(), torch.no_grad():
+        cold = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+        assert net.l_uvw is not None and len(net.encoder_cond_features) == 5
+        warm = net(x + 0.05 * cold, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+        net.reset_cond_features()
+        assert net.l_uvw is None
+    # identical ops + identical module arithmetic on the same CPU -> identical bits
+    assert torch.equal(cold, gold["eps_cold"]) and torch.equal(warm, gold["eps_warm"])
+
+
+def test_refiner_and_ssg_match_reference_python(oracle, golden_dir):
+    from point_diffusion_refinement_b200 import configs
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    from point_diffusion_refinement_b200.pointnet2_ssg_sem import PointNet2SemSegSSG
+    gold = torch.load(golden_dir + "/refiner_tiny.pt")
+    cfg = configs.tiny_pointnet_config()
+    cfg.update(include_t=False, point_upsample_factor=2, include_displacement_center_to_final_output=False)
+    net = C.fill_parameters_(PointNet2CloudCondition(cfg).eval(), seed=gold["param_seed"])
+    x, cond, ts, label = C.denoiser_inputs(2, 256, 384, seed=gold["input_seed"])
+    with C.package_bound_to_oracle(), torch.no_grad():
+        disp = net(x, cond, ts=None, label=label)
+    assert disp.shape == (2, 256, 9) and torch.equal(disp, gold["disp"])
+
+    gold = torch.load(golden_dir + "/ssg_tiny.pt")
+    net = PointNet2SemSegSSG(C.ssg_config()).eval()
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == gold["keys"]
+    C.fill_parameters_(net, seed=5)
+    pc = torch.randn(2, 256, 3, generator=torch.Generator().manual_seed(6))
+    with C.package_bound_to_oracle(), torch.no_grad():
+        y = net(pc, ts=torch.tensor([10.0, 500.0]), label=torch.tensor([1, 7]))
+    assert torch.equal(y, gold["out"])          # exercises three_nn + three_interpolate (PointnetFPModule)
+
+
+def test_schedules_match_reference(golden_dir):
+    from point_diffusion_refinement_b200 import configs, util, util_fastdpmv2 as fast
+    gold = torch.load(golden_dir + "/schedules.pt")
+    dh = util.calc_diffusion_hyperparams(**configs.DIFFUSION_CONFIG)
+    for k in ("Beta", "Alpha", "Alpha_bar", "Sigma"):
+        assert torch.equal(dh[k], gold["ddpm"][k]), k
+    for key, g in gold["fast"].items():
+        length, schedule = key.split("_")
+        eta = fast.get_VAR_noise(int(length), configs.DIFFUSION_CONFIG, schedule)
+        np.testing.assert_allclose(eta, g["eta"].numpy(), rtol=1e-12)
+        taus = fast._precompute_VAR_steps(dh, eta)
+        # the reference evaluated with a float64 Beta (see util_fastdpmv2._precompute_VAR_steps for why)
+        np.testing.assert_allclose(taus, g["taus_f64"].numpy(), rtol=0, atol=1e-4)
+        # ... and within the fp32 noise of the reference exactly as it runs under this container's numpy
+        np.testing.assert_allclose(taus, g["taus_as_run_here"].numpy(), atol=1.0)
+        assert fast.get_STEP_step(int(length), configs.DIFFUSION_CONFIG, schedule) == g["steps"]
+        assert all(a > b for a, b in zip(taus[:-1], taus[1:])) and abs(taus[-1]) < 0.1
+
+
+def test_ddim_coefficients_reduce_to_ddpm_limits():
+    from point_diffusion_refinement_b200.util_fastdpmv2 import _ddim_coefficients
+    sx, c, s = _ddim_coefficients(0.5, None, 0.7, last=True)       # last step: x0 = (x - sqrt(1-a) eps)/sqrt(a)
+    assert s == 0.0 and abs(sx - 2 ** 0.5) < 1e-6 and abs(c + (0.5 ** 0.5) * 2 ** 0.5) < 1e-6
+    sx, c, s = _ddim_coefficients(0.5, 0.8, 0.0, last=False)       # kappa = 0: deterministic DDIM
+    assert s == 0.0 and abs(c - ((0.2 ** 0.5) - (0.5 ** 0.5) * (1.6 ** 0.5))) < 1e-6
+
+
+def test_json_reader_and_configs_roundtrip():
+    from point_diffusion_refinement_b200 import configs, json_reader
+    cfg = configs.ddpm_pointnet_config()
+    s = json_reader.replace_list_with_string_in_a_dict(json.loads(json.dumps(cfg)))
+    assert isinstance(s["architecture"]["npoint"], str)
+    assert json_reader.restore_string_to_list_in_a_dict(s) == cfg
+
+
+def test_query_and_group_fill_rule(oracle):
+    """subset=False: a centre with no neighbour becomes its own zero-feature neighbour (pointnet2_utils.py:376-410)."""
+    from point_diffusion_refinement_b200.pointnet2_utils import QueryAndGroup
+    xyz = torch.tensor([[[0.0, 0, 0], [0.05, 0, 0], [5.0, 5, 5]]])
+    centres = torch.tensor([[[0.0, 0, 0], [9.0, 9, 9]]])
+    feats = torch.arange(6, dtype=torch.float32).reshape(1, 2, 3) + 1
+    q = QueryAndGroup(0.1, 4, use_xyz=True, include_abs_coordinate=True, include_center_coordinate=True)
+    with C.package_bound_to_oracle():
+        out, cnt = q(xyz, centres, feats, subset=False, return_counts=True)
+    assert out.shape == (1, 2 + 9, 2, 4) and cnt.tolist() == [[2, 0]]
+    assert out[0, :2, 1].abs().sum() == 0                      # features zeroed
+    assert out[0, 2:5, 1].abs().sum() == 0                     # relative xyz = 0
+    assert torch.equal(out[0, 5:8, 1, 0], centres[0, 1])       # abs xyz = the centre itself
+    assert out[0, 0, 0].tolist() == [1.0, 2.0, 1.0, 1.0]       # hits 0,1 then padded with the first hit
