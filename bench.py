@@ -45,6 +45,9 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=50)
     p.add_argument("--cpu-batch", type=int, default=2, help="shapes per step of the CPU arm (bounded sample)")
     p.add_argument("--no-tf32", action="store_true", help="fp32 SIMT GEMMs instead of TF32 tensor cores")
+    p.add_argument("--engine", default="fused", choices=["fused", "modules"],
+                   help="fused: compiled program of our kernels (fused.py); modules: per-layer torch modules")
+    p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -276,6 +279,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); one_step(T_CHAIN - 1); e1.record(); torch.cuda.synchronize()
         cold_ms = e0.elapsed_time(e1)
+        if args.engine == "fused":
+            net.enable_fused(True, use_tf32=False, use_graph=not args.no_graph)   # TF32 tcgen05 path: see gemm_tc.cu
         t = T_CHAIN - 2
         for _ in range(max(args.warmup, 3)):
             one_step(t); t -= 1
@@ -298,9 +303,15 @@ def main():
         ms_per_step = ms.item() / args.steps
 
         # ---- which of our kernels dominates, and its roofline (one extra, untimed, instrumented step) --
-        with KernelAccounting() as acct:
-            one_step(t); t -= 1
-            agg = acct.summary()
+        eng = getattr(net, "_fused_engine", None)
+        if eng is not None:
+            agg = eng.profile()
+            agg.pop("torch", None)
+            launches = args.steps * (eng.n_kernel_calls + 1)      # program kernels + the fused update, per step
+        else:
+            with KernelAccounting() as acct:
+                one_step(t); t -= 1
+                agg = acct.summary()
         net.reset_cond_features()
 
         # ---- e2e through the public API with host buffers ----------------------------------------------
@@ -354,6 +365,7 @@ def main():
         per_launch_ms = d["ms"] / d["calls"]
         achieved = (d["bytes"] / d["calls"]) / (per_launch_ms * 1e-3) / 1e9 if d["bytes"] else None
         roofline = {"kernel": top[0], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "tflops": (d.get("flops", 0) / (d["ms"] * 1e-3) / 1e12) if d.get("flops") else None,
                     "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json (burst)" if peaks else "fallback 6.65 TB/s",
                     "launches_per_step": d["calls"], "ms_per_launch": per_launch_ms,
@@ -371,8 +383,10 @@ def main():
     line = {
         "metric": "ddpm_shapes_per_sec_T1000", "value": value, "unit": "shapes/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if tf32 else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "T": T_CHAIN, "step": "one warm reverse step "
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.engine == "fused" else ("tf32" if tf32 else "f32"), "data": "synthetic",
+        "config": {"workload": WORKLOAD, "engine": args.engine, "cuda_graph": (args.engine == "fused" and not args.no_graph),
+                   "batch_per_gpu": B, "T": T_CHAIN, "step": "one warm reverse step "
                    "(eps_theta + posterior update, device Philox noise)", "cold_ms": cold_ms,
                    "l2": "per-step activation working set (>1 GB at B=32) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": "dp%d: shapes sharded by rank, no collective inside the chain, one final all_gather" % world},

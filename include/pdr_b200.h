@@ -139,6 +139,93 @@ int pdr_affine_noise_update(size_t count, float *x, const float *eps, float scal
 /* fill with N(0,1) (x_T), same generator. */
 int pdr_normal_fill(size_t count, float *x, uint64_t seed, uint64_t offset, void *stream);
 
+/* ================================================================================================
+ * Fused denoiser primitives (channels-LAST activations: a tensor (B, P, K, C) is the row-major matrix
+ * [B*P*K, ld] with ld >= C, ld % 4 == 0 and pad columns holding zeros).
+ * They replace, for the warm eps_theta step, the per-layer cuDNN/ATen launches of
+ *   Mlp_plus_t_emb / build_shared_mlp / MyGroupNorm   pointnet2_ops/pointnet2_modules.py:23-174
+ *   AttentionModule                                    pointnet2_ops/attention.py:35-96
+ *   QueryAndGroup / group_knn                          pointnet2_ops/pointnet2_utils.py:307-438,487-514
+ * ============================================================================================== */
+
+/* prologue applied to A while it is loaded (x = A[row, c], b = sample of the row):
+ *   PDR_PRO_NONE     x
+ *   PDR_PRO_GN_RELU  relu(x*sc[b,c] + sh[b,c])      (conv -> GroupNorm -> ReLU stacks)
+ *   PDR_PRO_RELU_GN  relu(x)*sc[b,c] + sh[b,c]      (AttentionModule.weight_conv: ReLU -> GroupNorm -> conv)
+ * then  + add[b,c] (per-sample embedding, may be NULL)  + R[row,c] (residual, may be NULL). */
+#define PDR_PRO_NONE 0
+#define PDR_PRO_GN_RELU 1
+#define PDR_PRO_RELU_GN 2
+
+typedef struct PdrGemmArgs {
+  /* C[M, N] = pro(A)[M, K] * W[N, K]^T + bias[N] + rowadd[(row / rowadd_div), N] */
+  const float *A; int lda; int K;        /* K and lda multiples of 4 */
+  const float *W; int ldw;               /* (N, ldw) row-major = Conv2d weight (Cout, Cin) zero-padded */
+  const float *bias;                     /* (N) or NULL */
+  float *C; int ldc; int N;              /* columns [N, ldc_zero_to) are written as zeros */
+  int ldc_zero_to;
+  int batch; int rows_per_sample;        /* M = batch * rows_per_sample; tiles never straddle samples */
+  int pro_mode;
+  const float *sc; const float *sh; int ld_scsh;   /* (batch, ld_scsh), ld_scsh % 4 == 0 */
+  const float *add; int ld_add;          /* (batch, ld_add) or NULL */
+  const float *R; int ldr;               /* (M, ldr) or NULL */
+  const float *rowadd; int ld_rowadd; int rowadd_div;   /* or NULL */
+  /* per-tile column statistics for the GroupNorm that follows: (batch*tiles_per_sample, N, 4) =
+   * sum y, sum y^2, sum relu(y), sum relu(y)^2 over the tile's valid rows; NULL = not needed */
+  float *stats;
+  int use_tf32;                          /* 0: fp32 SIMT FMA; 1: tensor cores (TF32 inputs, fp32 accumulate) */
+} PdrGemmArgs;
+int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
+int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);
+
+/* GroupNorm statistics -> per-sample per-channel affine (sc, sh), for a channel concatenation of up to
+ * two sources (e.g. [query conv | key conv] in AttentionModule).  Channels >= gn_channels pass through
+ * (sc = 1, sh = 0; MyGroupNorm, attention.py:6-23); pad columns of sc/sh are never written (keep them 0). */
+typedef struct PdrGnSource {
+  const float *stats; int tiles_per_sample; int ld_stats;  /* (batch*tiles, ld_stats, 4) from pdr_gemm_fused */
+  int col0; int ncols;                                     /* columns of that GEMM output used here */
+  int out_col0;                                            /* where these channels start in sc/sh (each source
+                                                              may be padded to a multiple of 4 columns) */
+  int use_relu;                                            /* take the statistics of relu(y) instead of y */
+  int rows; float mult;                                    /* rows the stats cover per sample; multiplicity of
+                                                              each row in the normalised tensor (K for the query
+                                                              of AttentionModule, which is expanded over K) */
+} PdrGnSource;
+typedef struct PdrGnArgs {
+  PdrGnSource src[2]; int nsrc;
+  int batch; int channels; int gn_channels; int groups;
+  const float *gamma; const float *beta; float eps;        /* (gn_channels) */
+  float *sc; float *sh; int ld_out;                        /* (batch, ld_out) */
+} PdrGnArgs;
+int pdr_gn_finalize(const PdrGnArgs *args, void *stream);
+
+/* out[row, c] = pro(x[row, c]) (+add +R) materialised; same prologue semantics as the GEMM. */
+int pdr_affine_rows(int batch, int rows_per_sample, int C, const float *x, int ldx, int pro_mode,
+                    const float *sc, const float *sh, int ld_scsh, const float *add, int ld_add, const float *R,
+                    int ldr, float *out, int ldo, void *stream);
+
+/* Soft-attention pooling over the K neighbours (attention.py:85-96):
+ * out[b,p,c] = sum_k softmax_k(S[b,p,k,c] masked to k < max(count[b,p],1)) * relu(V[b,p,k,c]*sc[b,c]+sh[b,c]).
+ * counts == NULL means 'all'.  S, V: (B*P*K, ld); out: (B*P, ldo) written at column offset 0 of `out`. */
+int pdr_attention_pool(int batch, int P, int K, int C, const float *S, int lds, const float *V, int ldv,
+                       const float *sc, const float *sh, int ld_scsh, const int *counts, float *out, int ldo,
+                       void *stream);
+
+/* Ball-query grouping into channels-last rows [feat(C) | rel(3) | abs(3) | centre(3) | 0-pad] with the
+ * subset=False fill rule (pointnet2_utils.py:376-410): counts == 0 -> feat = 0, abs = centre, rel = 0.
+ * feat (B, n, ldf), xyz (B, n, 3), centres (B, P, 3), idx (B, P, K) int32, counts (B, P) or NULL. */
+int pdr_group_ball(int batch, int n, int P, int K, int C, const float *feat, int ldf, const float *xyz,
+                   const float *centres, const int *idx, const int *counts, int fill_missing, float *out,
+                   int ldo, void *stream);
+/* kNN grouping rows [feat(C) | d2 | w | nn_abs(3) | nn_rel(3) | x(3) | 0-pad], w = normalised 1/(d2+1e-8)
+ * (pointnet2_utils.py:487-514).  idx (B, P, K) int64 and dists (B, P, K) from pdr_knn_points. */
+int pdr_group_knn(int batch, int n, int P, int K, int C, const float *feat, int ldf, const float *y,
+                  const float *x, const int64_t *idx, const float *dists, float *out, int ldo, void *stream);
+/* out[b, j, 0:C] = src[b, idx[b,j], 0:C] (rows); idx == NULL copies row j.  Used for FPS centre features and
+ * for placing a feature block into a column slice of a wider buffer (free concatenation). */
+int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, const int *idx, float *out,
+                    int ldo, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

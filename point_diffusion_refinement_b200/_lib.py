@@ -47,6 +47,18 @@ SIGNATURES = {
     "pdr_affine_noise_update": [_c_size_t, _ptr, _ptr, _c_float, _c_float, _c_float, _ptr, _c_u64, _c_u64,
                                 _ptr],
     "pdr_normal_fill": [_c_size_t, _ptr, _c_u64, _c_u64, _ptr],
+    # fused denoiser primitives (struct arguments are passed by address)
+    "pdr_gemm_tile_rows": [],
+    "pdr_gemm_fused": [_ptr, _ptr],
+    "pdr_gn_finalize": [_ptr, _ptr],
+    "pdr_affine_rows": [_c_int, _c_int, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _c_int, _ptr, _c_int, _ptr, _c_int,
+                        _ptr, _c_int, _ptr],
+    "pdr_attention_pool": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _ptr,
+                           _c_int, _ptr],
+    "pdr_group_ball": [_c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr,
+                       _c_int, _ptr],
+    "pdr_group_knn": [_c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
+    "pdr_gather_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr],
 }
 _RESTYPES = {
     "pdr_last_error_string": ctypes.c_char_p,

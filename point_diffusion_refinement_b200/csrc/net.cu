@@ -1,0 +1,461 @@
+// Fused denoiser primitives for sm_100a (channels-last activations).
+//
+// The reference evaluates one warm eps_theta step as ~1000 ATen/cuDNN launches: every 1x1 Conv2d, every
+// GroupNorm, ReLU, cat, expand, softmax materialises a (B, C, npoint, nsample) tensor
+// (pointnet2_ops/pointnet2_modules.py:69-174, attention.py:70-96).  Here the step is a short chain of
+//   gather -> [GEMM with GroupNorm/ReLU/embedding/residual folded into the A-operand load and the
+//              statistics of the NEXT GroupNorm folded into the epilogue] -> attention pooling
+// so that every activation is written once (raw conv output) and read once.
+//
+// This file: the fp32 SIMT GEMM (validation mode and small-problem path), GroupNorm finalisation,
+// attention pooling, grouping/gather kernels.  The tcgen05 (TF32) GEMM lives in gemm_tc.cu.
+#include "common.cuh"
+
+namespace pdr {
+
+int launch_gemm_tf32(const PdrGemmArgs &a, cudaStream_t stream);  // gemm_tc.cu
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// SIMT GEMM: C[128 x (16*TN)] per CTA, 256 threads, 8 x TN outputs per thread, K stepped by 16.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileM = 128;
+constexpr int kTileK = 16;
+constexpr int kGemmThreads = 256;
+
+__device__ __forceinline__ float pro_apply(int mode, float x, float sc, float sh) {
+  if (mode == PDR_PRO_GN_RELU) return fmaxf(fmaf(x, sc, sh), 0.f);
+  if (mode == PDR_PRO_RELU_GN) return fmaf(fmaxf(x, 0.f), sc, sh);
+  return x;
+}
+
+template <int TN>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_simt_kernel(const PdrGemmArgs a) {
+  constexpr int kTileN = 16 * TN;
+  __shared__ __align__(16) float As[kTileK][kTileM + 4];
+  __shared__ __align__(16) float Bs[kTileK][kTileN + 4];
+  __shared__ float s_red[kGemmThreads / 32][kTileN][4];
+
+  const int tid = threadIdx.x;
+  const int tiles_per_sample = (a.rows_per_sample + kTileM - 1) / kTileM;
+  const int tile = blockIdx.y;
+  const int b = tile / tiles_per_sample;
+  const int r0 = (tile % tiles_per_sample) * kTileM;            // first row of the tile inside the sample
+  const size_t row_base = (size_t)b * a.rows_per_sample + r0;   // global row of tile row 0
+  const int rows_valid = min(kTileM, a.rows_per_sample - r0);
+  const int n0 = blockIdx.x * kTileN;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // global -> register staging (2 float4 of A, kTileN*16/4/256 float4 of W per thread)
+  float4 ra[2];
+  float4 rw[(kTileN * kTileK / 4 + kGemmThreads - 1) / kGemmThreads];
+  constexpr int kWLoads = (kTileN * kTileK / 4 + kGemmThreads - 1) / kGemmThreads;
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * kGemmThreads;
+      const int row = f >> 2, kq = (f & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = k0 + kq;
+      if (row < rows_valid && k < a.K) {
+        const size_t grow = row_base + row;
+        v = *reinterpret_cast<const float4 *>(a.A + grow * a.lda + k);
+        if (a.pro_mode != PDR_PRO_NONE) {
+          const float4 s = *reinterpret_cast<const float4 *>(a.sc + (size_t)b * a.ld_scsh + k);
+          const float4 h = *reinterpret_cast<const float4 *>(a.sh + (size_t)b * a.ld_scsh + k);
+          v.x = pro_apply(a.pro_mode, v.x, s.x, h.x); v.y = pro_apply(a.pro_mode, v.y, s.y, h.y);
+          v.z = pro_apply(a.pro_mode, v.z, s.z, h.z); v.w = pro_apply(a.pro_mode, v.w, s.w, h.w);
+        }
+        if (a.add) {
+          const float4 e = *reinterpret_cast<const float4 *>(a.add + (size_t)b * a.ld_add + k);
+          v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+        }
+        if (a.R) {
+          const float4 r = *reinterpret_cast<const float4 *>(a.R + grow * a.ldr + k);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+      }
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < kWLoads; ++i) {
+      const int f = tid + i * kGemmThreads;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < kTileN * kTileK / 4) {
+        const int n = f >> 2, kq = (f & 3) * 4;
+        if (n0 + n < a.N && k0 + kq < a.K) v = *reinterpret_cast<const float4 *>(a.W + (size_t)(n0 + n) * a.ldw + k0 + kq);
+      }
+      rw[i] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * kGemmThreads;
+      const int row = f >> 2, kq = (f & 3) * 4;
+      As[kq + 0][row] = ra[i].x; As[kq + 1][row] = ra[i].y; As[kq + 2][row] = ra[i].z; As[kq + 3][row] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < kWLoads; ++i) {
+      const int f = tid + i * kGemmThreads;
+      if (f < kTileN * kTileK / 4) {
+        const int n = f >> 2, kq = (f & 3) * 4;
+        Bs[kq + 0][n] = rw[i].x; Bs[kq + 1][n] = rw[i].y; Bs[kq + 2][n] = rw[i].z; Bs[kq + 3][n] = rw[i].w;
+      }
+    }
+  };
+
+  load_tiles(0);
+  for (int k0 = 0; k0 < a.K; k0 += kTileK) {
+    __syncthreads();
+    store_tiles();
+    __syncthreads();
+    if (k0 + kTileK < a.K) load_tiles(k0 + kTileK);
+#pragma unroll
+    for (int kk = 0; kk < kTileK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+
+  // ---- epilogue: bias, broadcast row-add, store, per-column statistics ------------------------------
+  float st[TN][4];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = ty * 8 + i;
+    if (row >= rows_valid) continue;
+    const size_t grow = row_base + row;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < a.N) {
+        float y = acc[i][j];
+        if (a.bias) y += __ldg(a.bias + n);
+        if (a.rowadd) y += __ldg(a.rowadd + (grow / a.rowadd_div) * a.ld_rowadd + n);
+        a.C[grow * a.ldc + n] = y;
+        const float r = fmaxf(y, 0.f);
+        st[j][0] += y; st[j][1] = fmaf(y, y, st[j][1]); st[j][2] += r; st[j][3] = fmaf(r, r, st[j][3]);
+      } else if (n < a.ldc_zero_to) {
+        a.C[grow * a.ldc + n] = 0.f;
+      }
+    }
+  }
+  if (a.stats) {
+    // threads with equal tx hold the same columns: lanes l and l^16 inside a warp, then 8 warps
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st[j][q] += __shfl_xor_sync(0xffffffffu, st[j][q], 16);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane < 16) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s_red[warp][lane * TN + j][q] = st[j][q];
+    }
+    __syncthreads();
+    for (int f = tid; f < kTileN * 4; f += kGemmThreads) {
+      const int col = f >> 2, q = f & 3;
+      if (n0 + col < a.N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kGemmThreads / 32; ++w) s += s_red[w][col][q];
+        a.stats[((size_t)tile * a.N + n0 + col) * 4 + q] = s;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm finalisation: one CTA per sample.  Partial sums are added in tile order (deterministic),
+// in double, and the variance is E[x^2] - mean^2 (biased, like nn.GroupNorm).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const PdrGnArgs a) {
+  extern __shared__ double s_tot[];  // [channels][3] = weighted sum, weighted sum of squares, element count
+  const int b = blockIdx.x;
+  int c_off = 0;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const PdrGnSource src = a.src[s];
+    for (int c = threadIdx.x; c < src.ncols; c += blockDim.x) {
+      double sum = 0.0, sq = 0.0;
+      const float *p = src.stats + ((size_t)b * src.tiles_per_sample * src.ld_stats + src.col0 + c) * 4 +
+                       (src.use_relu ? 2 : 0);
+      for (int t = 0; t < src.tiles_per_sample; ++t, p += (size_t)src.ld_stats * 4) {
+        sum += (double)p[0];
+        sq += (double)p[1];
+      }
+      s_tot[(c_off + c) * 3 + 0] = (double)src.mult * sum;
+      s_tot[(c_off + c) * 3 + 1] = (double)src.mult * sq;
+      s_tot[(c_off + c) * 3 + 2] = (double)src.mult * (double)src.rows;
+    }
+    c_off += src.ncols;
+  }
+  __syncthreads();
+  const int cpg = a.groups > 0 ? a.gn_channels / a.groups : 1;
+  for (int c = threadIdx.x; c < a.channels; c += blockDim.x) {
+    float sc = 1.f, sh = 0.f;  // MyGroupNorm passes the trailing C % G channels through (attention.py:17-23)
+    if (c < a.gn_channels) {
+      const int g = c / cpg;
+      double sum = 0.0, sq = 0.0, n = 0.0;
+      for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+        sum += s_tot[cc * 3 + 0]; sq += s_tot[cc * 3 + 1]; n += s_tot[cc * 3 + 2];
+      }
+      const double mean = sum / n;
+      double var = sq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double rstd = 1.0 / sqrt(var + (double)a.eps);
+      const double gsc = (double)__ldg(a.gamma + c) * rstd;
+      sc = (float)gsc;
+      sh = (float)((double)__ldg(a.beta + c) - mean * gsc);
+    }
+    int s = 0, off = 0;
+    while (s + 1 < a.nsrc && c >= off + a.src[s].ncols) { off += a.src[s].ncols; ++s; }
+    const int o = a.src[s].out_col0 + (c - off);
+    a.sc[(size_t)b * a.ld_out + o] = sc;
+    a.sh[(size_t)b * a.ld_out + o] = sh;
+  }
+}
+
+// out[row, c] = pro(x)(+add)(+R) for c < C.  `out` may be a column slice of a wider matrix, so nothing
+// outside [0, C) is touched (pad columns stay zero from allocation).
+__global__ void __launch_bounds__(256)
+affine_rows_kernel(int rows_per_sample, int C, const float *__restrict__ x, int ldx, int mode,
+                   const float *__restrict__ sc, const float *__restrict__ sh, int ld_scsh,
+                   const float *__restrict__ add, int ld_add, const float *__restrict__ R, int ldr,
+                   float *__restrict__ out, int ldo, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long row = i / C;
+  const int b = (int)(row / rows_per_sample);
+  float v = x[row * ldx + c];
+  if (mode != PDR_PRO_NONE) v = pro_apply(mode, v, __ldg(sc + (size_t)b * ld_scsh + c), __ldg(sh + (size_t)b * ld_scsh + c));
+  if (add) v += __ldg(add + (size_t)b * ld_add + c);
+  if (R) v += R[row * ldr + c];
+  out[row * ldo + c] = v;
+}
+
+// Attention pooling: one thread per (b, p, c); the K scores/values of a (p, c) are strided by ld.
+__global__ void __launch_bounds__(256)
+attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds, const float *__restrict__ V,
+                      int ldv, const float *__restrict__ sc, const float *__restrict__ sh, int ld_scsh,
+                      const int *__restrict__ counts, float *__restrict__ out, int ldo, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long bp = i / C;           // b*P + p
+  const int b = (int)(bp / P);
+  int cnt = K;
+  if (counts) { cnt = __ldg(counts + bp); cnt = cnt < 1 ? 1 : cnt; }
+  const float gs = __ldg(sc + (size_t)b * ld_scsh + c), gh = __ldg(sh + (size_t)b * ld_scsh + c);
+  const float *s = S + (size_t)bp * K * lds + c;
+  const float *v = V + (size_t)bp * K * ldv + c;
+  float mx = -3.0e38f;
+  for (int k = 0; k < K; ++k) {
+    const float sv = k < cnt ? s[(size_t)k * lds] : -1e9f;  // scores*mask + (-1e9)*(1-mask), attention.py:88
+    mx = fmaxf(mx, sv);
+  }
+  float den = 0.f, num = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float sv = k < cnt ? s[(size_t)k * lds] : -1e9f;
+    const float e = expf(sv - mx);
+    den += e;
+    num = fmaf(e, fmaxf(fmaf(v[(size_t)k * ldv], gs, gh), 0.f), num);
+  }
+  out[bp * ldo + c] = num / den;
+}
+
+// Ball-query grouping, one thread per (row, output column).
+__global__ void __launch_bounds__(256)
+group_ball_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int ldf,
+                  const float *__restrict__ xyz, const float *__restrict__ centres, const int *__restrict__ idx,
+                  const int *__restrict__ counts, int fill_missing, float *__restrict__ out, int ldo,
+                  long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % ldo);
+  const long long row = i / ldo;             // (b*P + p)*K + k
+  const long long bp = row / K;
+  const int b = (int)(bp / P);
+  const int src = __ldg(idx + row);
+  const bool missing = fill_missing && counts && __ldg(counts + bp) == 0;
+  float v = 0.f;
+  if (c < C) {
+    v = missing ? 0.f : __ldg(feat + ((size_t)b * n + src) * ldf + c);
+  } else if (c < C + 9) {
+    const int q = c - C, d = q % 3;
+    const float cen = __ldg(centres + bp * 3 + d);
+    const float ab = missing ? cen : __ldg(xyz + ((size_t)b * n + src) * 3 + d);
+    v = q < 3 ? ab - cen : (q < 6 ? ab : cen);
+  }
+  out[row * ldo + c] = v;
+}
+
+// kNN grouping rows: [feat | d2 | w | nn_abs | nn_rel | x].
+__global__ void __launch_bounds__(256)
+group_knn_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int ldf, const float *__restrict__ y,
+                 const float *__restrict__ x, const int64_t *__restrict__ idx, const float *__restrict__ dists,
+                 float *__restrict__ out, int ldo, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % ldo);
+  const long long row = i / ldo;
+  const long long bp = row / K;
+  const int b = (int)(bp / P);
+  const int src = (int)__ldg(idx + row);
+  float v = 0.f;
+  if (c < C) {
+    v = __ldg(feat + ((size_t)b * n + src) * ldf + c);
+  } else if (c == C) {
+    v = __ldg(dists + row);
+  } else if (c == C + 1) {
+    // weight = (1/(d+1e-8)) / sum_k (1/(d_k+1e-8)), summed in neighbour order like torch.sum(dim=2)
+    float norm = 0.f;
+    for (int k = 0; k < K; ++k) norm += 1.0f / (__ldg(dists + bp * K + k) + 1e-8f);
+    v = (1.0f / (__ldg(dists + row) + 1e-8f)) / norm;
+  } else if (c < C + 11) {
+    const int q = c - C - 2, d = q % 3;
+    const float xv = __ldg(x + bp * 3 + d);
+    const float yv = __ldg(y + ((size_t)b * n + src) * 3 + d);
+    v = q < 3 ? yv : (q < 6 ? yv - xv : xv);
+  }
+  out[row * ldo + c] = v;
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel2(int n, int P, int C, const float *__restrict__ src, int lds, const int *__restrict__ idx,
+                    float *__restrict__ out, int ldo, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long bp = i / C;
+  const int b = (int)(bp / P);
+  const int j = idx ? __ldg(idx + bp) : (int)(bp % P);
+  out[bp * ldo + c] = __ldg(src + ((size_t)b * n + j) * lds + c);
+}
+
+inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
+
+}  // namespace
+}  // namespace pdr
+
+using namespace pdr;
+
+extern "C" int pdr_gemm_tile_rows(void) { return kTileM; }
+
+extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
+  PDR_REQUIRE(args, "gemm_fused: null args");
+  const PdrGemmArgs &a = *args;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PDR_REQUIRE(a.A && a.W && a.C, "gemm_fused: null pointer");
+  PDR_REQUIRE(a.K > 0 && a.N > 0 && a.batch > 0 && a.rows_per_sample > 0, "gemm_fused: bad sizes");
+  PDR_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && a.lda >= a.K && a.ldw >= a.K,
+              "gemm_fused: K/lda/ldw must be multiples of 4 (K=%d lda=%d ldw=%d)", a.K, a.lda, a.ldw);
+  PDR_REQUIRE(a.ldc >= a.N && a.ldc_zero_to <= a.ldc, "gemm_fused: ldc=%d < N=%d", a.ldc, a.N);
+  PDR_REQUIRE(a.pro_mode == PDR_PRO_NONE || (a.sc && a.sh && a.ld_scsh % 4 == 0 && ((uintptr_t)a.sc % 16) == 0 &&
+                                             ((uintptr_t)a.sh % 16) == 0),
+              "gemm_fused: prologue needs 16-byte aligned sc/sh with ld %% 4 == 0");
+  PDR_REQUIRE(!a.add || (a.ld_add % 4 == 0 && ((uintptr_t)a.add % 16) == 0), "gemm_fused: add alignment");
+  PDR_REQUIRE(!a.R || a.ldr % 4 == 0, "gemm_fused: ldr must be a multiple of 4");
+  PDR_REQUIRE(!a.rowadd || a.rowadd_div > 0, "gemm_fused: rowadd_div");
+  PDR_REQUIRE(((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.W % 16) == 0 && (!a.R || ((uintptr_t)a.R % 16) == 0),
+              "gemm_fused: A/W/R must be 16-byte aligned");
+  if (a.use_tf32) return launch_gemm_tf32(a, stream);
+  const int tiles_per_sample = ceil_div(a.rows_per_sample, kTileM);
+  const long long tiles = (long long)a.batch * tiles_per_sample;
+  PDR_REQUIRE(tiles <= 65535ll * 32768, "gemm_fused: too many tiles");
+  if (a.N <= 32) {
+    dim3 grid(ceil_div(a.N, 32), (unsigned)tiles);
+    gemm_simt_kernel<2><<<grid, kGemmThreads, 0, stream>>>(a);
+  } else {
+    dim3 grid(ceil_div(a.N, 64), (unsigned)tiles);
+    gemm_simt_kernel<4><<<grid, kGemmThreads, 0, stream>>>(a);
+  }
+  return check_launch("gemm_simt_kernel");
+}
+
+extern "C" int pdr_gn_finalize(const PdrGnArgs *args, void *stream) {
+  PDR_REQUIRE(args, "gn_finalize: null args");
+  const PdrGnArgs &a = *args;
+  PDR_REQUIRE(a.nsrc >= 1 && a.nsrc <= 2 && a.batch > 0 && a.channels > 0, "gn_finalize: bad sizes");
+  PDR_REQUIRE(a.gn_channels <= a.channels && a.groups > 0 && a.gn_channels % a.groups == 0,
+              "gn_finalize: channels=%d gn=%d groups=%d ld=%d", a.channels, a.gn_channels, a.groups, a.ld_out);
+  int tot = 0;
+  for (int s = 0; s < a.nsrc; ++s) tot += a.src[s].ncols;
+  PDR_REQUIRE(tot == a.channels, "gn_finalize: sources cover %d of %d channels", tot, a.channels);
+  PDR_REQUIRE(a.gamma && a.beta && a.sc && a.sh, "gn_finalize: null pointer");
+  const size_t smem = (size_t)a.channels * 3 * sizeof(double);
+  PDR_REQUIRE(smem <= 48 * 1024, "gn_finalize: too many channels");
+  gn_finalize_kernel<<<a.batch, 256, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("gn_finalize_kernel");
+}
+
+extern "C" int pdr_affine_rows(int batch, int rows_per_sample, int C, const float *x, int ldx, int pro_mode,
+                               const float *sc, const float *sh, int ld_scsh, const float *add, int ld_add,
+                               const float *R, int ldr, float *out, int ldo, void *stream) {
+  PDR_REQUIRE(batch > 0 && rows_per_sample > 0 && C > 0 && ldo >= C && x && out, "affine_rows: bad arguments");
+  const long long total = (long long)batch * rows_per_sample * C;
+  affine_rows_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(rows_per_sample, C, x, ldx, pro_mode, sc, sh,
+                                                                          ld_scsh, add, ld_add, R, ldr, out, ldo, total);
+  return check_launch("affine_rows_kernel");
+}
+
+extern "C" int pdr_attention_pool(int batch, int P, int K, int C, const float *S, int lds, const float *V, int ldv,
+                                  const float *sc, const float *sh, int ld_scsh, const int *counts, float *out,
+                                  int ldo, void *stream) {
+  PDR_REQUIRE(batch > 0 && P > 0 && K > 0 && C > 0 && S && V && sc && sh && out, "attention_pool: bad arguments");
+  const long long total = (long long)batch * P * C;
+  attention_pool_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh, ld_scsh,
+                                                                             counts, out, ldo, total);
+  return check_launch("attention_pool_kernel");
+}
+
+extern "C" int pdr_group_ball(int batch, int n, int P, int K, int C, const float *feat, int ldf, const float *xyz,
+                              const float *centres, const int *idx, const int *counts, int fill_missing,
+                              float *out, int ldo, void *stream) {
+  PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && C >= 0 && ldo >= C + 9, "group_ball: bad sizes");
+  PDR_REQUIRE((feat || C == 0) && xyz && centres && idx && out, "group_ball: null pointer");
+  const long long total = (long long)batch * P * K * ldo;
+  group_ball_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, K, C, feat, ldf, xyz, centres, idx,
+                                                                         counts, fill_missing, out, ldo, total);
+  return check_launch("group_ball_kernel");
+}
+
+extern "C" int pdr_group_knn(int batch, int n, int P, int K, int C, const float *feat, int ldf, const float *y,
+                             const float *x, const int64_t *idx, const float *dists, float *out, int ldo,
+                             void *stream) {
+  PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && C >= 0 && ldo >= C + 11, "group_knn: bad sizes");
+  PDR_REQUIRE((feat || C == 0) && y && x && idx && dists && out, "group_knn: null pointer");
+  const long long total = (long long)batch * P * K * ldo;
+  group_knn_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, K, C, feat, ldf, y, x, idx, dists, out,
+                                                                        ldo, total);
+  return check_launch("group_knn_kernel");
+}
+
+extern "C" int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, const int *idx, float *out,
+                               int ldo, void *stream) {
+  PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && C > 0 && src && out, "gather_rows: bad arguments");
+  const long long total = (long long)batch * P * C;
+  gather_rows_kernel2<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, C, src, lds, idx, out, ldo, total);
+  return check_launch("gather_rows_kernel");
+}

@@ -148,6 +148,28 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
         head_in = dec[0] + 3 + (dec_map_dim[0] if self.include_local_feature else 0)
         self.fc_lyaer = self._build_head(head_in, copy.deepcopy(self.network_activation_function), bn=self.bn)
 
+    # -- fused warm path --------------------------------------------------------------------------------
+    def enable_fused(self, enabled=True, use_tf32=False, use_graph=True):
+        """Route warm calls (``use_retained_condition_feature=True`` with a retained state) through the
+        compiled sm_100a program of :mod:`fused` instead of the per-layer module path.  The first (cold) call
+        of a chain still runs the modules: it encodes the condition cloud once."""
+        self._fused_cfg = dict(use_tf32=use_tf32, use_graph=use_graph) if enabled else None
+        self._fused_engine = None
+        return self
+
+    def _fused_step(self, pointcloud, ts):
+        from .fused import FusedDenoiser
+        B, N, _ = pointcloud.shape
+        eng = getattr(self, "_fused_engine", None)
+        if eng is None or (eng.B, eng.N) != (B, N):
+            eng = FusedDenoiser(self, B, N, **self._fused_cfg)
+            self._fused_engine = eng
+            self._fused_bound = None
+        if self._fused_bound is not self._cond_state:
+            eng.set_condition(self._cond_state, self._cond_label)
+            self._fused_bound = self._cond_state
+        return eng.step(pointcloud, ts)
+
     # -- retained condition state -------------------------------------------------------------------
     def reset_cond_features(self):
         self._cond_state = None
@@ -199,6 +221,9 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
         """pointcloud (B,N,3), condition (B,M,3+C), ts (B,), label (B,) long -> (B,N,out_dim)."""
         if self.include_global_feature or self.include_local_feature:
             assert condition is not None
+        if (use_retained_condition_feature and self._cond_state is not None
+                and getattr(self, "_fused_cfg", None) is not None and pointcloud.is_cuda and not torch.is_grad_enabled()):
+            return self._fused_step(pointcloud, ts).clone()
         with torch.no_grad():
             if self.attach_position_to_input_feature:
                 pointcloud = torch.cat([pointcloud, pointcloud[:, :, 0:3] / self.scale_factor], dim=2)
@@ -216,6 +241,7 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
             if use_retained_condition_feature:
                 cs.global_feature = None if cs.global_feature is None else cs.global_feature.detach().clone()
                 self._cond_state = cs
+                self._cond_label = label
 
         if self.include_global_feature:
             condition_emb = cs.global_feature

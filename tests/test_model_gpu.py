@@ -142,3 +142,36 @@ def test_refiner_and_ssg_fixture(golden_dir):
             torch.testing.assert_close(y.cpu(), gold["out"], rtol=1e-4, atol=1e-4)
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_engine_matches_modules_and_fixture(golden_dir, tag, use_graph):
+    """The compiled warm step (fused.py: our GEMM/GroupNorm/attention kernels) against the per-layer module
+    path and against the reference-Python fixture, fp32 (SIMT) arithmetic."""
+    from point_diffusion_refinement_b200 import configs
+    gold = torch.load(golden_dir + "/denoiser_%s.pt" % tag)
+    cfg = configs.tiny_pointnet_config() if tag == "tiny" else configs.ddpm_pointnet_config()
+    net = _net(cfg, gold["param_seed"])
+    x, cond, ts, label = [t.to(DEV) for t in C.denoiser_inputs(gold["B"], gold["N"], gold["M"], seed=gold["input_seed"])]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)          # cold (modules)
+            x2 = x + 0.05 * gold["eps_cold"].to(DEV)
+            warm_mod = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+            net.enable_fused(True, use_tf32=False, use_graph=use_graph)
+            warm_fused = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+            again = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+            other = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)  # replay with new inputs
+            net.enable_fused(False)
+            other_mod = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+            net.reset_cond_features()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert torch.equal(warm_fused, again)                       # deterministic (no float atomics)
+    torch.testing.assert_close(warm_fused, warm_mod, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(other, other_mod, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(warm_fused.cpu(), gold["eps_warm"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(other.cpu(), gold["eps_cold"], rtol=1e-4, atol=1e-4)
