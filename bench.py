@@ -280,7 +280,7 @@ def main():
         e0.record(); one_step(T_CHAIN - 1); e1.record(); torch.cuda.synchronize()
         cold_ms = e0.elapsed_time(e1)
         if args.engine == "fused":
-            net.enable_fused(True, use_tf32=False, use_graph=not args.no_graph)   # TF32 tcgen05 path: see gemm_tc.cu
+            net.enable_fused(True, use_tf32=tf32, use_graph=not args.no_graph)    # tcgen05 TF32 GEMMs (gemm_tc.cu)
         t = T_CHAIN - 2
         for _ in range(max(args.warmup, 3)):
             one_step(t); t -= 1
@@ -384,7 +384,7 @@ def main():
         "metric": "ddpm_shapes_per_sec_T1000", "value": value, "unit": "shapes/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.engine == "fused" else ("tf32" if tf32 else "f32"), "data": "synthetic",
+        "dtype": "tf32" if tf32 else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "engine": args.engine, "cuda_graph": (args.engine == "fused" and not args.no_graph),
                    "batch_per_gpu": B, "T": T_CHAIN, "step": "one warm reverse step "
                    "(eps_theta + posterior update, device Philox noise)", "cold_ms": cold_ms,

@@ -1,0 +1,114 @@
+"""GPU: the fused GEMM primitive (pdr_gemm_fused) -- fp32 SIMT path against a float64 torch restatement, and
+the tcgen05 TF32 path against the SIMT path -- over the shapes, prologues and epilogues the denoiser uses."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run(lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32, want_stats=True, ldc=None):
+    from point_diffusion_refinement_b200.fused import GemmArgs
+    M, K = A.shape
+    ldc = ldc or (N + 3) // 4 * 4
+    C = torch.full((M, ldc), float("nan"), device=DEV)
+    tiles = (rps + lib.pdr_gemm_tile_rows() - 1) // lib.pdr_gemm_tile_rows()
+    stats = torch.zeros(B * tiles, N, 4, device=DEV)
+    g = GemmArgs()
+    g.A, g.lda, g.K = A.data_ptr(), A.stride(0), K
+    g.W, g.ldw = W.data_ptr(), W.stride(0)
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.C, g.ldc, g.N, g.ldc_zero_to = C.data_ptr(), ldc, N, ldc
+    g.batch, g.rows_per_sample, g.pro_mode = B, rps, pro
+    if pro:
+        g.sc, g.sh, g.ld_scsh = sc.data_ptr(), sh.data_ptr(), sc.stride(0)
+    if add is not None:
+        g.add, g.ld_add = add.data_ptr(), add.stride(0)
+    if R is not None:
+        g.R, g.ldr = R.data_ptr(), R.stride(0)
+    if rowadd is not None:
+        g.rowadd, g.ld_rowadd, g.rowadd_div = rowadd.data_ptr(), rowadd.stride(0), div
+    g.stats = stats.data_ptr() if want_stats else None
+    g.use_tf32 = int(use_tf32)
+    rc = lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(g)), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.pdr_last_error_string()
+    torch.cuda.synchronize()
+    return C, stats.view(B, tiles, N, 4).sum(1)
+
+
+def _reference(A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div):
+    M, K = A.shape
+    x = A.double().view(B, rps, K)
+    if pro == 1:
+        x = torch.relu(x * sc.double()[:, None, :K] + sh.double()[:, None, :K])
+    elif pro == 2:
+        x = torch.relu(x) * sc.double()[:, None, :K] + sh.double()[:, None, :K]
+    if add is not None:
+        x = x + add.double()[:, None, :K]
+    x = x.reshape(M, K)
+    if R is not None:
+        x = x + R.double()[:, :K]
+    y = x @ W.double()[:, :K].t()
+    if bias is not None:
+        y = y + bias.double()
+    if rowadd is not None:
+        y = y + rowadd.double()[:, :N].repeat_interleave(div, dim=0)
+    st = torch.stack([y.view(B, rps, N).sum(1), (y ** 2).view(B, rps, N).sum(1), torch.relu(y).view(B, rps, N).sum(1),
+                      (torch.relu(y) ** 2).view(B, rps, N).sum(1)], dim=-1)
+    return y, st
+
+
+CASES = [  # B, rows_per_sample, K, N, pro, add, R, rowadd_div
+    (2, 4096, 44, 140, 0, False, False, 0),      # SA0 merged first|res|key
+    (2, 4096, 32, 32, 1, True, False, 0),        # GN+ReLU prologue + t embedding
+    (3, 1024, 64, 64, 1, True, True, 0),         # feat_out_conv with residual
+    (2, 2048, 44, 64, 2, False, False, 8),       # weight_conv key part + broadcast query part
+    (2, 512, 652, 256, 1, False, False, 0),      # deep K
+    (1, 4160, 332, 300, 0, False, False, 0),     # N > 256 (two column tiles), ragged rows (4160 = 32*130)
+    (5, 200, 128, 3, 1, False, False, 0),        # head: N = 3, rows not a multiple of 128
+    (2, 16, 36, 36, 0, False, False, 0),         # tiny query conv
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_gemm_simt_matches_float64(cuda_lib, case):
+    B, rps, K, N, pro, use_add, use_R, div = case
+    g = torch.Generator().manual_seed(K * N + rps)
+    M = B * rps
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    sc = (1 + 0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    sh = (0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    add = torch.randn(B, K, generator=g).to(DEV) if use_add else None
+    R = torch.randn(M, K, generator=g).to(DEV) if use_R else None
+    rowadd = torch.randn(M // div, (N + 3) // 4 * 4, generator=g).to(DEV) if div else None
+    y64, st64 = _reference(A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div)
+    C, st = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=False)
+    torch.testing.assert_close(C[:, :N].double(), y64, rtol=1e-4, atol=1e-4)
+    assert C[:, N:].abs().sum() == 0                                  # pad columns are written as zeros
+    torch.testing.assert_close(st.double(), st64, rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_gemm_tcgen05_matches_simt(cuda_lib, case):
+    B, rps, K, N, pro, use_add, use_R, div = case
+    g = torch.Generator().manual_seed(K * N + rps + 1)
+    M = B * rps
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    sc = (1 + 0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    sh = (0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    add = torch.randn(B, K, generator=g).to(DEV) if use_add else None
+    R = torch.randn(M, K, generator=g).to(DEV) if use_R else None
+    rowadd = torch.randn(M // div, (N + 3) // 4 * 4, generator=g).to(DEV) if div else None
+    C0, st0 = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=False)
+    C1, st1 = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True)
+    # TF32: 10-bit mantissa inputs, fp32 accumulate -> ~1e-3 relative to the row scale
+    torch.testing.assert_close(C1[:, :N], C0[:, :N], rtol=5e-3, atol=5e-3)
+    torch.testing.assert_close(st1, st0, rtol=5e-3, atol=5e-1)
+    C2, _ = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True)
+    assert torch.equal(C1[:, :N], C2[:, :N])                          # deterministic

@@ -175,3 +175,20 @@ def test_fused_engine_matches_modules_and_fixture(golden_dir, tag, use_graph):
     torch.testing.assert_close(other, other_mod, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(warm_fused.cpu(), gold["eps_warm"], rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(other.cpu(), gold["eps_cold"], rtol=1e-4, atol=1e-4)
+
+
+def test_fused_engine_tf32_within_tolerance(golden_dir):
+    """tcgen05 TF32 GEMMs inside the compiled step: same 2e-2 bar as the TF32 module path."""
+    from point_diffusion_refinement_b200 import configs
+    gold = torch.load(golden_dir + "/denoiser_full.pt")
+    net = _net(configs.ddpm_pointnet_config(), gold["param_seed"])
+    x, cond, ts, label = [t.to(DEV) for t in C.denoiser_inputs(gold["B"], gold["N"], gold["M"], seed=gold["input_seed"])]
+    with torch.no_grad():
+        net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+        net.enable_fused(True, use_tf32=True, use_graph=True)
+        x2 = x + 0.05 * gold["eps_cold"].to(DEV)
+        warm = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+        again = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+        net.reset_cond_features()
+    assert torch.equal(warm, again)
+    torch.testing.assert_close(warm.cpu(), gold["eps_warm"], rtol=2e-2, atol=2e-2)
