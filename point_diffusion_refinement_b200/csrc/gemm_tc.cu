@@ -2,29 +2,41 @@
 //
 //   C[M, N] = pro(A)[M, K] . W[N, K]^T + bias (+ rowadd)          fp32 in HBM, TF32 MMA, fp32 accumulate
 //
-// Same contract as the SIMT kernel in net.cu (PdrGemmArgs); this is the production path for the large
-// grouped 1x1 convolutions (M = B*npoint*nsample rows).  Per CTA: one 128-row tile x BN columns.
-//   * A cannot come through TMA: GroupNorm scale/shift + ReLU + per-sample embedding + residual are applied
-//     to it on the way in.  All 256 threads load A (coalesced 128 B rows) and W chunks into registers,
-//     transform, round to TF32 (cvt.rna) and store into shared memory in the canonical K-major
-//     SWIZZLE_128B layout (16-byte chunk c of row r lands at chunk c ^ (r & 7)); fence.proxy.async makes the
-//     generic-proxy stores visible to the tensor core.
-//   * One thread issues tcgen05.mma.cta_group::1.kind::tf32 (128 x BN x 8 per instruction, 4 per 32-float
-//     K chunk) with the accumulator in TMEM; tcgen05.commit arrives on an mbarrier that recycles the
-//     shared-memory stage, so the loads of chunk k+1 overlap the MMAs of chunk k.
-//   * Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / broadcast row-add -> global store,
-//     plus the per-column (sum, sum^2, relu-sum, relu-sum^2) tile statistics consumed by the next GroupNorm.
-// smem <= 97 KiB and TMEM <= 256 columns per CTA, so two CTAs share an SM and one's epilogue overlaps the
-// other's loads.
+// Same contract as the SIMT kernel in net.cu (PdrGemmArgs).  These GEMMs are tall and skinny (M = B*npoint*
+// nsample up to 2 M rows, K and N tens to hundreds): they are HBM-bound, the tensor core is there so that
+// the math never is.  The first version (one CTA per 128-row tile, load -> MMA -> epilogue in sequence) ran
+// at 9-12 % of HBM peak: every CTA paid a DRAM round trip, a TMEM allocation and an epilogue with nothing
+// else in flight (profiles/r01_ncu_gemm_tcgen05_v1_summary.csv).  This version is PERSISTENT and
+// WARP-SPECIALISED, one CTA per SM looping over (row tile, column tile) work items:
+//
+//   warps 4..11  producers  global A rows (coalesced 128 B) -> registers -> GroupNorm scale/shift, ReLU,
+//                           per-sample embedding, residual -> cvt.rna.tf32 -> shared memory in the canonical
+//                           K-major SWIZZLE_128B layout (chunk c of row r at c ^ (r & 7)) ->
+//                           fence.proxy.async -> mbarrier full[s].  A cannot use TMA because of the
+//                           transform.  The loads of chunk i+1 are issued before chunk i is stored, and the
+//                           ring is 3-6 stages deep, so DRAM requests stay in flight across tile boundaries.
+//   warp 12      MMA        one thread: tcgen05.mma.cta_group::1.kind::tf32 (128 x BN x 8), accumulators in
+//                           TMEM (double buffered: 2 x BN columns); tcgen05.commit -> empty[s] / tmem_full[a].
+//   warps 0..3   epilogue   tcgen05.ld 32 lanes x 32 columns -> bias / broadcast row-add -> transpose through
+//                           shared memory -> fully coalesced 128 B row stores + the per-column
+//                           (sum, sum^2, relu-sum, relu-sum^2) statistics the next GroupNorm needs ->
+//                           tmem_empty[a].
+//   When the whole weight matrix fits in 64 KiB of shared memory it is staged once per CTA (W-resident mode)
+//   and the ring carries A only.
 #include "common.cuh"
 
 namespace pdr {
 namespace {
 
-constexpr int kTcThreads = 256;
+constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
+constexpr int kTcThreads = kEpiThreads + kProdThreads + 32;   // 416
+constexpr int kMmaWarp = kEpiWarps + kProdWarps;              // 12
 constexpr int kTcTileM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTcTileM * 128;     // 16 KiB
+constexpr int kWResidentBytes = 64 * 1024;
+constexpr int kMaxStages = 6;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -42,6 +54,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -72,41 +87,68 @@ __device__ __forceinline__ float pro1(int mode, float x, float sc, float sh) {
   if (mode == PDR_PRO_RELU_GN) return fmaf(fmaxf(x, 0.f), sc, sh);
   return x;
 }
+__device__ __forceinline__ float4 tf32x4(float4 v) {
+  return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, 2)
-gemm_tf32_kernel(const PdrGemmArgs a) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool pred) {
+  // src-size 0 zero-fills the 16 destination bytes (rows beyond the tile, K tail)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(pred ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kDirectDepth = 4;   // chunks of cp.async in flight per producer thread, direct mode
+constexpr int kRawDepth = 3;      // raw ring depth, transform mode
+
+struct TcPlan {
+  int n_tiles_n;        // column tiles (N / BN rounded up)
+  int tiles_per_sample; // row tiles per sample
+  int total_items;      // n_tiles_n * batch * tiles_per_sample, column tile fastest
+  int nk;               // K chunks
+  int stages;           // MMA-layout ring depth
+  int direct;           // 1: no prologue -> cp.async lands straight in the MMA ring; 0: raw ring + transform
+  int raw_bytes;        // bytes of one raw stage (A [+ R]) in transform mode
+};
+
+template <int BN, bool WRES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   constexpr int kBTileBytes = BN * 128;
-  constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  constexpr int kWLoads = BN * 8 / kTcThreads;          // float4 per thread per chunk (>= 1 for BN >= 32)
+  constexpr int kStageBytes = WRES ? kATileBytes : kATileBytes + kBTileBytes;
+  constexpr int kWLoads = BN * 8 / kProdThreads;        // float4 of W per producer thread per chunk
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_empty[STAGES];
-  __shared__ uint64_t bar_done;
+  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2], bar_wready;
   __shared__ uint32_t s_tmem_base;
+  // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
+  // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
+  // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
+  __shared__ float s_epi[kEpiWarps][32 * 33];
+  __shared__ float s_part[4][BN][4];
 
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // layout: [W resident (WRES)] [stages] [epilogue transpose tiles 4 x 32 x 33 f32] [column partials 4 x BN x 4 f32]
+  uint8_t *s_wres = smem;
+  uint8_t *s_stages = smem + (WRES ? (size_t)plan.nk * kBTileBytes : 0);
+  uint8_t *s_raw = s_stages + (size_t)plan.stages * kStageBytes;
 
-  const int tiles_per_sample = (a.rows_per_sample + kTcTileM - 1) / kTcTileM;
-  const int tile = blockIdx.y;
-  const int b = tile / tiles_per_sample;
-  const int r0 = (tile % tiles_per_sample) * kTcTileM;
-  const size_t row_base = (size_t)b * a.rows_per_sample + r0;
-  const int rows_valid = min(kTcTileM, a.rows_per_sample - r0);
-  const int n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = plan.stages, nk = plan.nk;
 
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&bar_empty[s], 1);
-    mbar_init(&bar_done, 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], kProdThreads); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
+    mbar_init(&bar_tempty[0], kEpiThreads); mbar_init(&bar_tempty[1], kEpiThreads);
+    mbar_init(&bar_wready, kProdThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                 "r"((uint32_t)BN)
+                 "r"((uint32_t)(2 * BN))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -118,203 +160,358 @@ gemm_tf32_kernel(const PdrGemmArgs a) {
   // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
   constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
 
-  // ---- loader mapping: A chunk = 128 rows x 8 float4; thread handles rows (tid>>3) + 32*i, float4 #(tid&7) ----
-  const int chunk = tid & 7;
-  const int arow = tid >> 3;
-  float4 ra[4];
-  float4 rw[kWLoads];
-
-  auto load_chunk = [&](int k0) {
-    const int k = k0 + chunk * 4;
-    const bool kin = k < a.K;
-    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = h4;
-    if (kin) {
-      if (a.pro_mode != PDR_PRO_NONE) {
-        s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)b * a.ld_scsh + k));
-        h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)b * a.ld_scsh + k));
-      }
-      if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)b * a.ld_add + k));
-    }
+  if (warp >= kEpiWarps && warp < kMmaWarp) {
+    // =============================== PRODUCERS ===============================================
+    const int ptid = tid - kEpiThreads;
+    const int chunk = ptid & 7;       // which 16-byte piece of the 128-byte K chunk
+    const int arow = ptid >> 3;       // rows arow + 32*i
+    if (WRES) {                        // stage the whole weight matrix once
+      for (int kc = 0; kc < nk; ++kc) {
+        const int k = kc * kTcBK + chunk * 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = arow + 32 * i;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kin && row < rows_valid) {
-        const size_t grow = row_base + row;
-        v = *reinterpret_cast<const float4 *>(a.A + grow * a.lda + k);
-        v.x = pro1(a.pro_mode, v.x, s4.x, h4.x) + e4.x; v.y = pro1(a.pro_mode, v.y, s4.y, h4.y) + e4.y;
-        v.z = pro1(a.pro_mode, v.z, s4.z, h4.z) + e4.z; v.w = pro1(a.pro_mode, v.w, s4.w, h4.w) + e4.w;
-        if (a.R) {
-          const float4 r = *reinterpret_cast<const float4 *>(a.R + grow * a.ldr + k);
-          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        for (int i = 0; i < kWLoads; ++i) {
+          const int n = arow + 32 * i;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < a.K && n < a.N) v = tf32x4(__ldg(reinterpret_cast<const float4 *>(a.W + (size_t)n * a.ldw + k)));
+          *reinterpret_cast<float4 *>(s_wres + (size_t)kc * kBTileBytes + n * 128 + ((chunk ^ (n & 7)) << 4)) = v;
         }
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
       }
-      ra[i] = v;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&bar_wready);
     }
+    // chunk sequence of this CTA: items blockIdx.x, +gridDim.x, ... ; nk chunks each
+    const int my_items = plan.total_items > (int)blockIdx.x
+                             ? (plan.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int my_chunks = my_items * nk;
+    struct Cursor { int item, kc; };
+    auto advance = [&](Cursor &c) { if (++c.kc == nk) { c.kc = 0; c.item += gridDim.x; } };
+    struct Geo { int b, rows_valid, n0; size_t row_base; };
+    auto geo_of = [&](int item) {
+      Geo g;
+      const int tile = item / plan.n_tiles_n;
+      g.n0 = (item % plan.n_tiles_n) * BN;
+      g.b = tile / plan.tiles_per_sample;
+      const int r0 = (tile % plan.tiles_per_sample) * kTcTileM;
+      g.row_base = (size_t)g.b * a.rows_per_sample + r0;
+      g.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
+      return g;
+    };
+    if (plan.direct) {
+      // ---- no prologue: cp.async straight into the swizzled MMA stage, kDirectDepth chunks in flight ----
+      auto issue = [&](const Cursor &c, int stage) {
+        const Geo g = geo_of(c.item);
+        const int k = c.kc * kTcBK + chunk * 4;
+        const bool kin = k < a.K;
+        const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes);
 #pragma unroll
-    for (int i = 0; i < kWLoads; ++i) {
-      const int n = arow + 32 * i;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kin && n0 + n < a.N) {
-        v = __ldg(reinterpret_cast<const float4 *>(a.W + (size_t)(n0 + n) * a.ldw + k));
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-      }
-      rw[i] = v;
-    }
-  };
-  auto store_chunk = [&](int s) {
-    uint8_t *sa = smem + (size_t)s * kStageBytes;
-    uint8_t *sb = sa + kATileBytes;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = arow + 32 * i;
-      *reinterpret_cast<float4 *>(sa + row * 128 + ((chunk ^ (row & 7)) << 4)) = ra[i];
-    }
-#pragma unroll
-    for (int i = 0; i < kWLoads; ++i) {
-      const int n = arow + 32 * i;
-      *reinterpret_cast<float4 *>(sb + n * 128 + ((chunk ^ (n & 7)) << 4)) = rw[i];
-    }
-  };
-
-  const int nk = (a.K + kTcBK - 1) / kTcBK;
-  load_chunk(0);
-  for (int kc = 0; kc < nk; ++kc) {
-    const int s = kc % STAGES;
-    if (kc >= STAGES) mbar_wait(&bar_empty[s], (uint32_t)((kc / STAGES - 1) & 1));
-    store_chunk(s);
-    if (kc + 1 < nk) load_chunk((kc + 1) * kTcBK);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes);
-      const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + kATileBytes);
-#pragma unroll
-      for (int k8 = 0; k8 < kTcBK / 8; ++k8)
-        umma_tf32(tmem_base, adesc + (uint64_t)(k8 * 2), bdesc + (uint64_t)(k8 * 2), kIdesc, (kc | k8) ? 1u : 0u);
-      umma_commit(&bar_empty[s]);
-      if (kc == nk - 1) umma_commit(&bar_done);
-    }
-  }
-  mbar_wait(&bar_done, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // ---- epilogue ---------------------------------------------------------------------------------------
-  // stage memory is free now: per-warp 32x33 transpose tiles, then per-quarter column partials
-  float *s_t = reinterpret_cast<float *>(smem) + warp * (32 * 33);
-  float *s_part = reinterpret_cast<float *>(smem) + 8 * 32 * 33;     // [4 quarters][BN][4]
-  const int quarter = warp & 3;
-  constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
-  const bool warp_active = BN >= 64 || warp < 4;
-  const int cbeg = BN >= 64 ? (warp >> 2) * kColsPerWarp : 0;
-  const int row = quarter * 32 + lane;
-  const bool rvalid = row < rows_valid;
-  const size_t grow = row_base + row;
-  const bool vec_ok = (a.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
-  if (warp_active) {
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + kColsPerWarp; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const float *radd = (a.rowadd && rvalid) ? a.rowadd + (grow / a.rowadd_div) * a.ld_rowadd : nullptr;
-      float y[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        float t = 0.f;
-        if (rvalid && n < a.N) {
-          t = __uint_as_float(v[j]);
-          if (a.bias) t += __ldg(a.bias + n);
-          if (radd) t += __ldg(radd + n);
+        for (int i = 0; i < 4; ++i) {
+          const int row = arow + 32 * i;
+          const bool ok = kin && row < g.rows_valid;
+          const float *src = ok ? a.A + (g.row_base + row) * a.lda + k : a.A;
+          cp_async16(sa + row * 128 + ((chunk ^ (row & 7)) << 4), src, ok);
         }
-        y[j] = t;
-      }
-      if (rvalid) {
-        float *crow = a.C + grow * a.ldc + n0 + c0;
-        if (vec_ok && n0 + c0 + 32 <= a.N) {
+        if (!WRES) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(crow + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < a.N) crow[j] = y[j];
-            else if (n < a.ldc_zero_to) crow[j] = 0.f;
+          for (int i = 0; i < kWLoads; ++i) {
+            const int n = arow + 32 * i;
+            const bool ok = kin && g.n0 + n < a.N;
+            const float *src = ok ? a.W + (size_t)(g.n0 + n) * a.ldw + k : a.W;
+            cp_async16(sa + kATileBytes + n * 128 + ((chunk ^ (n & 7)) << 4), src, ok);
           }
         }
+      };
+      Cursor ci{(int)blockIdx.x, 0};
+      int issued = 0, stage_i = 0, phase_i = 0, stage_c = 0;
+      for (int d = 0; d < kDirectDepth; ++d) {
+        if (issued < my_chunks) {
+          mbar_wait(&bar_empty[stage_i], (uint32_t)(phase_i ^ 1));
+          issue(ci, stage_i);
+          advance(ci); ++issued;
+          if (++stage_i == S) { stage_i = 0; phase_i ^= 1; }
+        }
+        cp_async_commit();
       }
-      if (a.stats) {
+      for (int done = 0; done < my_chunks; ++done) {
+        cp_async_wait<kDirectDepth - 1>();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&bar_full[stage_c]);
+        if (++stage_c == S) stage_c = 0;
+        if (issued < my_chunks) {
+          mbar_wait(&bar_empty[stage_i], (uint32_t)(phase_i ^ 1));
+          issue(ci, stage_i);
+          advance(ci); ++issued;
+          if (++stage_i == S) { stage_i = 0; phase_i ^= 1; }
+        }
+        cp_async_commit();
+      }
+    } else {
+      // ---- prologue needed: cp.async into a raw ring (kRawDepth in flight), then each thread transforms
+      //      exactly the 16-byte pieces it copied (no cross-thread hazard) into the MMA ring ----
+      auto issue_raw = [&](const Cursor &c, int slot) {
+        const Geo g = geo_of(c.item);
+        const int k = c.kc * kTcBK + chunk * 4;
+        const bool kin = k < a.K;
+        const uint32_t sr = smem_u32(s_raw + (size_t)slot * plan.raw_bytes);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s_t[lane * 33 + j] = y[j];
-        __syncwarp();
-        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const float t = s_t[r * 33 + lane];
-          const float p = fmaxf(t, 0.f);
-          q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
+        for (int i = 0; i < 4; ++i) {
+          const int row = arow + 32 * i;
+          const bool ok = kin && row < g.rows_valid;
+          const size_t off = (g.row_base + row);
+          cp_async16(sr + row * 128 + (chunk << 4), ok ? a.A + off * a.lda + k : a.A, ok);
+          if (a.R) cp_async16(sr + kATileBytes + row * 128 + (chunk << 4), ok ? a.R + off * a.ldr + k : a.R, ok);
+        }
+      };
+      Cursor ci{(int)blockIdx.x, 0}, cc{(int)blockIdx.x, 0};
+      int issued = 0, stage = 0, phase = 0;
+      for (int d = 0; d < kRawDepth; ++d) {
+        if (issued < my_chunks) { issue_raw(ci, d); advance(ci); ++issued; }
+        cp_async_commit();
+      }
+      for (int done = 0; done < my_chunks; ++done) {
+        const int slot = done % kRawDepth;
+        cp_async_wait<kRawDepth - 1>();
+        const Geo g = geo_of(cc.item);
+        const int k = cc.kc * kTcBK + chunk * 4;
+        const bool kin = k < a.K;
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = h4;
+        if (kin) {
+          if (a.pro_mode != PDR_PRO_NONE) {
+            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)g.b * a.ld_scsh + k));
+            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)g.b * a.ld_scsh + k));
+          }
+          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)g.b * a.ld_add + k));
+        }
+        float4 rw[WRES ? 1 : kWLoads];
+        if (!WRES) {
+#pragma unroll
+          for (int i = 0; i < kWLoads; ++i) {
+            const int n = arow + 32 * i;
+            rw[i] = (kin && g.n0 + n < a.N) ? __ldg(reinterpret_cast<const float4 *>(a.W + (size_t)(g.n0 + n) * a.ldw + k))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
+        const uint8_t *sr = s_raw + (size_t)slot * plan.raw_bytes;
+        uint8_t *sa = s_stages + (size_t)stage * kStageBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = arow + 32 * i;
+          float4 v = *reinterpret_cast<const float4 *>(sr + row * 128 + (chunk << 4));
+          if (kin && row < g.rows_valid) {
+            v.x = pro1(a.pro_mode, v.x, s4.x, h4.x) + e4.x; v.y = pro1(a.pro_mode, v.y, s4.y, h4.y) + e4.y;
+            v.z = pro1(a.pro_mode, v.z, s4.z, h4.z) + e4.z; v.w = pro1(a.pro_mode, v.w, s4.w, h4.w) + e4.w;
+            if (a.R) {
+              const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + row * 128 + (chunk << 4));
+              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            v = tf32x4(v);
+          } else {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          *reinterpret_cast<float4 *>(sa + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+        }
+        if (!WRES) {
+#pragma unroll
+          for (int i = 0; i < kWLoads; ++i) {
+            const int n = arow + 32 * i;
+            *reinterpret_cast<float4 *>(sa + kATileBytes + n * 128 + ((chunk ^ (n & 7)) << 4)) = tf32x4(rw[i]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&bar_full[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+        advance(cc);
+        if (issued < my_chunks) { issue_raw(ci, slot); advance(ci); ++issued; }   // the slot just consumed is free
+        cp_async_commit();
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =============================== MMA ISSUER ==============================================
+    // the whole warp walks the pipeline (so it stays convergent for the block-wide barrier at the end);
+    // lane 0 alone issues tcgen05.mma / tcgen05.commit
+    if (WRES) mbar_wait(&bar_wready, 0);
+    int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < plan.total_items; item += gridDim.x) {
+      mbar_wait(&bar_tempty[acc], (uint32_t)(acc_phase ^ 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(&bar_full[stage], (uint32_t)phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes);
+          const uint32_t sb = WRES ? smem_u32(s_wres + (size_t)kc * kBTileBytes) : sa + kATileBytes;
+          const uint64_t adesc = make_desc(sa), bdesc = make_desc(sb);
+#pragma unroll
+          for (int k8 = 0; k8 < kTcBK / 8; ++k8)
+            umma_tf32(d_tmem, adesc + (uint64_t)(k8 * 2), bdesc + (uint64_t)(k8 * 2), kIdesc, (kc | k8) ? 1u : 0u);
+          umma_commit(&bar_empty[stage]);
+          if (kc == nk - 1) umma_commit(&bar_tfull[acc]);
         }
         __syncwarp();
-        float *dst = s_part + ((size_t)quarter * BN + c0 + lane) * 4;
-        dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // =============================== EPILOGUE ================================================
+    const int quarter = warp;                     // TMEM lanes [32*quarter, +32)
+    float *s_t = s_epi[warp];
+    int acc = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < plan.total_items; item += gridDim.x) {
+      const int tile = item / plan.n_tiles_n, n0 = (item % plan.n_tiles_n) * BN;
+      const int b = tile / plan.tiles_per_sample;
+      const int r0 = (tile % plan.tiles_per_sample) * kTcTileM;
+      const size_t row_base = (size_t)b * a.rows_per_sample + r0;
+      const int rows_valid = min(kTcTileM, a.rows_per_sample - r0);
+      const int wrows = max(0, min(32, rows_valid - quarter * 32));   // valid rows among this warp's 32
+      const size_t wrow0 = row_base + quarter * 32;                   // first global row of this warp
+      size_t radd_g0 = 0;
+      int radd_rem0 = 0;
+      if (a.rowadd) { radd_g0 = wrow0 / (size_t)a.rowadd_div; radd_rem0 = (int)(wrow0 % (size_t)a.rowadd_div); }
+      mbar_wait(&bar_tfull[acc], (uint32_t)acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= a.ldc_zero_to && n0 + c0 >= a.N) break;      // nothing to write in this or later blocks
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // park my row (lane = row) in the transpose tile; stride 33 keeps both phases bank-conflict free
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s_t[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        // lane = column from here on: bias and broadcast row-add are added per column, every store
+        // instruction writes 32 consecutive floats of one row (128 B, fully coalesced)
+        const int n = n0 + c0 + lane;
+        const bool nin = n < a.N;
+        const bool nstore = nin || n < a.ldc_zero_to;
+        const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        float *cp = a.C + wrow0 * a.ldc + n;
+        const size_t ldc = (size_t)a.ldc;
+        const float *st = s_t + lane;
+        // the loops below are the hot path of the epilogue warps: keep them branch-free and free of 64-bit
+        // index arithmetic (running pointers only)
+        if (!a.rowadd) {
+#pragma unroll 8
+          for (int r = 0; r < wrows; ++r) {
+            float t = st[r * 33] + bias_n;
+            t = nin ? t : 0.f;
+            if (nstore) *cp = t;
+            cp += ldc;
+            const float p = fmaxf(t, 0.f);
+            q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
+          }
+        } else {
+          // rows (wrow0 + r) / div share one broadcast row; div divides the sample's row count, so the
+          // group index advances every `div` rows
+          const float *rp = a.rowadd + radd_g0 * a.ld_rowadd + (nin ? n : 0);
+          int rem = radd_rem0;
+#pragma unroll 4
+          for (int r = 0; r < wrows; ++r) {
+            float t = st[r * 33] + bias_n + __ldg(rp);
+            t = nin ? t : 0.f;
+            if (nstore) *cp = t;
+            cp += ldc;
+            if (++rem == a.rowadd_div) { rem = 0; rp += a.ld_rowadd; }
+            const float p = fmaxf(t, 0.f);
+            q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
+          }
+        }
+        __syncwarp();
+        if (a.stats) { s_part[quarter][c0 + lane][0] = q0; s_part[quarter][c0 + lane][1] = q1;
+                       s_part[quarter][c0 + lane][2] = q2; s_part[quarter][c0 + lane][3] = q3; }
+      }
+      // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&bar_tempty[acc]);
+      if (a.stats) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        for (int f = tid; f < BN * 4; f += kEpiThreads) {
+          const int col = f >> 2, q = f & 3;
+          if (n0 + col < a.N)
+            a.stats[((size_t)tile * a.N + n0 + col) * 4 + q] =
+                s_part[0][col][q] + s_part[1][col][q] + s_part[2][col][q] + s_part[3][col][q];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (a.stats) {
-    for (int f = tid; f < BN * 4; f += kTcThreads) {
-      const int col = f >> 2, q = f & 3;
-      if (n0 + col < a.N) {
-        const float s = s_part[((size_t)0 * BN + col) * 4 + q] + s_part[((size_t)1 * BN + col) * 4 + q] +
-                        s_part[((size_t)2 * BN + col) * 4 + q] + s_part[((size_t)3 * BN + col) * 4 + q];
-        a.stats[((size_t)tile * a.N + n0 + col) * 4 + q] = s;
-      }
-    }
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                 : "memory");
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, bool WRES>
 int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
-  constexpr size_t kSmem = (size_t)STAGES * (kATileBytes + BN * 128) + 1024;
-  static_assert(kSmem >= (size_t)(8 * 32 * 33 + 4 * BN * 4) * 4 + 1024, "epilogue scratch must fit in the stages");
-  auto kern = gemm_tf32_kernel<BN, STAGES>;
+  TcPlan plan;
+  plan.n_tiles_n = ceil_div(a.N, BN);
+  plan.tiles_per_sample = ceil_div(a.rows_per_sample, kTcTileM);
+  const long long items = (long long)plan.n_tiles_n * a.batch * plan.tiles_per_sample;
+  if (items > 0x7fffffffll) { set_error("gemm_tf32: too many tiles"); return PDR_ERR_INVALID_ARGUMENT; }
+  plan.total_items = (int)items;
+  plan.nk = ceil_div(a.K, kTcBK);
+  const size_t epi = 0;   // epilogue scratch is static shared memory now
+  const size_t static_smem = (size_t)(kEpiWarps * 32 * 33 + 4 * BN * 4) * sizeof(float) + 256;
+  const size_t stage = WRES ? kATileBytes : kATileBytes + BN * 128;
+  const size_t budget = 226 * 1024 - static_smem;
+  size_t smem = 0;
+  bool planned = false;
+  // prefer the direct (no-transform) producer when the GEMM has no prologue and depth+1 stages fit
+  for (int direct = (a.pro_mode == PDR_PRO_NONE && !a.add && !a.R) ? 1 : 0; direct >= 0 && !planned; --direct) {
+    plan.direct = direct;
+    plan.raw_bytes = direct ? 0 : kATileBytes * (a.R ? 2 : 1);
+    const size_t fixed = 1024 + epi + (WRES ? (size_t)plan.nk * BN * 128 : 0) + (size_t)kRawDepth * plan.raw_bytes;
+    if (fixed + 2 * stage > budget) continue;
+    int stages = (int)((budget - fixed) / stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < (direct ? kDirectDepth + 1 : 2)) continue;
+    plan.stages = stages;
+    smem = fixed + (size_t)stages * stage;
+    planned = true;
+  }
+  if (!planned) { set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N); return PDR_ERR_UNSUPPORTED; }
+  auto kern = gemm_tf32_persistent<BN, WRES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
     configured = true;
   }
-  const int tiles_per_sample = ceil_div(a.rows_per_sample, kTcTileM);
-  const long long tiles = (long long)a.batch * tiles_per_sample;
-  if (tiles > 65535) { set_error("gemm_tf32: %lld tiles > 65535", tiles); return PDR_ERR_INVALID_ARGUMENT; }
-  dim3 grid(ceil_div(a.N, BN), (unsigned)tiles);
-  kern<<<grid, kTcThreads, kSmem, stream>>>(a);
-  return check_launch("gemm_tf32_kernel");
+  const int grid = plan.total_items < kNumSMs ? plan.total_items : kNumSMs;
+  kern<<<grid, kTcThreads, smem, stream>>>(a, plan);
+  return check_launch("gemm_tf32_persistent");
+}
+
+template <int BN>
+int dispatch_wres(const PdrGemmArgs &a, cudaStream_t stream) {
+  const int nk = ceil_div(a.K, kTcBK);
+  const bool wres = ceil_div(a.N, BN) == 1 && (size_t)nk * BN * 128 <= (size_t)kWResidentBytes;
+  return wres ? launch_tc<BN, true>(a, stream) : launch_tc<BN, false>(a, stream);
 }
 
 }  // namespace
 
 int launch_gemm_tf32(const PdrGemmArgs &a, cudaStream_t stream) {
-  if (a.N > 128) return launch_tc<256, 2>(a, stream);
-  if (a.N > 64) return launch_tc<128, 3>(a, stream);
-  if (a.N > 32) return launch_tc<64, 4>(a, stream);
-  return launch_tc<32, 4>(a, stream);
+  if (a.N > 128) return dispatch_wres<256>(a, stream);
+  if (a.N > 64) return dispatch_wres<128>(a, stream);
+  if (a.N > 32) return dispatch_wres<64>(a, stream);
+  return dispatch_wres<32>(a, stream);
 }
 
 }  // namespace pdr
