@@ -186,39 +186,66 @@ gemm_simt_kernel(const PdrGemmArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm finalisation: one CTA per sample.  Partial sums are added in tile order (deterministic),
-// in double, and the variance is E[x^2] - mean^2 (biased, like nn.GroupNorm).
+// GroupNorm finalisation.  grid = (batch, group splits); each CTA owns a contiguous range of groups.
+// The per-tile partial sums written by the GEMM epilogues are added in a FIXED order (warp w takes tiles
+// w, w+8, ...; the 8 warp partials are then added in warp order), in double, so the result is
+// deterministic; variance is E[x^2] - mean^2 (biased, like nn.GroupNorm).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kGnThreads = 256;
+constexpr int kGnSplit = 4;
+
+__global__ void __launch_bounds__(kGnThreads)
 gn_finalize_kernel(const PdrGnArgs a) {
-  extern __shared__ double s_tot[];  // [channels][3] = weighted sum, weighted sum of squares, element count
+  extern __shared__ double s_tot[];                 // [channels in range][3] = weighted sum, sum of squares, count
+  __shared__ double s_red[kGnThreads / 32][32][2];
   const int b = blockIdx.x;
-  int c_off = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpg = a.gn_channels / a.groups;
+  const int gpc = (a.groups + gridDim.y - 1) / gridDim.y;           // groups per CTA
+  const int g_lo = min(a.groups, (int)blockIdx.y * gpc), g_hi = min(a.groups, g_lo + gpc);
+  const int c_lo = g_lo * cpg;
+  // the last split also writes the pass-through channels [gn_channels, channels)
+  const int c_hi = (blockIdx.y == gridDim.y - 1) ? a.channels : g_hi * cpg;
+  const int c_gn_hi = g_hi * cpg;                                   // channels that need statistics: [c_lo, c_gn_hi)
+
+  int src_off = 0;
   for (int s = 0; s < a.nsrc; ++s) {
     const PdrGnSource src = a.src[s];
-    for (int c = threadIdx.x; c < src.ncols; c += blockDim.x) {
+    const int v_lo = max(c_lo, src_off), v_hi = min(c_gn_hi, src_off + src.ncols);   // virtual channels of this source
+    for (int v0 = v_lo; v0 < v_hi; v0 += 32) {
+      const int v = v0 + lane;
       double sum = 0.0, sq = 0.0;
-      const float *p = src.stats + ((size_t)b * src.tiles_per_sample * src.ld_stats + src.col0 + c) * 4 +
-                       (src.use_relu ? 2 : 0);
-      for (int t = 0; t < src.tiles_per_sample; ++t, p += (size_t)src.ld_stats * 4) {
-        sum += (double)p[0];
-        sq += (double)p[1];
+      if (v < v_hi) {
+        const float *p = src.stats + ((size_t)b * src.tiles_per_sample * src.ld_stats + src.col0 + (v - src_off)) * 4 +
+                         (src.use_relu ? 2 : 0);
+        for (int t = warp; t < src.tiles_per_sample; t += kGnThreads / 32) {
+          const float2 q = *reinterpret_cast<const float2 *>(p + (size_t)t * src.ld_stats * 4);
+          sum += (double)q.x;
+          sq += (double)q.y;
+        }
       }
-      s_tot[(c_off + c) * 3 + 0] = (double)src.mult * sum;
-      s_tot[(c_off + c) * 3 + 1] = (double)src.mult * sq;
-      s_tot[(c_off + c) * 3 + 2] = (double)src.mult * (double)src.rows;
+      s_red[warp][lane][0] = sum;
+      s_red[warp][lane][1] = sq;
+      __syncthreads();
+      if (warp == 0 && v < v_hi) {
+        double ts = 0.0, tq = 0.0;
+#pragma unroll
+        for (int w = 0; w < kGnThreads / 32; ++w) { ts += s_red[w][lane][0]; tq += s_red[w][lane][1]; }
+        s_tot[(v - c_lo) * 3 + 0] = (double)src.mult * ts;
+        s_tot[(v - c_lo) * 3 + 1] = (double)src.mult * tq;
+        s_tot[(v - c_lo) * 3 + 2] = (double)src.mult * (double)src.rows;
+      }
+      __syncthreads();
     }
-    c_off += src.ncols;
+    src_off += src.ncols;
   }
-  __syncthreads();
-  const int cpg = a.groups > 0 ? a.gn_channels / a.groups : 1;
-  for (int c = threadIdx.x; c < a.channels; c += blockDim.x) {
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += kGnThreads) {
     float sc = 1.f, sh = 0.f;  // MyGroupNorm passes the trailing C % G channels through (attention.py:17-23)
     if (c < a.gn_channels) {
       const int g = c / cpg;
       double sum = 0.0, sq = 0.0, n = 0.0;
       for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
-        sum += s_tot[cc * 3 + 0]; sq += s_tot[cc * 3 + 1]; n += s_tot[cc * 3 + 2];
+        sum += s_tot[(cc - c_lo) * 3 + 0]; sq += s_tot[(cc - c_lo) * 3 + 1]; n += s_tot[(cc - c_lo) * 3 + 2];
       }
       const double mean = sum / n;
       double var = sq / n - mean * mean;
@@ -255,7 +282,10 @@ affine_rows_kernel(int rows_per_sample, int C, const float *__restrict__ x, int 
   out[row * ldo + c] = v;
 }
 
-// Attention pooling: one thread per (b, p, c); the K scores/values of a (p, c) are strided by ld.
+// Attention pooling: one thread per (b, p, c); the K scores/values of a (p, c) are strided by ld, consecutive
+// threads take consecutive channels (coalesced).  KT > 0: the K scores live in registers, S and V are read
+// exactly once.
+template <int KT>
 __global__ void __launch_bounds__(256)
 attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds, const float *__restrict__ V,
                       int ldv, const float *__restrict__ sc, const float *__restrict__ sh, int ld_scsh,
@@ -270,76 +300,91 @@ attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds,
   const float gs = __ldg(sc + (size_t)b * ld_scsh + c), gh = __ldg(sh + (size_t)b * ld_scsh + c);
   const float *s = S + (size_t)bp * K * lds + c;
   const float *v = V + (size_t)bp * K * ldv + c;
-  float mx = -3.0e38f;
-  for (int k = 0; k < K; ++k) {
-    const float sv = k < cnt ? s[(size_t)k * lds] : -1e9f;  // scores*mask + (-1e9)*(1-mask), attention.py:88
-    mx = fmaxf(mx, sv);
-  }
-  float den = 0.f, num = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float sv = k < cnt ? s[(size_t)k * lds] : -1e9f;
-    const float e = expf(sv - mx);
-    den += e;
-    num = fmaf(e, fmaxf(fmaf(v[(size_t)k * ldv], gs, gh), 0.f), num);
+  float mx = -3.0e38f, den = 0.f, num = 0.f;
+  if (KT > 0) {
+    float sv[KT > 0 ? KT : 1];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      sv[k] = k < cnt ? s[(size_t)k * lds] : -1e9f;   // scores*mask + (-1e9)*(1-mask), attention.py:88
+      mx = fmaxf(mx, sv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const float e = expf(sv[k] - mx);
+      den += e;
+      num = fmaf(e, fmaxf(fmaf(v[(size_t)k * ldv], gs, gh), 0.f), num);
+    }
+  } else {
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, k < cnt ? s[(size_t)k * lds] : -1e9f);
+    for (int k = 0; k < K; ++k) {
+      const float e = expf((k < cnt ? s[(size_t)k * lds] : -1e9f) - mx);
+      den += e;
+      num = fmaf(e, fmaxf(fmaf(v[(size_t)k * ldv], gs, gh), 0.f), num);
+    }
   }
   out[bp * ldo + c] = num / den;
 }
 
-// Ball-query grouping, one thread per (row, output column).
+// Ball-query grouping.  block = (32 lanes over the output columns, 8 rows): the neighbour index, the
+// centre and the validity flag are loaded once per row, the feature row is copied with coalesced loads and
+// stores, and there is no 64-bit division anywhere.
 __global__ void __launch_bounds__(256)
 group_ball_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int ldf,
                   const float *__restrict__ xyz, const float *__restrict__ centres, const int *__restrict__ idx,
-                  const int *__restrict__ counts, int fill_missing, float *__restrict__ out, int ldo,
-                  long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % ldo);
-  const long long row = i / ldo;             // (b*P + p)*K + k
-  const long long bp = row / K;
-  const int b = (int)(bp / P);
+                  const int *__restrict__ counts, int fill_missing, float *__restrict__ out, int ldo, int rows) {
+  const int row = blockIdx.x * 8 + threadIdx.y;          // (b*P + p)*K + k
+  if (row >= rows) return;
+  const int bp = row / K;
+  const int b = bp / P;
   const int src = __ldg(idx + row);
   const bool missing = fill_missing && counts && __ldg(counts + bp) == 0;
-  float v = 0.f;
-  if (c < C) {
-    v = missing ? 0.f : __ldg(feat + ((size_t)b * n + src) * ldf + c);
-  } else if (c < C + 9) {
-    const int q = c - C, d = q % 3;
-    const float cen = __ldg(centres + bp * 3 + d);
-    const float ab = missing ? cen : __ldg(xyz + ((size_t)b * n + src) * 3 + d);
-    v = q < 3 ? ab - cen : (q < 6 ? ab : cen);
+  const float *frow = feat + ((size_t)b * n + src) * ldf;
+  float *orow = out + (size_t)row * ldo;
+  for (int c = threadIdx.x; c < C; c += 32) orow[c] = missing ? 0.f : __ldg(frow + c);
+  const int q = threadIdx.x;
+  if (q < ldo - C) {
+    float v = 0.f;
+    if (q < 9) {
+      const int d = q % 3;
+      const float cen = __ldg(centres + (size_t)bp * 3 + d);
+      const float ab = missing ? cen : __ldg(xyz + ((size_t)b * n + src) * 3 + d);
+      v = q < 3 ? ab - cen : (q < 6 ? ab : cen);
+    }
+    orow[C + q] = v;
   }
-  out[row * ldo + c] = v;
 }
 
-// kNN grouping rows: [feat | d2 | w | nn_abs | nn_rel | x].
+// kNN grouping rows: [feat | d2 | w | nn_abs | nn_rel | x | 0-pad], same block shape.
 __global__ void __launch_bounds__(256)
 group_knn_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int ldf, const float *__restrict__ y,
                  const float *__restrict__ x, const int64_t *__restrict__ idx, const float *__restrict__ dists,
-                 float *__restrict__ out, int ldo, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % ldo);
-  const long long row = i / ldo;
-  const long long bp = row / K;
-  const int b = (int)(bp / P);
+                 float *__restrict__ out, int ldo, int rows) {
+  const int row = blockIdx.x * 8 + threadIdx.y;
+  if (row >= rows) return;
+  const int bp = row / K;
+  const int b = bp / P;
   const int src = (int)__ldg(idx + row);
-  float v = 0.f;
-  if (c < C) {
-    v = __ldg(feat + ((size_t)b * n + src) * ldf + c);
-  } else if (c == C) {
-    v = __ldg(dists + row);
-  } else if (c == C + 1) {
-    // weight = (1/(d+1e-8)) / sum_k (1/(d_k+1e-8)), summed in neighbour order like torch.sum(dim=2)
-    float norm = 0.f;
-    for (int k = 0; k < K; ++k) norm += 1.0f / (__ldg(dists + bp * K + k) + 1e-8f);
-    v = (1.0f / (__ldg(dists + row) + 1e-8f)) / norm;
-  } else if (c < C + 11) {
-    const int q = c - C - 2, d = q % 3;
-    const float xv = __ldg(x + bp * 3 + d);
-    const float yv = __ldg(y + ((size_t)b * n + src) * 3 + d);
-    v = q < 3 ? yv : (q < 6 ? yv - xv : xv);
+  const float *frow = feat + ((size_t)b * n + src) * ldf;
+  float *orow = out + (size_t)row * ldo;
+  for (int c = threadIdx.x; c < C; c += 32) orow[c] = __ldg(frow + c);
+  const int q = threadIdx.x;
+  if (q < ldo - C) {
+    float v = 0.f;
+    if (q == 0) {
+      v = __ldg(dists + row);
+    } else if (q == 1) {
+      // weight = (1/(d+1e-8)) / sum_k (1/(d_k+1e-8)), summed in neighbour order like torch.sum(dim=2)
+      float norm = 0.f;
+      for (int k = 0; k < K; ++k) norm += 1.0f / (__ldg(dists + (size_t)bp * K + k) + 1e-8f);
+      v = (1.0f / (__ldg(dists + row) + 1e-8f)) / norm;
+    } else if (q < 11) {
+      const int t = q - 2, d = t % 3;
+      const float xv = __ldg(x + (size_t)bp * 3 + d);
+      const float yv = __ldg(y + ((size_t)b * n + src) * 3 + d);
+      v = t < 3 ? yv : (t < 6 ? yv - xv : xv);
+    }
+    orow[C + q] = v;
   }
-  out[row * ldo + c] = v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -404,9 +449,10 @@ extern "C" int pdr_gn_finalize(const PdrGnArgs *args, void *stream) {
   for (int s = 0; s < a.nsrc; ++s) tot += a.src[s].ncols;
   PDR_REQUIRE(tot == a.channels, "gn_finalize: sources cover %d of %d channels", tot, a.channels);
   PDR_REQUIRE(a.gamma && a.beta && a.sc && a.sh, "gn_finalize: null pointer");
-  const size_t smem = (size_t)a.channels * 3 * sizeof(double);
+  const int split = a.groups >= kGnSplit ? kGnSplit : 1;
+  const size_t smem = (size_t)a.channels * 3 * sizeof(double);      // upper bound for any split
   PDR_REQUIRE(smem <= 48 * 1024, "gn_finalize: too many channels");
-  gn_finalize_kernel<<<a.batch, 256, smem, (cudaStream_t)stream>>>(a);
+  gn_finalize_kernel<<<dim3(a.batch, split), kGnThreads, smem, (cudaStream_t)stream>>>(a);
   return check_launch("gn_finalize_kernel");
 }
 
@@ -425,8 +471,15 @@ extern "C" int pdr_attention_pool(int batch, int P, int K, int C, const float *S
                                   int ldo, void *stream) {
   PDR_REQUIRE(batch > 0 && P > 0 && K > 0 && C > 0 && S && V && sc && sh && out, "attention_pool: bad arguments");
   const long long total = (long long)batch * P * C;
-  attention_pool_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh, ld_scsh,
-                                                                             counts, out, ldo, total);
+  if (K == 32)
+    attention_pool_kernel<32><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
+                                                                                   ld_scsh, counts, out, ldo, total);
+  else if (K == 8)
+    attention_pool_kernel<8><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
+                                                                                  ld_scsh, counts, out, ldo, total);
+  else
+    attention_pool_kernel<0><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
+                                                                                  ld_scsh, counts, out, ldo, total);
   return check_launch("attention_pool_kernel");
 }
 
@@ -435,9 +488,10 @@ extern "C" int pdr_group_ball(int batch, int n, int P, int K, int C, const float
                               float *out, int ldo, void *stream) {
   PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && C >= 0 && ldo >= C + 9, "group_ball: bad sizes");
   PDR_REQUIRE((feat || C == 0) && xyz && centres && idx && out, "group_ball: null pointer");
-  const long long total = (long long)batch * P * K * ldo;
-  group_ball_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, K, C, feat, ldf, xyz, centres, idx,
-                                                                         counts, fill_missing, out, ldo, total);
+  const long long rows = (long long)batch * P * K;
+  PDR_REQUIRE(rows < (1ll << 31) && ldo - C <= 32, "group_ball: too many rows or pad too wide");
+  group_ball_kernel<<<(unsigned)((rows + 7) / 8), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      n, P, K, C, feat, ldf, xyz, centres, idx, counts, fill_missing, out, ldo, (int)rows);
   return check_launch("group_ball_kernel");
 }
 
@@ -446,9 +500,10 @@ extern "C" int pdr_group_knn(int batch, int n, int P, int K, int C, const float 
                              void *stream) {
   PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && C >= 0 && ldo >= C + 11, "group_knn: bad sizes");
   PDR_REQUIRE((feat || C == 0) && y && x && idx && dists && out, "group_knn: null pointer");
-  const long long total = (long long)batch * P * K * ldo;
-  group_knn_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, K, C, feat, ldf, y, x, idx, dists, out,
-                                                                        ldo, total);
+  const long long rows = (long long)batch * P * K;
+  PDR_REQUIRE(rows < (1ll << 31) && ldo - C <= 32, "group_knn: too many rows or pad too wide");
+  group_knn_kernel<<<(unsigned)((rows + 7) / 8), dim3(32, 8), 0, (cudaStream_t)stream>>>(n, P, K, C, feat, ldf, y, x, idx,
+                                                                                          dists, out, ldo, (int)rows);
   return check_launch("group_knn_kernel");
 }
 
