@@ -43,7 +43,8 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=32, help="shapes per GPU")
     p.add_argument("--e2e-steps", type=int, default=50)
-    p.add_argument("--cpu-batch", type=int, default=2, help="shapes per step of the CPU arm (bounded sample)")
+    p.add_argument("--cpu-batch", type=int, default=1, help="shapes per step of the CPU arm (bounded sample)")
+    p.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = min(cores, 32))")
     p.add_argument("--no-tf32", action="store_true", help="fp32 SIMT GEMMs instead of TF32 tensor cores")
     p.add_argument("--engine", default="fused", choices=["fused", "modules"],
                    help="fused: compiled program of our kernels (fused.py); modules: per-layer torch modules")
@@ -184,6 +185,15 @@ class KernelAccounting:
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the same step through the package's host modules bound to the CPU oracle
 # ------------------------------------------------------------------------------------------------------
+def cpu_threads(requested=0):
+    """Threads for the CPU arm.  Above ~32 threads the many small per-layer CPU kernels of this workload only
+    contend (measured: 128 threads are 10x SLOWER than 8 on the same step), so the arm uses min(cores, 32)."""
+    n = requested if requested > 0 else min(os.cpu_count() or 1, 32)
+    os.environ["OMP_NUM_THREADS"] = str(n)      # before the oracle's libgomp is loaded
+    torch.set_num_threads(n)
+    return n
+
+
 def cpu_step_seconds(batch, steps, warmup):
     """Seconds per warm DDPM step on the host cores (oracle port: C/OpenMP ops + CPU torch for the MLPs)."""
     from tests import common as C
@@ -208,8 +218,7 @@ def cpu_step_seconds(batch, steps, warmup):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    cores = cpu_threads(args.cpu_threads)
     dt = cpu_step_seconds(args.cpu_batch, args.steps, args.warmup)
     value = args.cpu_batch / (T_CHAIN * dt)
     sample = "%d shapes/step x %d warm steps of the same denoise step (oracle C/OpenMP ops + CPU torch MLPs)" % (
@@ -374,12 +383,12 @@ def main():
                     "per_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count()
-        torch.set_num_threads(cores)
+        cores = cpu_threads(args.cpu_threads)
         dt = cpu_step_seconds(args.cpu_batch, 2, 1)
         cpu_baseline = {"value": args.cpu_batch / (T_CHAIN * dt), "unit": "shapes/s", "cores": cores, "kind": "port",
-                        "sample": "%d shapes x 2 warm steps of the same denoise step on the host "
-                                  "(oracle C/OpenMP ops + CPU torch MLPs); %.2f s/step" % (args.cpu_batch, dt)}
+                        "sample": "%d shape(s) x 2 warm steps of the same denoise step on the host "
+                                  "(oracle C/OpenMP ops + CPU torch MLPs, %d threads of %d cores); %.2f s/step"
+                                  % (args.cpu_batch, cores, os.cpu_count() or 0, dt)}
     line = {
         "metric": "ddpm_shapes_per_sec_T1000", "value": value, "unit": "shapes/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
