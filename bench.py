@@ -49,6 +49,7 @@ def parse():
     p.add_argument("--engine", default="fused", choices=["fused", "modules"],
                    help="fused: compiled program of our kernels (fused.py); modules: per-layer torch modules")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--dump-ops", default="", help="write the per-op timing of one eager program replay to this JSON file")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -316,6 +317,9 @@ def main():
         if eng is not None:
             agg = eng.profile()
             agg.pop("torch", None)
+            if args.dump_ops and rank == 0:
+                with open(args.dump_ops, "w") as f:
+                    json.dump(eng.last_profile, f)
             launches = args.steps * (eng.n_kernel_calls + 1)      # program kernels + the fused update, per step
         else:
             with KernelAccounting() as acct:

@@ -35,7 +35,7 @@ constexpr int kMmaWarp = kEpiWarps + kProdWarps;              // 12
 constexpr int kTcTileM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTcTileM * 128;     // 16 KiB
-constexpr int kWResidentBytes = 64 * 1024;
+constexpr int kWResidentBytes = 160 * 1024;   // upper bound; the planner checks what actually fits
 constexpr int kMaxStages = 6;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -179,48 +179,70 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&bar_wready);
     }
-    // chunk sequence of this CTA: items blockIdx.x, +gridDim.x, ... ; nk chunks each
+    // chunk sequence of this CTA: items blockIdx.x, +gridDim.x, ... ; nk chunks each.
+    // The producer loop runs once per 16 KiB chunk in every producer thread, so it is kept lean: item geometry
+    // is cached per cursor and advanced incrementally (no integer division in the common case), global and
+    // shared addresses are running pointers / per-thread constants.
     const int my_items = plan.total_items > (int)blockIdx.x
                              ? (plan.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int my_chunks = my_items * nk;
-    struct Cursor { int item, kc; };
-    auto advance = [&](Cursor &c) { if (++c.kc == nk) { c.kc = 0; c.item += gridDim.x; } };
-    struct Geo { int b, rows_valid, n0; size_t row_base; };
-    auto geo_of = [&](int item) {
-      Geo g;
-      const int tile = item / plan.n_tiles_n;
-      g.n0 = (item % plan.n_tiles_n) * BN;
-      g.b = tile / plan.tiles_per_sample;
-      const int r0 = (tile % plan.tiles_per_sample) * kTcTileM;
-      g.row_base = (size_t)g.b * a.rows_per_sample + r0;
-      g.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
-      return g;
+    const int G = (int)gridDim.x;
+    const bool fast_adv = plan.n_tiles_n == 1 && plan.tiles_per_sample >= G;
+    struct Cur {                 // one (item, K-chunk) position in this CTA's sequence + cached geometry
+      int item, kc, b, tis, n0, rows_valid;
+      const float *pa;           // &A[row_base + arow][chunk*4]
+      const float *pr;           // same for the residual
     };
+    auto locate = [&](Cur &c) {  // full (division) geometry of c.item
+      const int tile = c.item / plan.n_tiles_n;
+      c.n0 = (c.item - tile * plan.n_tiles_n) * BN;
+      c.b = tile / plan.tiles_per_sample;
+      c.tis = tile - c.b * plan.tiles_per_sample;
+    };
+    auto derive = [&](Cur &c) {  // pointers and row count from (b, tis)
+      const int r0 = c.tis * kTcTileM;
+      c.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
+      const size_t row = (size_t)c.b * a.rows_per_sample + r0 + arow;
+      c.pa = a.A + row * a.lda + chunk * 4;
+      c.pr = a.R ? a.R + row * a.ldr + chunk * 4 : nullptr;
+    };
+    auto advance = [&](Cur &c) {
+      if (++c.kc < nk) return;
+      c.kc = 0;
+      c.item += G;
+      if (fast_adv) { c.tis += G; if (c.tis >= plan.tiles_per_sample) { c.tis -= plan.tiles_per_sample; ++c.b; } }
+      else locate(c);
+      derive(c);
+    };
+    const uint32_t sw_off = (uint32_t)(arow * 128 + ((chunk ^ (arow & 7)) << 4));   // row arow+32i: + i*4096
+    const uint32_t raw_off = (uint32_t)(arow * 128 + (chunk << 4));
+    const size_t a_step = (size_t)32 * a.lda, r_step = (size_t)32 * a.ldr;
+    const size_t w_step = (size_t)32 * a.ldw;
+    Cur ci;
+    ci.item = (int)blockIdx.x; ci.kc = 0;
+    locate(ci); derive(ci);
+
     if (plan.direct) {
       // ---- no prologue: cp.async straight into the swizzled MMA stage, kDirectDepth chunks in flight ----
-      auto issue = [&](const Cursor &c, int stage) {
-        const Geo g = geo_of(c.item);
-        const int k = c.kc * kTcBK + chunk * 4;
-        const bool kin = k < a.K;
-        const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes);
+      auto issue = [&](const Cur &c, int stage) {
+        const int kofs = c.kc * kTcBK;
+        const bool kin = kofs + chunk * 4 < a.K;
+        const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes) + sw_off;
+        const float *src = c.pa + kofs;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int row = arow + 32 * i;
-          const bool ok = kin && row < g.rows_valid;
-          const float *src = ok ? a.A + (g.row_base + row) * a.lda + k : a.A;
-          cp_async16(sa + row * 128 + ((chunk ^ (row & 7)) << 4), src, ok);
+          const bool ok = kin && arow + 32 * i < c.rows_valid;
+          cp_async16(sa + i * 4096, ok ? src + i * a_step : a.A, ok);
         }
         if (!WRES) {
+          const float *wsrc = a.W + (size_t)(c.n0 + arow) * a.ldw + kofs + chunk * 4;
 #pragma unroll
           for (int i = 0; i < kWLoads; ++i) {
-            const int n = arow + 32 * i;
-            const bool ok = kin && g.n0 + n < a.N;
-            const float *src = ok ? a.W + (size_t)(g.n0 + n) * a.ldw + k : a.W;
-            cp_async16(sa + kATileBytes + n * 128 + ((chunk ^ (n & 7)) << 4), src, ok);
+            const bool ok = kin && c.n0 + arow + 32 * i < a.N;
+            cp_async16(sa + kATileBytes + i * 4096, ok ? wsrc + i * w_step : a.W, ok);
           }
         }
       };
-      Cursor ci{(int)blockIdx.x, 0};
       int issued = 0, stage_i = 0, phase_i = 0, stage_c = 0;
       for (int d = 0; d < kDirectDepth; ++d) {
         if (issued < my_chunks) {
@@ -247,75 +269,67 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     } else {
       // ---- prologue needed: cp.async into a raw ring (kRawDepth in flight), then each thread transforms
       //      exactly the 16-byte pieces it copied (no cross-thread hazard) into the MMA ring ----
-      auto issue_raw = [&](const Cursor &c, int slot) {
-        const Geo g = geo_of(c.item);
-        const int k = c.kc * kTcBK + chunk * 4;
-        const bool kin = k < a.K;
-        const uint32_t sr = smem_u32(s_raw + (size_t)slot * plan.raw_bytes);
+      auto issue_raw = [&](const Cur &c, int slot) {
+        const int kofs = c.kc * kTcBK;
+        const bool kin = kofs + chunk * 4 < a.K;
+        const uint32_t sr = smem_u32(s_raw + (size_t)slot * plan.raw_bytes) + raw_off;
+        const float *src = c.pa + kofs;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int row = arow + 32 * i;
-          const bool ok = kin && row < g.rows_valid;
-          const size_t off = (g.row_base + row);
-          cp_async16(sr + row * 128 + (chunk << 4), ok ? a.A + off * a.lda + k : a.A, ok);
-          if (a.R) cp_async16(sr + kATileBytes + row * 128 + (chunk << 4), ok ? a.R + off * a.ldr + k : a.R, ok);
+          const bool ok = kin && arow + 32 * i < c.rows_valid;
+          cp_async16(sr + i * 4096, ok ? src + i * a_step : a.A, ok);
+          if (a.R) cp_async16(sr + kATileBytes + i * 4096, ok ? c.pr + kofs + i * r_step : a.R, ok);
         }
       };
-      Cursor ci{(int)blockIdx.x, 0}, cc{(int)blockIdx.x, 0};
-      int issued = 0, stage = 0, phase = 0;
+      Cur cc = ci;               // completion cursor trails the issue cursor by kRawDepth chunks
+      int issued = 0, stage = 0, phase = 0, slot = 0;
       for (int d = 0; d < kRawDepth; ++d) {
         if (issued < my_chunks) { issue_raw(ci, d); advance(ci); ++issued; }
         cp_async_commit();
       }
       for (int done = 0; done < my_chunks; ++done) {
-        const int slot = done % kRawDepth;
         cp_async_wait<kRawDepth - 1>();
-        const Geo g = geo_of(cc.item);
         const int k = cc.kc * kTcBK + chunk * 4;
         const bool kin = k < a.K;
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = h4;
         if (kin) {
           if (a.pro_mode != PDR_PRO_NONE) {
-            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)g.b * a.ld_scsh + k));
-            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)g.b * a.ld_scsh + k));
+            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)cc.b * a.ld_scsh + k));
+            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)cc.b * a.ld_scsh + k));
           }
-          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)g.b * a.ld_add + k));
+          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)cc.b * a.ld_add + k));
         }
         float4 rw[WRES ? 1 : kWLoads];
         if (!WRES) {
 #pragma unroll
           for (int i = 0; i < kWLoads; ++i) {
-            const int n = arow + 32 * i;
-            rw[i] = (kin && g.n0 + n < a.N) ? __ldg(reinterpret_cast<const float4 *>(a.W + (size_t)(g.n0 + n) * a.ldw + k))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = cc.n0 + arow + 32 * i;
+            rw[i] = (kin && n < a.N) ? __ldg(reinterpret_cast<const float4 *>(a.W + (size_t)n * a.ldw + k))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
-        const uint8_t *sr = s_raw + (size_t)slot * plan.raw_bytes;
-        uint8_t *sa = s_stages + (size_t)stage * kStageBytes;
+        const uint8_t *sr = s_raw + (size_t)slot * plan.raw_bytes + raw_off;
+        uint8_t *sa = s_stages + (size_t)stage * kStageBytes + sw_off;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int row = arow + 32 * i;
-          float4 v = *reinterpret_cast<const float4 *>(sr + row * 128 + (chunk << 4));
-          if (kin && row < g.rows_valid) {
+          float4 v = *reinterpret_cast<const float4 *>(sr + i * 4096);
+          if (kin && arow + 32 * i < cc.rows_valid) {
             v.x = pro1(a.pro_mode, v.x, s4.x, h4.x) + e4.x; v.y = pro1(a.pro_mode, v.y, s4.y, h4.y) + e4.y;
             v.z = pro1(a.pro_mode, v.z, s4.z, h4.z) + e4.z; v.w = pro1(a.pro_mode, v.w, s4.w, h4.w) + e4.w;
             if (a.R) {
-              const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + row * 128 + (chunk << 4));
+              const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + i * 4096);
               v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
             v = tf32x4(v);
           } else {
             v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          *reinterpret_cast<float4 *>(sa + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+          *reinterpret_cast<float4 *>(sa + i * 4096) = v;
         }
         if (!WRES) {
 #pragma unroll
-          for (int i = 0; i < kWLoads; ++i) {
-            const int n = arow + 32 * i;
-            *reinterpret_cast<float4 *>(sa + kATileBytes + n * 128 + ((chunk ^ (n & 7)) << 4)) = tf32x4(rw[i]);
-          }
+          for (int i = 0; i < kWLoads; ++i) *reinterpret_cast<float4 *>(sa + kATileBytes + i * 4096) = tf32x4(rw[i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&bar_full[stage]);
@@ -323,6 +337,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         advance(cc);
         if (issued < my_chunks) { issue_raw(ci, slot); advance(ci); ++issued; }   // the slot just consumed is free
         cp_async_commit();
+        if (++slot == kRawDepth) slot = 0;
       }
     }
   } else if (warp == kMmaWarp) {
@@ -413,19 +428,24 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
             q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
           }
         } else {
-          // rows (wrow0 + r) / div share one broadcast row; div divides the sample's row count, so the
-          // group index advances every `div` rows
+          // rows (wrow0 + r) / div share one broadcast row (the query term of AttentionModule, expanded over
+          // the K neighbours): load it once per group of rows instead of once per row
           const float *rp = a.rowadd + radd_g0 * a.ld_rowadd + (nin ? n : 0);
-          int rem = radd_rem0;
-#pragma unroll 4
-          for (int r = 0; r < wrows; ++r) {
-            float t = st[r * 33] + bias_n + __ldg(rp);
-            t = nin ? t : 0.f;
-            if (nstore) *cp = t;
-            cp += ldc;
-            if (++rem == a.rowadd_div) { rem = 0; rp += a.ld_rowadd; }
-            const float p = fmaxf(t, 0.f);
-            q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
+          int r = 0, rem = radd_rem0;
+          while (r < wrows) {
+            const float cur = bias_n + (nin ? __ldg(rp) : 0.f);
+            const int rend = min(wrows, r + (a.rowadd_div - rem));
+#pragma unroll 8
+            for (; r < rend; ++r) {
+              float t = st[r * 33] + cur;
+              t = nin ? t : 0.f;
+              if (nstore) *cp = t;
+              cp += ldc;
+              const float p = fmaxf(t, 0.f);
+              q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
+            }
+            rem = 0;
+            rp += a.ld_rowadd;
           }
         }
         __syncwarp();
@@ -457,6 +477,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   }
 }
 
+constexpr int kPlanDoesNotFit = 12345;
+
 template <int BN, bool WRES>
 int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   TcPlan plan;
@@ -485,7 +507,11 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     smem = fixed + (size_t)stages * stage;
     planned = true;
   }
-  if (!planned) { set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N); return PDR_ERR_UNSUPPORTED; }
+  if (!planned) {
+    if (WRES) return kPlanDoesNotFit;   // caller retries with streamed weights
+    set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N);
+    return PDR_ERR_UNSUPPORTED;
+  }
   auto kern = gemm_tf32_persistent<BN, WRES>;
   static bool configured = false;
   if (!configured) {
@@ -502,7 +528,11 @@ template <int BN>
 int dispatch_wres(const PdrGemmArgs &a, cudaStream_t stream) {
   const int nk = ceil_div(a.K, kTcBK);
   const bool wres = ceil_div(a.N, BN) == 1 && (size_t)nk * BN * 128 <= (size_t)kWResidentBytes;
-  return wres ? launch_tc<BN, true>(a, stream) : launch_tc<BN, false>(a, stream);
+  if (wres) {
+    const int rc = launch_tc<BN, true>(a, stream);
+    if (rc != kPlanDoesNotFit) return rc;
+  }
+  return launch_tc<BN, false>(a, stream);
 }
 
 }  // namespace

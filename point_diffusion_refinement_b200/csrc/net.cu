@@ -325,32 +325,49 @@ attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds,
   out[bp * ldo + c] = num / den;
 }
 
-// Ball-query grouping.  block = (32 lanes over the output columns, 8 rows): the neighbour index, the
-// centre and the validity flag are loaded once per row, the feature row is copied with coalesced loads and
-// stores, and there is no 64-bit division anywhere.
+// Ball-query grouping.  block = (32 lanes over the output columns, 8 warps); every warp assembles kGbRows
+// consecutive rows at a time so that their index -> feature-row -> store chains overlap.  The neighbour index,
+// the centre and the validity flag are loaded once per row; no 64-bit division anywhere.
+constexpr int kGbRows = 4;
 __global__ void __launch_bounds__(256)
 group_ball_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int ldf,
                   const float *__restrict__ xyz, const float *__restrict__ centres, const int *__restrict__ idx,
                   const int *__restrict__ counts, int fill_missing, float *__restrict__ out, int ldo, int rows) {
-  const int row = blockIdx.x * 8 + threadIdx.y;          // (b*P + p)*K + k
-  if (row >= rows) return;
-  const int bp = row / K;
-  const int b = bp / P;
-  const int src = __ldg(idx + row);
-  const bool missing = fill_missing && counts && __ldg(counts + bp) == 0;
-  const float *frow = feat + ((size_t)b * n + src) * ldf;
-  float *orow = out + (size_t)row * ldo;
-  for (int c = threadIdx.x; c < C; c += 32) orow[c] = missing ? 0.f : __ldg(frow + c);
+  const int row0 = (blockIdx.x * 8 + threadIdx.y) * kGbRows;          // (b*P + p)*K + k
+  if (row0 >= rows) return;
+  int src[kGbRows], bp[kGbRows];
+  bool missing[kGbRows], on[kGbRows];
+#pragma unroll
+  for (int u = 0; u < kGbRows; ++u) {
+    const int row = row0 + u;
+    on[u] = row < rows;
+    const int rr = on[u] ? row : rows - 1;
+    bp[u] = rr / K;
+    src[u] = __ldg(idx + rr);
+    missing[u] = fill_missing && counts && __ldg(counts + bp[u]) == 0;
+  }
   const int q = threadIdx.x;
+  for (int c = threadIdx.x; c < C; c += 32) {
+    float v[kGbRows];
+#pragma unroll
+    for (int u = 0; u < kGbRows; ++u)
+      v[u] = missing[u] ? 0.f : __ldg(feat + ((size_t)(bp[u] / P) * n + src[u]) * ldf + c);
+#pragma unroll
+    for (int u = 0; u < kGbRows; ++u)
+      if (on[u]) out[(size_t)(row0 + u) * ldo + c] = v[u];
+  }
   if (q < ldo - C) {
-    float v = 0.f;
-    if (q < 9) {
-      const int d = q % 3;
-      const float cen = __ldg(centres + (size_t)bp * 3 + d);
-      const float ab = missing ? cen : __ldg(xyz + ((size_t)b * n + src) * 3 + d);
-      v = q < 3 ? ab - cen : (q < 6 ? ab : cen);
+#pragma unroll
+    for (int u = 0; u < kGbRows; ++u) {
+      float v = 0.f;
+      if (q < 9) {
+        const int d = q % 3;
+        const float cen = __ldg(centres + (size_t)bp[u] * 3 + d);
+        const float ab = missing[u] ? cen : __ldg(xyz + ((size_t)(bp[u] / P) * n + src[u]) * 3 + d);
+        v = q < 3 ? ab - cen : (q < 6 ? ab : cen);
+      }
+      if (on[u]) out[(size_t)(row0 + u) * ldo + C + q] = v;
     }
-    orow[C + q] = v;
   }
 }
 
@@ -490,7 +507,7 @@ extern "C" int pdr_group_ball(int batch, int n, int P, int K, int C, const float
   PDR_REQUIRE((feat || C == 0) && xyz && centres && idx && out, "group_ball: null pointer");
   const long long rows = (long long)batch * P * K;
   PDR_REQUIRE(rows < (1ll << 31) && ldo - C <= 32, "group_ball: too many rows or pad too wide");
-  group_ball_kernel<<<(unsigned)((rows + 7) / 8), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+  group_ball_kernel<<<(unsigned)((rows + 8 * kGbRows - 1) / (8 * kGbRows)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
       n, P, K, C, feat, ldf, xyz, centres, idx, counts, fill_missing, out, ldo, (int)rows);
   return check_launch("group_ball_kernel");
 }

@@ -673,6 +673,7 @@ class FusedDenoiser:
             evs.append((s, e))
         torch.cuda.synchronize(self.dev)
         agg = {}
+        self.last_profile = [dict(info, op=name, ms=s.elapsed_time(e)) for (name, info), (s, e) in zip(self.meta, evs)]
         for (name, info), (s, e) in zip(self.meta, evs):
             d = agg.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
             d["calls"] += 1
