@@ -28,10 +28,10 @@
 namespace pdr {
 namespace {
 
-constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kEpiWarps = 8, kProdWarps = 8;   // 8 epilogue warps: two per TMEM lane quarter, alternating 32-column blocks
 constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
-constexpr int kTcThreads = kEpiThreads + kProdThreads + 32;   // 416
-constexpr int kMmaWarp = kEpiWarps + kProdWarps;              // 12
+constexpr int kTcThreads = kEpiThreads + kProdThreads + 32;   // 544
+constexpr int kMmaWarp = kEpiWarps + kProdWarps;              // 16
 constexpr int kTcTileM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTcTileM * 128;     // 16 KiB
@@ -95,11 +95,16 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool p
   // src-size 0 zero-fills the 16 destination bytes (rows beyond the tile, K tail)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(pred ? 16 : 0) : "memory");
 }
+// the mbarrier receives one arrival from this thread once ALL its earlier cp.async copies have landed; the
+// thread itself does not wait (and, unlike wait_group + fence, is not stalled behind younger copies)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kDirectDepth = 4;   // chunks of cp.async in flight per producer thread, direct mode
+constexpr int kDirectDepth = 3;   // chunks of cp.async in flight per producer thread, direct mode (needs >= 3 stages)
 constexpr int kRawDepth = 3;      // raw ring depth, transform mode
 
 struct TcPlan {
@@ -122,18 +127,21 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2], bar_wready;
+  __shared__ uint64_t bar_rfull[kRawDepth], bar_rempty[kRawDepth];   // raw ring (transform mode)
   __shared__ uint32_t s_tmem_base;
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
   // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
   __shared__ float s_epi[kEpiWarps][32 * 33];
-  __shared__ float s_part[4][BN][4];
+  // the column partials (4 lane quarters x BN x 4 sums) live in the dynamic region and are touched only through
+  // explicit ld/st.shared (a handful of accesses per block), which keeps static shared memory under 48 KB
 
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // layout: [W resident (WRES)] [stages] [epilogue transpose tiles 4 x 32 x 33 f32] [column partials 4 x BN x 4 f32]
+  // layout: [W resident (WRES)] [MMA stages] [raw ring (transform mode)] [column partials 4 x BN x float4]
   uint8_t *s_wres = smem;
   uint8_t *s_stages = smem + (WRES ? (size_t)plan.nk * kBTileBytes : 0);
   uint8_t *s_raw = s_stages + (size_t)plan.stages * kStageBytes;
+  const uint32_t s_part = smem_u32(s_raw + (size_t)kRawDepth * plan.raw_bytes);   // [4][BN] float4
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = plan.stages, nk = plan.nk;
@@ -143,6 +151,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
     mbar_init(&bar_tempty[0], kEpiThreads); mbar_init(&bar_tempty[1], kEpiThreads);
     mbar_init(&bar_wready, kProdThreads);
+    for (int r = 0; r < kRawDepth; ++r) { mbar_init(&bar_rfull[r], kProdThreads / 2); mbar_init(&bar_rempty[r], kProdThreads / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -223,7 +232,10 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     locate(ci); derive(ci);
 
     if (plan.direct) {
-      // ---- no prologue: cp.async straight into the swizzled MMA stage, kDirectDepth chunks in flight ----
+      // ---- no prologue: all 8 producer warps cp.async straight into the swizzled MMA stage.  Completion is
+      //      signalled by cp.async.mbarrier.arrive (no wait_group, no fence: a fence.proxy.async compiles to
+      //      MEMBAR.ALL.CTA, which also waits for the YOUNGER copies in flight and serialised the ring --
+      //      2.5 us per 16 KiB chunk in the previous version).  Depth = number of stages. ----
       auto issue = [&](const Cur &c, int stage) {
         const int kofs = c.kc * kTcBK;
         const bool kin = kofs + chunk * 4 < a.K;
@@ -243,101 +255,121 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           }
         }
       };
-      int issued = 0, stage_i = 0, phase_i = 0, stage_c = 0;
-      for (int d = 0; d < kDirectDepth; ++d) {
-        if (issued < my_chunks) {
-          mbar_wait(&bar_empty[stage_i], (uint32_t)(phase_i ^ 1));
-          issue(ci, stage_i);
-          advance(ci); ++issued;
-          if (++stage_i == S) { stage_i = 0; phase_i ^= 1; }
-        }
-        cp_async_commit();
+      int stage = 0, phase = 0;
+      for (int j = 0; j < my_chunks; ++j) {
+        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
+        issue(ci, stage);
+        cp_async_arrive_noinc(&bar_full[stage]);
+        advance(ci);
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
-      for (int done = 0; done < my_chunks; ++done) {
-        cp_async_wait<kDirectDepth - 1>();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&bar_full[stage_c]);
-        if (++stage_c == S) stage_c = 0;
-        if (issued < my_chunks) {
-          mbar_wait(&bar_empty[stage_i], (uint32_t)(phase_i ^ 1));
-          issue(ci, stage_i);
-          advance(ci); ++issued;
-          if (++stage_i == S) { stage_i = 0; phase_i ^= 1; }
+    } else if (warp < kEpiWarps + kProdWarps / 2) {
+      // ---- transform mode, LOADER half (warps 4..7): raw A (+ residual) into the raw ring, weights (when
+      //      streamed) straight into the MMA stage; never blocks on its own copies ----
+      const int ltid = tid - kEpiThreads;            // 0..127
+      const int lchunk = ltid & 7, lrow = ltid >> 3;  // rows lrow + 16*i, i < 8
+      const uint32_t l_raw = (uint32_t)(lrow * 128 + (lchunk << 4));
+      const uint32_t l_sw = (uint32_t)(lrow * 128 + ((lchunk ^ (lrow & 7)) << 4));     // row lrow+16i: (row&7) is lrow&7
+      Cur cl;
+      cl.item = (int)blockIdx.x; cl.kc = 0;
+      auto derive_l = [&](Cur &c) {
+        const int r0 = c.tis * kTcTileM;
+        c.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
+        const size_t row = (size_t)c.b * a.rows_per_sample + r0 + lrow;
+        c.pa = a.A + row * a.lda + lchunk * 4;
+        c.pr = a.R ? a.R + row * a.ldr + lchunk * 4 : nullptr;
+      };
+      locate(cl); derive_l(cl);
+      const size_t a16 = (size_t)16 * a.lda, r16 = (size_t)16 * a.ldr, w16 = (size_t)16 * a.ldw;
+      int stage = 0, phase = 0, slot = 0, rphase = 0;
+      for (int j = 0; j < my_chunks; ++j) {
+        const int kofs = cl.kc * kTcBK;
+        const bool kin = kofs + lchunk * 4 < a.K;
+        mbar_wait(&bar_rempty[slot], (uint32_t)(rphase ^ 1));
+        const uint32_t sr = smem_u32(s_raw + (size_t)slot * plan.raw_bytes) + l_raw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = kin && lrow + 16 * i < cl.rows_valid;
+          cp_async16(sr + i * 2048, ok ? cl.pa + kofs + i * a16 : a.A, ok);
+          if (a.R) cp_async16(sr + kATileBytes + i * 2048, ok ? cl.pr + kofs + i * r16 : a.R, ok);
         }
-        cp_async_commit();
+        cp_async_arrive_noinc(&bar_rfull[slot]);
+        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));      // stage of chunk j is free (also orders the phases of full[])
+        if (!WRES) {
+          const uint32_t sb = smem_u32(s_stages + (size_t)stage * kStageBytes) + kATileBytes + l_sw;
+          const float *wsrc = a.W + (size_t)(cl.n0 + lrow) * a.ldw + kofs + lchunk * 4;
+#pragma unroll
+          for (int i = 0; i < BN / 16; ++i) {
+            const bool ok = kin && cl.n0 + lrow + 16 * i < a.N;
+            cp_async16(sb + i * 2048, ok ? wsrc + i * w16 : a.W, ok);
+          }
+        }
+        cp_async_arrive_noinc(&bar_full[stage]);
+        // advance (loader-local geometry)
+        if (++cl.kc == nk) {
+          cl.kc = 0; cl.item += G;
+          if (fast_adv) { cl.tis += G; if (cl.tis >= plan.tiles_per_sample) { cl.tis -= plan.tiles_per_sample; ++cl.b; } }
+          else locate(cl);
+          derive_l(cl);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
+        if (++slot == kRawDepth) { slot = 0; rphase ^= 1; }
       }
     } else {
-      // ---- prologue needed: cp.async into a raw ring (kRawDepth in flight), then each thread transforms
-      //      exactly the 16-byte pieces it copied (no cross-thread hazard) into the MMA ring ----
-      auto issue_raw = [&](const Cur &c, int slot) {
-        const int kofs = c.kc * kTcBK;
-        const bool kin = kofs + chunk * 4 < a.K;
-        const uint32_t sr = smem_u32(s_raw + (size_t)slot * plan.raw_bytes) + raw_off;
-        const float *src = c.pa + kofs;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool ok = kin && arow + 32 * i < c.rows_valid;
-          cp_async16(sr + i * 4096, ok ? src + i * a_step : a.A, ok);
-          if (a.R) cp_async16(sr + kATileBytes + i * 4096, ok ? c.pr + kofs + i * r_step : a.R, ok);
-        }
-      };
-      Cur cc = ci;               // completion cursor trails the issue cursor by kRawDepth chunks
-      int issued = 0, stage = 0, phase = 0, slot = 0;
-      for (int d = 0; d < kRawDepth; ++d) {
-        if (issued < my_chunks) { issue_raw(ci, d); advance(ci); ++issued; }
-        cp_async_commit();
-      }
-      for (int done = 0; done < my_chunks; ++done) {
-        cp_async_wait<kRawDepth - 1>();
-        const int k = cc.kc * kTcBK + chunk * 4;
+      // ---- transform mode, TRANSFORM half (warps 8..11): raw ring -> GroupNorm/ReLU/embedding/residual ->
+      //      TF32 -> swizzled MMA stage.  Their only outstanding memory traffic is LDS/STS, so the
+      //      fence.proxy.async that publishes the stores to the tensor core is cheap here. ----
+      const int ttid = tid - kEpiThreads - kProdThreads / 2;   // 0..127
+      const int tchunk = ttid & 7, trow = ttid >> 3;            // rows trow + 16*i, i < 8
+      const uint32_t t_raw = (uint32_t)(trow * 128 + (tchunk << 4));
+      const uint32_t t_sw = (uint32_t)(trow * 128 + ((tchunk ^ (trow & 7)) << 4));
+      Cur ct;
+      ct.item = (int)blockIdx.x; ct.kc = 0;
+      locate(ct);
+      int rows_valid_t = min(kTcTileM, a.rows_per_sample - ct.tis * kTcTileM);
+      int stage = 0, phase = 0, slot = 0, rphase = 0;
+      for (int j = 0; j < my_chunks; ++j) {
+        const int k = ct.kc * kTcBK + tchunk * 4;
         const bool kin = k < a.K;
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = h4;
         if (kin) {
           if (a.pro_mode != PDR_PRO_NONE) {
-            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)cc.b * a.ld_scsh + k));
-            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)cc.b * a.ld_scsh + k));
+            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)ct.b * a.ld_scsh + k));
+            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)ct.b * a.ld_scsh + k));
           }
-          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)cc.b * a.ld_add + k));
+          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)ct.b * a.ld_add + k));
         }
-        float4 rw[WRES ? 1 : kWLoads];
-        if (!WRES) {
-#pragma unroll
-          for (int i = 0; i < kWLoads; ++i) {
-            const int n = cc.n0 + arow + 32 * i;
-            rw[i] = (kin && n < a.N) ? __ldg(reinterpret_cast<const float4 *>(a.W + (size_t)n * a.ldw + k))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+        mbar_wait(&bar_rfull[slot], (uint32_t)rphase);
         mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
-        const uint8_t *sr = s_raw + (size_t)slot * plan.raw_bytes + raw_off;
-        uint8_t *sa = s_stages + (size_t)stage * kStageBytes + sw_off;
+        const uint8_t *sr = s_raw + (size_t)slot * plan.raw_bytes + t_raw;
+        uint8_t *sa = s_stages + (size_t)stage * kStageBytes + t_sw;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 v = *reinterpret_cast<const float4 *>(sr + i * 4096);
-          if (kin && arow + 32 * i < cc.rows_valid) {
+        for (int i = 0; i < 8; ++i) {
+          float4 v = *reinterpret_cast<const float4 *>(sr + i * 2048);
+          if (kin && trow + 16 * i < rows_valid_t) {
             v.x = pro1(a.pro_mode, v.x, s4.x, h4.x) + e4.x; v.y = pro1(a.pro_mode, v.y, s4.y, h4.y) + e4.y;
             v.z = pro1(a.pro_mode, v.z, s4.z, h4.z) + e4.z; v.w = pro1(a.pro_mode, v.w, s4.w, h4.w) + e4.w;
             if (a.R) {
-              const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + i * 4096);
+              const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + i * 2048);
               v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
             v = tf32x4(v);
           } else {
             v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          *reinterpret_cast<float4 *>(sa + i * 4096) = v;
-        }
-        if (!WRES) {
-#pragma unroll
-          for (int i = 0; i < kWLoads; ++i) *reinterpret_cast<float4 *>(sa + kATileBytes + i * 4096) = tf32x4(rw[i]);
+          *reinterpret_cast<float4 *>(sa + i * 2048) = v;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&bar_full[stage]);
+        mbar_arrive(&bar_rempty[slot]);
+        if (++ct.kc == nk) {
+          ct.kc = 0; ct.item += G;
+          if (fast_adv) { ct.tis += G; if (ct.tis >= plan.tiles_per_sample) { ct.tis -= plan.tiles_per_sample; ++ct.b; } }
+          else locate(ct);
+          rows_valid_t = min(kTcTileM, a.rows_per_sample - ct.tis * kTcTileM);
+        }
         if (++stage == S) { stage = 0; phase ^= 1; }
-        advance(cc);
-        if (issued < my_chunks) { issue_raw(ci, slot); advance(ci); ++issued; }   // the slot just consumed is free
-        cp_async_commit();
-        if (++slot == kRawDepth) slot = 0;
+        if (++slot == kRawDepth) { slot = 0; rphase ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -370,7 +402,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     }
   } else {
     // =============================== EPILOGUE ================================================
-    const int quarter = warp;                     // TMEM lanes [32*quarter, +32)
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+    const int half = warp >> 2;                   // which of the two warps sharing this lane quarter
     float *s_t = s_epi[warp];
     int acc = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < plan.total_items; item += gridDim.x) {
@@ -387,7 +420,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       mbar_wait(&bar_tfull[acc], (uint32_t)acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= a.ldc_zero_to && n0 + c0 >= a.N) break;      // nothing to write in this or later blocks
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0);
@@ -449,8 +482,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           }
         }
         __syncwarp();
-        if (a.stats) { s_part[quarter][c0 + lane][0] = q0; s_part[quarter][c0 + lane][1] = q1;
-                       s_part[quarter][c0 + lane][2] = q2; s_part[quarter][c0 + lane][3] = q3; }
+        if (a.stats)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part + (uint32_t)((quarter * BN + c0 + lane) * 16)),
+                       "f"(q0), "f"(q1), "f"(q2), "f"(q3) : "memory");
       }
       // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -459,9 +493,15 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         for (int f = tid; f < BN * 4; f += kEpiThreads) {
           const int col = f >> 2, q = f & 3;
-          if (n0 + col < a.N)
-            a.stats[((size_t)tile * a.N + n0 + col) * 4 + q] =
-                s_part[0][col][q] + s_part[1][col][q] + s_part[2][col][q] + s_part[3][col][q];
+          if (n0 + col < a.N) {
+            float p0, p1, p2, p3;
+            const uint32_t pa = s_part + (uint32_t)(f * 4);
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p0) : "r"(pa) : "memory");
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p1) : "r"(pa + BN * 16) : "memory");
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p2) : "r"(pa + 2 * BN * 16) : "memory");
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p3) : "r"(pa + 3 * BN * 16) : "memory");
+            a.stats[((size_t)tile * a.N + n0 + col) * 4 + q] = p0 + p1 + p2 + p3;
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
@@ -488,8 +528,8 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   if (items > 0x7fffffffll) { set_error("gemm_tf32: too many tiles"); return PDR_ERR_INVALID_ARGUMENT; }
   plan.total_items = (int)items;
   plan.nk = ceil_div(a.K, kTcBK);
-  const size_t epi = 0;   // epilogue scratch is static shared memory now
-  const size_t static_smem = (size_t)(kEpiWarps * 32 * 33 + 4 * BN * 4) * sizeof(float) + 256;
+  const size_t epi = (size_t)4 * BN * 16;   // column partials; the transpose tiles are static shared memory
+  const size_t static_smem = (size_t)(kEpiWarps * 32 * 33) * sizeof(float) + 256;
   const size_t stage = WRES ? kATileBytes : kATileBytes + BN * 128;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;
@@ -502,13 +542,13 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     if (fixed + 2 * stage > budget) continue;
     int stages = (int)((budget - fixed) / stage);
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < (direct ? kDirectDepth + 1 : 2)) continue;
+    if (stages < 2) continue;
     plan.stages = stages;
     smem = fixed + (size_t)stages * stage;
     planned = true;
   }
   if (!planned) {
-    if (WRES) return kPlanDoesNotFit;   // caller retries with streamed weights
+    if (WRES || BN > 128) return kPlanDoesNotFit;   // caller retries with streamed weights / narrower column tiles
     set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N);
     return PDR_ERR_UNSUPPORTED;
   }
@@ -538,7 +578,10 @@ int dispatch_wres(const PdrGemmArgs &a, cudaStream_t stream) {
 }  // namespace
 
 int launch_gemm_tf32(const PdrGemmArgs &a, cudaStream_t stream) {
-  if (a.N > 128) return dispatch_wres<256>(a, stream);
+  if (a.N > 128) {
+    const int rc = dispatch_wres<256>(a, stream);
+    if (rc != kPlanDoesNotFit) return rc;
+  }
   if (a.N > 64) return dispatch_wres<128>(a, stream);
   if (a.N > 32) return dispatch_wres<64>(a, stream);
   return dispatch_wres<32>(a, stream);

@@ -110,6 +110,13 @@ def _pack(blocks, device):
     return torch.cat(outs, dim=0).contiguous().to(device)
 
 
+def tf32_round(w):
+    """Round fp32 to the nearest TF32 value (10-bit mantissa, ties away from zero = cvt.rna.tf32.f32), so that the
+    tensor core's truncation of weights copied raw by cp.async is exact."""
+    bits = w.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def _bias(conv, n, device):
     if conv.bias is None:
         return torch.zeros(n, device=device)
@@ -215,6 +222,9 @@ class FusedDenoiser:
             st = Stats(self._zeros(batch * tiles, N, 4), tiles, N, rows_per_sample)
             g.stats = st.t.data_ptr()
         g.use_tf32 = self.use_tf32 if rows_per_sample * batch >= 4096 else 0
+        if g.use_tf32:
+            W = tf32_round(W)
+            g.W = W.data_ptr()
         self.keep += [g, W, bias]
         M = batch * rows_per_sample
         nbytes = 4 * (M * K + M * N + (M * K if R is not None else 0) + N * K +
