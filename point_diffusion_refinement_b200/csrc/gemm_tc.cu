@@ -28,10 +28,14 @@
 namespace pdr {
 namespace {
 
-constexpr int kEpiWarps = 8, kProdWarps = 8;   // 8 epilogue warps: two per TMEM lane quarter, alternating 32-column blocks
-constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
-constexpr int kTcThreads = kEpiThreads + kProdThreads + 32;   // 544
-constexpr int kMmaWarp = kEpiWarps + kProdWarps;              // 16
+constexpr int kEpiWarps = 8, kProdWarps = 8, kLoadWarps = 2;
+// warps [0,8): epilogue, two per TMEM lane quarter, alternating 32-column blocks
+// warps [8,16): producers -- direct mode: cp.async into the MMA ring; transform mode: raw ring -> prologue -> TF32
+// warps [16,18): loaders (transform mode only): raw A/R into the raw ring, streamed W into the MMA ring
+// warp 18: MMA issue
+constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32, kLoadThreads = kLoadWarps * 32;
+constexpr int kTcThreads = kEpiThreads + kProdThreads + kLoadThreads + 32;   // 608
+constexpr int kMmaWarp = kEpiWarps + kProdWarps + kLoadWarps;   // 18
 constexpr int kTcTileM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTcTileM * 128;     // 16 KiB
@@ -147,11 +151,12 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   const int S = plan.stages, nk = plan.nk;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], kProdThreads); mbar_init(&bar_empty[s], 1); }
+    const int full_count = plan.direct ? kProdThreads : kProdThreads + kLoadThreads;
+    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], full_count); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
     mbar_init(&bar_tempty[0], kEpiThreads); mbar_init(&bar_tempty[1], kEpiThreads);
     mbar_init(&bar_wready, kProdThreads);
-    for (int r = 0; r < kRawDepth; ++r) { mbar_init(&bar_rfull[r], kProdThreads / 2); mbar_init(&bar_rempty[r], kProdThreads / 2); }
+    for (int r = 0; r < kRawDepth; ++r) { mbar_init(&bar_rfull[r], kLoadThreads); mbar_init(&bar_rempty[r], kProdThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -174,7 +179,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     const int ptid = tid - kEpiThreads;
     const int chunk = ptid & 7;       // which 16-byte piece of the 128-byte K chunk
     const int arow = ptid >> 3;       // rows arow + 32*i
-    if (WRES) {                        // stage the whole weight matrix once
+    const bool is_loader = warp >= kEpiWarps + kProdWarps;
+    if (WRES && !is_loader) {          // stage the whole weight matrix once
       for (int kc = 0; kc < nk; ++kc) {
         const int k = kc * kTcBK + chunk * 4;
 #pragma unroll
@@ -256,20 +262,21 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         }
       };
       int stage = 0, phase = 0;
-      for (int j = 0; j < my_chunks; ++j) {
+      for (int j = 0; j < (is_loader ? 0 : my_chunks); ++j) {
         mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
         issue(ci, stage);
         cp_async_arrive_noinc(&bar_full[stage]);
         advance(ci);
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
-    } else if (warp < kEpiWarps + kProdWarps / 2) {
-      // ---- transform mode, LOADER half (warps 4..7): raw A (+ residual) into the raw ring, weights (when
-      //      streamed) straight into the MMA stage; never blocks on its own copies ----
-      const int ltid = tid - kEpiThreads;            // 0..127
-      const int lchunk = ltid & 7, lrow = ltid >> 3;  // rows lrow + 16*i, i < 8
+    } else if (is_loader) {
+      // ---- transform mode, LOADERS (warps 16,17): raw A (+ residual) into the raw ring, weights (when streamed)
+      //      straight into the MMA stage; completion is signalled through cp.async.mbarrier.arrive, so these two
+      //      warps never block on their own copies ----
+      const int ltid = tid - kEpiThreads - kProdThreads;   // 0..63
+      const int lchunk = ltid & 7, lrow = ltid >> 3;        // rows lrow + 8*i, i < 16; (row & 7) == lrow
       const uint32_t l_raw = (uint32_t)(lrow * 128 + (lchunk << 4));
-      const uint32_t l_sw = (uint32_t)(lrow * 128 + ((lchunk ^ (lrow & 7)) << 4));     // row lrow+16i: (row&7) is lrow&7
+      const uint32_t l_sw = (uint32_t)(lrow * 128 + ((lchunk ^ lrow) << 4));
       Cur cl;
       cl.item = (int)blockIdx.x; cl.kc = 0;
       auto derive_l = [&](Cur &c) {
@@ -280,7 +287,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         c.pr = a.R ? a.R + row * a.ldr + lchunk * 4 : nullptr;
       };
       locate(cl); derive_l(cl);
-      const size_t a16 = (size_t)16 * a.lda, r16 = (size_t)16 * a.ldr, w16 = (size_t)16 * a.ldw;
+      const size_t a8 = (size_t)8 * a.lda, r8 = (size_t)8 * a.ldr, w8 = (size_t)8 * a.ldw;
       int stage = 0, phase = 0, slot = 0, rphase = 0;
       for (int j = 0; j < my_chunks; ++j) {
         const int kofs = cl.kc * kTcBK;
@@ -288,10 +295,16 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         mbar_wait(&bar_rempty[slot], (uint32_t)(rphase ^ 1));
         const uint32_t sr = smem_u32(s_raw + (size_t)slot * plan.raw_bytes) + l_raw;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool ok = kin && lrow + 16 * i < cl.rows_valid;
-          cp_async16(sr + i * 2048, ok ? cl.pa + kofs + i * a16 : a.A, ok);
-          if (a.R) cp_async16(sr + kATileBytes + i * 2048, ok ? cl.pr + kofs + i * r16 : a.R, ok);
+        for (int i = 0; i < 16; ++i) {
+          const bool ok = kin && lrow + 8 * i < cl.rows_valid;
+          cp_async16(sr + i * 1024, ok ? cl.pa + kofs + i * a8 : a.A, ok);
+        }
+        if (a.R) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool ok = kin && lrow + 8 * i < cl.rows_valid;
+            cp_async16(sr + kATileBytes + i * 1024, ok ? cl.pr + kofs + i * r8 : a.R, ok);
+          }
         }
         cp_async_arrive_noinc(&bar_rfull[slot]);
         mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));      // stage of chunk j is free (also orders the phases of full[])
@@ -299,13 +312,12 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           const uint32_t sb = smem_u32(s_stages + (size_t)stage * kStageBytes) + kATileBytes + l_sw;
           const float *wsrc = a.W + (size_t)(cl.n0 + lrow) * a.ldw + kofs + lchunk * 4;
 #pragma unroll
-          for (int i = 0; i < BN / 16; ++i) {
-            const bool ok = kin && cl.n0 + lrow + 16 * i < a.N;
-            cp_async16(sb + i * 2048, ok ? wsrc + i * w16 : a.W, ok);
+          for (int i = 0; i < BN / 8; ++i) {
+            const bool ok = kin && cl.n0 + lrow + 8 * i < a.N;
+            cp_async16(sb + i * 1024, ok ? wsrc + i * w8 : a.W, ok);
           }
         }
         cp_async_arrive_noinc(&bar_full[stage]);
-        // advance (loader-local geometry)
         if (++cl.kc == nk) {
           cl.kc = 0; cl.item += G;
           if (fast_adv) { cl.tis += G; if (cl.tis >= plan.tiles_per_sample) { cl.tis -= plan.tiles_per_sample; ++cl.b; } }
@@ -316,58 +328,73 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         if (++slot == kRawDepth) { slot = 0; rphase ^= 1; }
       }
     } else {
-      // ---- transform mode, TRANSFORM half (warps 8..11): raw ring -> GroupNorm/ReLU/embedding/residual ->
-      //      TF32 -> swizzled MMA stage.  Their only outstanding memory traffic is LDS/STS, so the
-      //      fence.proxy.async that publishes the stores to the tensor core is cheap here. ----
-      const int ttid = tid - kEpiThreads - kProdThreads / 2;   // 0..127
-      const int tchunk = ttid & 7, trow = ttid >> 3;            // rows trow + 16*i, i < 8
-      const uint32_t t_raw = (uint32_t)(trow * 128 + (tchunk << 4));
-      const uint32_t t_sw = (uint32_t)(trow * 128 + ((tchunk ^ (trow & 7)) << 4));
+      // ---- transform mode, TRANSFORMERS (warps 8..15): raw ring -> GroupNorm/ReLU/embedding/residual -> TF32 ->
+      //      swizzled MMA stage.  This loop bounds every GEMM with a prologue, so it is kept to ~6 instructions
+      //      per element: both prologue flavours are one clamp-fma-clamp
+      //          y = max(fma(max(x, lo1), sc, sh), lo2) + e (+ r)
+      //      with (lo1, lo2) = (-inf, 0) for GN->ReLU, (0, -inf) for ReLU->GN, (-inf, -inf) for none; rows beyond
+      //      the tile and the K tail need no test (the loaders zero-filled them, sc/sh/e default to 1/0/0 there,
+      //      rows are independent in the MMA and the epilogue never reads the padding rows).  sc/sh/e of the NEXT
+      //      chunk are fetched before the current one is processed. ----
+      const uint32_t t_raw = (uint32_t)(arow * 128 + (chunk << 4));          // rows arow + 32*i, i < 4
+      const uint32_t t_sw = sw_off;
+      const float ninf = __int_as_float(0xff800000);
+      const float lo1 = a.pro_mode == PDR_PRO_RELU_GN ? 0.f : ninf;
+      const float lo2 = a.pro_mode == PDR_PRO_GN_RELU ? 0.f : ninf;
       Cur ct;
       ct.item = (int)blockIdx.x; ct.kc = 0;
       locate(ct);
-      int rows_valid_t = min(kTcTileM, a.rows_per_sample - ct.tis * kTcTileM);
+      auto fetch = [&](const Cur &c, float4 &s4, float4 &h4, float4 &e4) {
+        const int k = c.kc * kTcBK + chunk * 4;
+        s4 = make_float4(1.f, 1.f, 1.f, 1.f); h4 = make_float4(0.f, 0.f, 0.f, 0.f); e4 = h4;
+        if (k < a.K) {
+          if (a.pro_mode != PDR_PRO_NONE) {
+            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)c.b * a.ld_scsh + k));
+            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)c.b * a.ld_scsh + k));
+          }
+          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)c.b * a.ld_add + k));
+        }
+      };
+      float4 s4, h4, e4;
+      if (my_chunks > 0) fetch(ct, s4, h4, e4);
       int stage = 0, phase = 0, slot = 0, rphase = 0;
       for (int j = 0; j < my_chunks; ++j) {
-        const int k = ct.kc * kTcBK + tchunk * 4;
-        const bool kin = k < a.K;
-        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = h4;
-        if (kin) {
-          if (a.pro_mode != PDR_PRO_NONE) {
-            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)ct.b * a.ld_scsh + k));
-            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)ct.b * a.ld_scsh + k));
-          }
-          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)ct.b * a.ld_add + k));
+        if (++ct.kc == nk) {                                    // cursor of chunk j + 1
+          ct.kc = 0; ct.item += G;
+          if (fast_adv) { ct.tis += G; if (ct.tis >= plan.tiles_per_sample) { ct.tis -= plan.tiles_per_sample; ++ct.b; } }
+          else locate(ct);
         }
+        float4 ns4 = s4, nh4 = h4, ne4 = e4;
+        if (j + 1 < my_chunks) fetch(ct, ns4, nh4, ne4);
         mbar_wait(&bar_rfull[slot], (uint32_t)rphase);
         mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
         const uint8_t *sr = s_raw + (size_t)slot * plan.raw_bytes + t_raw;
         uint8_t *sa = s_stages + (size_t)stage * kStageBytes + t_sw;
+        auto xf = [&](float x, float sc, float sh, float e) {
+          return fmaxf(fmaf(fmaxf(x, lo1), sc, sh), lo2) + e;
+        };
+        if (a.R) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 v = *reinterpret_cast<const float4 *>(sr + i * 2048);
-          if (kin && trow + 16 * i < rows_valid_t) {
-            v.x = pro1(a.pro_mode, v.x, s4.x, h4.x) + e4.x; v.y = pro1(a.pro_mode, v.y, s4.y, h4.y) + e4.y;
-            v.z = pro1(a.pro_mode, v.z, s4.z, h4.z) + e4.z; v.w = pro1(a.pro_mode, v.w, s4.w, h4.w) + e4.w;
-            if (a.R) {
-              const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + i * 2048);
-              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-            }
-            v = tf32x4(v);
-          } else {
-            v = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 4; ++i) {
+            float4 v = *reinterpret_cast<const float4 *>(sr + i * 4096);
+            const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + i * 4096);
+            v.x = xf(v.x, s4.x, h4.x, e4.x) + r.x; v.y = xf(v.y, s4.y, h4.y, e4.y) + r.y;
+            v.z = xf(v.z, s4.z, h4.z, e4.z) + r.z; v.w = xf(v.w, s4.w, h4.w, e4.w) + r.w;
+            *reinterpret_cast<float4 *>(sa + i * 4096) = tf32x4(v);
           }
-          *reinterpret_cast<float4 *>(sa + i * 2048) = v;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 v = *reinterpret_cast<const float4 *>(sr + i * 4096);
+            v.x = xf(v.x, s4.x, h4.x, e4.x); v.y = xf(v.y, s4.y, h4.y, e4.y);
+            v.z = xf(v.z, s4.z, h4.z, e4.z); v.w = xf(v.w, s4.w, h4.w, e4.w);
+            *reinterpret_cast<float4 *>(sa + i * 4096) = tf32x4(v);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&bar_full[stage]);
         mbar_arrive(&bar_rempty[slot]);
-        if (++ct.kc == nk) {
-          ct.kc = 0; ct.item += G;
-          if (fast_adv) { ct.tis += G; if (ct.tis >= plan.tiles_per_sample) { ct.tis -= plan.tiles_per_sample; ++ct.b; } }
-          else locate(ct);
-          rows_valid_t = min(kTcTileM, a.rows_per_sample - ct.tis * kTcTileM);
-        }
+        s4 = ns4; h4 = nh4; e4 = ne4;
         if (++stage == S) { stage = 0; phase ^= 1; }
         if (++slot == kRawDepth) { slot = 0; rphase ^= 1; }
       }
