@@ -136,7 +136,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
   // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
-  __shared__ float s_epi[kEpiWarps][32 * 33];
+  __shared__ float s_epi[kEpiWarps][32 * 17];
   // the column partials (4 lane quarters x BN x 4 sums) live in the dynamic region and are touched only through
   // explicit ld/st.shared (a handful of accesses per block), which keeps static shared memory under 48 KB
 
@@ -431,92 +431,60 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     // =============================== EPILOGUE ================================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     const int half = warp >> 2;                   // which of the two warps sharing this lane quarter
-    constexpr int CW = BN == 32 ? 16 : 32;   // epilogue block width
-    constexpr int kTs = CW + 1;              // transpose tile stride
     float *s_t = s_epi[warp];
     int acc = 0, acc_phase = 0;
-    // item geometry: divisions only when the item sequence is irregular (several column tiles, or fewer row
-    // tiles per sample than CTAs); the common case advances (b, tile-in-sample) incrementally
-    const int G = (int)gridDim.x;
-    const bool fast_adv = plan.n_tiles_n == 1 && plan.tiles_per_sample >= G;
-    const bool radd_split = a.rowadd && a.rows_per_sample % a.rowadd_div == 0;   // groups never straddle samples
-    const int groups_per_sample = a.rowadd ? a.rows_per_sample / a.rowadd_div : 0;
-    int b = 0, tis = 0, n0 = 0, tile = 0;
-    for (int item = blockIdx.x; item < plan.total_items; item += G) {
-      if (fast_adv && item != (int)blockIdx.x) {
-        tis += G; tile += G;
-        if (tis >= plan.tiles_per_sample) { tis -= plan.tiles_per_sample; ++b; }
-      } else {
-        tile = item / plan.n_tiles_n; n0 = (item - tile * plan.n_tiles_n) * BN;
-        b = tile / plan.tiles_per_sample; tis = tile - b * plan.tiles_per_sample;
-      }
-      const int r0 = tis * kTcTileM;
+    for (int item = blockIdx.x; item < plan.total_items; item += gridDim.x) {
+      const int tile = item / plan.n_tiles_n, n0 = (item % plan.n_tiles_n) * BN;
+      const int b = tile / plan.tiles_per_sample;
+      const int r0 = (tile % plan.tiles_per_sample) * kTcTileM;
       const size_t row_base = (size_t)b * a.rows_per_sample + r0;
       const int rows_valid = min(kTcTileM, a.rows_per_sample - r0);
       const int wrows = max(0, min(32, rows_valid - quarter * 32));   // valid rows among this warp's 32
       const size_t wrow0 = row_base + quarter * 32;                   // first global row of this warp
       size_t radd_g0 = 0;
       int radd_rem0 = 0;
-      if (a.rowadd) {
-        if (radd_split) {
-          const int g = (r0 + quarter * 32) / a.rowadd_div;
-          radd_rem0 = r0 + quarter * 32 - g * a.rowadd_div;
-          radd_g0 = (size_t)b * groups_per_sample + g;
-        } else {
-          radd_g0 = wrow0 / (size_t)a.rowadd_div; radd_rem0 = (int)(wrow0 % (size_t)a.rowadd_div);
-        }
-      }
+      if (a.rowadd) { radd_g0 = wrow0 / (size_t)a.rowadd_div; radd_rem0 = (int)(wrow0 % (size_t)a.rowadd_div); }
       mbar_wait(&bar_tfull[acc], (uint32_t)acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cb = half * CW; cb < BN; cb += 2 * CW) {
-        // the two warps of a lane quarter alternate CW-column blocks: CW = 32 normally, 16 for the narrowest tile
-        // (BN = 32) so that all 8 warps have work there as well
-        if (n0 + cb >= a.ldc_zero_to && n0 + cb >= a.N) break;      // nothing to write in this or later blocks
-        uint32_t v[CW];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= a.ldc_zero_to && n0 + c0 >= a.N) break;      // nothing to write in this or later blocks
+        // the two warps of a lane quarter split every 32-column block 16/16, so that all 8 warps work on narrow
+        // tiles (BN = 32) as well
+        const int cb = c0 + 16 * half;
+        if (n0 + cb >= a.ldc_zero_to && n0 + cb >= a.N) continue;
+        uint32_t v[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cb);
-        if constexpr (CW == 32) {
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr));
-        } else {
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-              : "r"(taddr));
-        }
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // park my row (lane = row) in the transpose tile; the odd stride keeps both phases bank-conflict free
+        // park my row (lane = row) in the transpose tile; stride 17 keeps both phases bank-conflict free
 #pragma unroll
-        for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) s_t[lane * 17 + j] = __uint_as_float(v[j]);
         __syncwarp();
-        // from here on lane = (row group hi, column cl): a store instruction writes 32 / CW row segments of CW
-        // consecutive floats; bias and the broadcast row-add are per column
-        const int hi = lane / CW, cl = lane % CW;
-        constexpr int kRowsPer = CW;                  // rows walked by one lane group (32 rows * CW / 32 lanes)
+        // from here on lane = (row half, column): lanes 0..15 walk rows 0..15, lanes 16..31 rows 16..31 of the
+        // warp's 32; bias and the broadcast row-add are per column, every store instruction writes two 64-byte
+        // row segments
+        const int hi = lane >> 4, cl = lane & 15;
         const int n = n0 + cb + cl;
         const bool nin = n < a.N;
         const bool nstore = nin || n < a.ldc_zero_to;
         const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
         const size_t ldc = (size_t)a.ldc;
-        float *cp = a.C + (wrow0 + kRowsPer * hi) * ldc + n;
-        const float *st = s_t + (kRowsPer * hi) * kTs + cl;
-        const int my_rows = max(0, min(kRowsPer, wrows - kRowsPer * hi));
+        float *cp = a.C + (wrow0 + 16 * hi) * ldc + n;
+        const float *st = s_t + (16 * hi) * 17 + cl;
+        const int my_rows = max(0, min(16, wrows - 16 * hi));
         // the loops below are the hot path of the epilogue warps: keep them branch-free and free of 64-bit
         // index arithmetic (running pointers only)
         if (!a.rowadd) {
 #pragma unroll 8
           for (int r = 0; r < my_rows; ++r) {
-            float t = st[r * kTs] + bias_n;
+            float t = st[r * 17] + bias_n;
             t = nin ? t : 0.f;
             if (nstore) *cp = t;
             cp += ldc;
@@ -526,7 +494,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         } else {
           // rows (wrow0 + r) / div share one broadcast row (the query term of AttentionModule, expanded over
           // the K neighbours): one load per group of rows, issued one group ahead of its use
-          const int first = radd_rem0 + kRowsPer * hi;
+          const int first = radd_rem0 + 16 * hi;
           const int gskip = first / a.rowadd_div;
           int rem = first - gskip * a.rowadd_div;
           const float *rp = a.rowadd + (radd_g0 + gskip) * a.ld_rowadd + (nin ? n : 0);
@@ -539,7 +507,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
             if (nin && rend < my_rows) nxt = __ldg(rp);
 #pragma unroll 8
             for (; r < rend; ++r) {
-              float t = st[r * kTs] + cur;
+              float t = st[r * 17] + cur;
               t = nin ? t : 0.f;
               if (nstore) *cp = t;
               cp += ldc;
@@ -551,10 +519,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         }
         __syncwarp();
         if (a.stats) {
-          if constexpr (CW == 16) {
-            q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-            q2 += __shfl_xor_sync(0xffffffffu, q2, 16); q3 += __shfl_xor_sync(0xffffffffu, q3, 16);
-          }
+          q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+          q2 += __shfl_xor_sync(0xffffffffu, q2, 16); q3 += __shfl_xor_sync(0xffffffffu, q3, 16);
           if (hi == 0)
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part + (uint32_t)((quarter * BN + cb + cl) * 16)),
                          "f"(q0), "f"(q1), "f"(q2), "f"(q3) : "memory");
@@ -603,7 +569,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   plan.total_items = (int)items;
   plan.nk = ceil_div(a.K, kTcBK);
   const size_t epi = (size_t)4 * BN * 16;   // column partials; the transpose tiles are static shared memory
-  const size_t static_smem = (size_t)(kEpiWarps * 32 * 33) * sizeof(float) + 256;
+  const size_t static_smem = (size_t)(kEpiWarps * 32 * 17) * sizeof(float) + 256;
   const size_t stage = WRES ? kATileBytes : kATileBytes + BN * 128;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;

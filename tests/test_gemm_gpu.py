@@ -73,6 +73,8 @@ CASES = [  # B, rows_per_sample, K, N, pro, add, R, rowadd_div
     (2, 1024, 512, 512, 1, True, True, 0),       # residual + wide N: planner falls back to 128-column tiles
     (2, 4096, 172, 128, 1, True, False, 0),      # prologue, weights resident (96 KiB)
     (1, 8192, 332, 588, 0, False, False, 0),     # no prologue, 3 column tiles, streamed weights
+    (3, 640, 44, 64, 2, False, False, 5),        # broadcast row groups that straddle the 16-row epilogue halves
+    (2, 200, 32, 32, 1, True, False, 8),         # narrow tile, ragged rows, row groups of 8
 ]
 
 
