@@ -197,9 +197,8 @@ constexpr int kGnSplit = 4;
 __global__ void __launch_bounds__(kGnThreads)
 gn_finalize_kernel(const PdrGnArgs a) {
   extern __shared__ double s_tot[];                 // [channels in range][3] = weighted sum, sum of squares, count
-  __shared__ double s_red[kGnThreads / 32][32][2];
+  __shared__ double s_red[kGnThreads][2];
   const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cpg = a.gn_channels / a.groups;
   const int gpc = (a.groups + gridDim.y - 1) / gridDim.y;           // groups per CTA
   const int g_lo = min(a.groups, (int)blockIdx.y * gpc), g_hi = min(a.groups, g_lo + gpc);
@@ -208,32 +207,38 @@ gn_finalize_kernel(const PdrGnArgs a) {
   const int c_hi = (blockIdx.y == gridDim.y - 1) ? a.channels : g_hi * cpg;
   const int c_gn_hi = g_hi * cpg;                                   // channels that need statistics: [c_lo, c_gn_hi)
 
+  // accumulate phase: thread = (tile slice, channel), channel fastest, so that all 256 threads read partials even
+  // when this CTA owns only a handful of channels; slices are folded in a fixed order (deterministic)
   int src_off = 0;
   for (int s = 0; s < a.nsrc; ++s) {
     const PdrGnSource src = a.src[s];
     const int v_lo = max(c_lo, src_off), v_hi = min(c_gn_hi, src_off + src.ncols);   // virtual channels of this source
-    for (int v0 = v_lo; v0 < v_hi; v0 += 32) {
-      const int v = v0 + lane;
+    for (int v0 = v_lo; v0 < v_hi; v0 += kGnThreads) {
+      const int ncs = min(kGnThreads, v_hi - v0);
+      int cw = 1;
+      while (cw < ncs) cw <<= 1;                      // channels per slice row, power of two <= 256
+      const int nsl = kGnThreads / cw;                // tile slices
+      const int cl = threadIdx.x & (cw - 1), slice = threadIdx.x / cw;
+      const int v = v0 + cl;
       double sum = 0.0, sq = 0.0;
-      if (v < v_hi) {
+      if (cl < ncs) {
         const float *p = src.stats + ((size_t)b * src.tiles_per_sample * src.ld_stats + src.col0 + (v - src_off)) * 4 +
                          (src.use_relu ? 2 : 0);
-        for (int t = warp; t < src.tiles_per_sample; t += kGnThreads / 32) {
+        for (int t = slice; t < src.tiles_per_sample; t += nsl) {
           const float2 q = *reinterpret_cast<const float2 *>(p + (size_t)t * src.ld_stats * 4);
           sum += (double)q.x;
           sq += (double)q.y;
         }
       }
-      s_red[warp][lane][0] = sum;
-      s_red[warp][lane][1] = sq;
+      s_red[threadIdx.x][0] = sum;
+      s_red[threadIdx.x][1] = sq;
       __syncthreads();
-      if (warp == 0 && v < v_hi) {
+      if (threadIdx.x < ncs) {
         double ts = 0.0, tq = 0.0;
-#pragma unroll
-        for (int w = 0; w < kGnThreads / 32; ++w) { ts += s_red[w][lane][0]; tq += s_red[w][lane][1]; }
-        s_tot[(v - c_lo) * 3 + 0] = (double)src.mult * ts;
-        s_tot[(v - c_lo) * 3 + 1] = (double)src.mult * tq;
-        s_tot[(v - c_lo) * 3 + 2] = (double)src.mult * (double)src.rows;
+        for (int w = 0; w < nsl; ++w) { ts += s_red[w * cw + threadIdx.x][0]; tq += s_red[w * cw + threadIdx.x][1]; }
+        s_tot[(v0 + threadIdx.x - c_lo) * 3 + 0] = (double)src.mult * ts;
+        s_tot[(v0 + threadIdx.x - c_lo) * 3 + 1] = (double)src.mult * tq;
+        s_tot[(v0 + threadIdx.x - c_lo) * 3 + 2] = (double)src.mult * (double)src.rows;
       }
       __syncthreads();
     }
@@ -325,49 +330,51 @@ attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds,
   out[bp * ldo + c] = num / den;
 }
 
-// Ball-query grouping.  block = (32 lanes over the output columns, 8 warps); every warp assembles kGbRows
-// consecutive rows at a time so that their index -> feature-row -> store chains overlap.  The neighbour index,
-// the centre and the validity flag are loaded once per row; no 64-bit division anywhere.
-constexpr int kGbRows = 4;
+// Ball-query grouping.  A warp assembles 32 consecutive output rows: lane u first fetches the neighbour index,
+// centre and validity flag of row u, then the warp walks the 32 * ldo output floats as ONE flat, contiguous span
+// (lane = consecutive floats, every store instruction writes 128 contiguous bytes whatever the row width) and
+// pulls the per-row values from lane u by shuffle.  All loads of an unrolled group are independent, so a lane has
+// several gathers in flight.
+constexpr int kGbRows = 32;    // rows per warp
 __global__ void __launch_bounds__(256)
 group_ball_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int ldf,
                   const float *__restrict__ xyz, const float *__restrict__ centres, const int *__restrict__ idx,
                   const int *__restrict__ counts, int fill_missing, float *__restrict__ out, int ldo, int rows) {
+  const int lane = threadIdx.x;
   const int row0 = (blockIdx.x * 8 + threadIdx.y) * kGbRows;          // (b*P + p)*K + k
   if (row0 >= rows) return;
-  int src[kGbRows], bp[kGbRows];
-  bool missing[kGbRows], on[kGbRows];
-#pragma unroll
-  for (int u = 0; u < kGbRows; ++u) {
-    const int row = row0 + u;
-    on[u] = row < rows;
-    const int rr = on[u] ? row : rows - 1;
-    bp[u] = rr / K;
-    src[u] = __ldg(idx + rr);
-    missing[u] = fill_missing && counts && __ldg(counts + bp[u]) == 0;
-  }
-  const int q = threadIdx.x;
-  for (int c = threadIdx.x; c < C; c += 32) {
-    float v[kGbRows];
-#pragma unroll
-    for (int u = 0; u < kGbRows; ++u)
-      v[u] = missing[u] ? 0.f : __ldg(feat + ((size_t)(bp[u] / P) * n + src[u]) * ldf + c);
-#pragma unroll
-    for (int u = 0; u < kGbRows; ++u)
-      if (on[u]) out[(size_t)(row0 + u) * ldo + c] = v[u];
-  }
-  if (q < ldo - C) {
-#pragma unroll
-    for (int u = 0; u < kGbRows; ++u) {
-      float v = 0.f;
-      if (q < 9) {
-        const int d = q % 3;
-        const float cen = __ldg(centres + (size_t)bp[u] * 3 + d);
-        const float ab = missing[u] ? cen : __ldg(xyz + ((size_t)(bp[u] / P) * n + src[u]) * 3 + d);
-        v = q < 3 ? ab - cen : (q < 6 ? ab : cen);
+  const int nrows = min(kGbRows, rows - row0);
+  const int rr = min(row0 + lane, rows - 1);
+  const int bp_l = rr / K;
+  const int fb_l = (bp_l / P) * n + __ldg(idx + rr);                  // row of the gathered point in feat / xyz
+  const int miss_l = (fill_missing && counts && __ldg(counts + bp_l) == 0) ? 1 : 0;
+  float *obase = out + (size_t)row0 * ldo;
+  const int total = nrows * ldo;
+  int u = 0, col = lane;
+  while (col >= ldo) { col -= ldo; ++u; }
+#pragma unroll 4
+  for (int e = lane; e < kGbRows * ldo; e += 32) {
+    const int uu = min(u, kGbRows - 1);
+    const int fb = __shfl_sync(0xffffffffu, fb_l, uu);
+    const int bp = __shfl_sync(0xffffffffu, bp_l, uu);
+    const int miss = __shfl_sync(0xffffffffu, miss_l, uu);
+    float v = 0.f;
+    if (e < total) {
+      if (col < C) {
+        if (!miss) v = __ldg(feat + (size_t)fb * ldf + col);
+      } else {
+        const int q = col - C;
+        if (q < 9) {
+          const int d = q - 3 * (q / 3);
+          const float cen = __ldg(centres + (size_t)bp * 3 + d);
+          const float ab = miss ? cen : __ldg(xyz + (size_t)fb * 3 + d);
+          v = q < 3 ? ab - cen : (q < 6 ? ab : cen);
+        }
       }
-      if (on[u]) out[(size_t)(row0 + u) * ldo + C + q] = v;
+      obase[e] = v;
     }
+    col += 32;
+    while (col >= ldo) { col -= ldo; ++u; }
   }
 }
 
