@@ -40,7 +40,7 @@ constexpr int kTcTileM = 128;
 constexpr int kTcBK = 32;                       // floats per K chunk = one 128-byte swizzle row
 constexpr int kATileBytes = kTcTileM * 128;     // 16 KiB
 constexpr int kWResidentBytes = 160 * 1024;   // upper bound; the planner checks what actually fits
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 10;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -109,7 +109,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kDirectDepth = 3;   // chunks of cp.async in flight per producer thread, direct mode (needs >= 3 stages)
-constexpr int kRawDepth = 3;      // raw ring depth, transform mode
 
 struct TcPlan {
   int n_tiles_n;        // column tiles (N / BN rounded up)
@@ -118,20 +117,20 @@ struct TcPlan {
   int nk;               // K chunks
   int stages;           // MMA-layout ring depth
   int direct;           // 1: no prologue -> cp.async lands straight in the MMA ring; 0: raw ring + transform
-  int raw_bytes;        // bytes of one raw stage (A [+ R]) in transform mode
+  int stage_bytes;      // bytes of one ring stage: A tile [+ W tile when streamed] [+ residual tile]
+  int r_off;            // offset of the residual tile inside a stage (transform mode with R)
 };
 
 template <int BN, bool WRES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   constexpr int kBTileBytes = BN * 128;
-  constexpr int kStageBytes = WRES ? kATileBytes : kATileBytes + kBTileBytes;
   constexpr int kWLoads = BN * 8 / kProdThreads;        // float4 of W per producer thread per chunk
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2], bar_wready;
-  __shared__ uint64_t bar_rfull[kRawDepth], bar_rempty[kRawDepth];   // raw ring (transform mode)
+  __shared__ uint64_t bar_rfull[kMaxStages];   // transform mode: raw A (+R) of the stage has landed
   __shared__ uint32_t s_tmem_base;
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
@@ -144,8 +143,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   // layout: [W resident (WRES)] [MMA stages] [raw ring (transform mode)] [column partials 4 x BN x float4]
   uint8_t *s_wres = smem;
   uint8_t *s_stages = smem + (WRES ? (size_t)plan.nk * kBTileBytes : 0);
-  uint8_t *s_raw = s_stages + (size_t)plan.stages * kStageBytes;
-  const uint32_t s_part = smem_u32(s_raw + (size_t)kRawDepth * plan.raw_bytes);   // [4][BN] float4
+  const uint32_t kStageBytes = (uint32_t)plan.stage_bytes;
+  const uint32_t s_part = smem_u32(s_stages + (size_t)plan.stages * kStageBytes);   // [4][BN] float4
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = plan.stages, nk = plan.nk;
@@ -156,7 +155,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
     mbar_init(&bar_tempty[0], kEpiThreads); mbar_init(&bar_tempty[1], kEpiThreads);
     mbar_init(&bar_wready, kProdThreads);
-    for (int r = 0; r < kRawDepth; ++r) { mbar_init(&bar_rfull[r], kLoadThreads); mbar_init(&bar_rempty[r], kProdThreads); }
+    for (int r = 0; r < S; ++r) mbar_init(&bar_rfull[r], kLoadThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -275,7 +274,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       //      warps never block on their own copies ----
       const int ltid = tid - kEpiThreads - kProdThreads;   // 0..63
       const int lchunk = ltid & 7, lrow = ltid >> 3;        // rows lrow + 8*i, i < 16; (row & 7) == lrow
-      const uint32_t l_raw = (uint32_t)(lrow * 128 + (lchunk << 4));
       const uint32_t l_sw = (uint32_t)(lrow * 128 + ((lchunk ^ lrow) << 4));
       Cur cl;
       cl.item = (int)blockIdx.x; cl.kc = 0;
@@ -288,33 +286,31 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       };
       locate(cl); derive_l(cl);
       const size_t a8 = (size_t)8 * a.lda, r8 = (size_t)8 * a.ldr, w8 = (size_t)8 * a.ldw;
-      int stage = 0, phase = 0, slot = 0, rphase = 0;
+      int stage = 0, phase = 0;
       for (int j = 0; j < my_chunks; ++j) {
         const int kofs = cl.kc * kTcBK;
         const bool kin = kofs + lchunk * 4 < a.K;
-        mbar_wait(&bar_rempty[slot], (uint32_t)(rphase ^ 1));
-        const uint32_t sr = smem_u32(s_raw + (size_t)slot * plan.raw_bytes) + l_raw;
+        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));      // the MMAs that read this stage have retired
+        const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes) + l_sw;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const bool ok = kin && lrow + 8 * i < cl.rows_valid;
-          cp_async16(sr + i * 1024, ok ? cl.pa + kofs + i * a8 : a.A, ok);
+          cp_async16(sa + i * 1024, ok ? cl.pa + kofs + i * a8 : a.A, ok);
         }
         if (a.R) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const bool ok = kin && lrow + 8 * i < cl.rows_valid;
-            cp_async16(sr + kATileBytes + i * 1024, ok ? cl.pr + kofs + i * r8 : a.R, ok);
+            cp_async16(sa + plan.r_off + i * 1024, ok ? cl.pr + kofs + i * r8 : a.R, ok);
           }
         }
-        cp_async_arrive_noinc(&bar_rfull[slot]);
-        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));      // stage of chunk j is free (also orders the phases of full[])
+        cp_async_arrive_noinc(&bar_rfull[stage]);
         if (!WRES) {
-          const uint32_t sb = smem_u32(s_stages + (size_t)stage * kStageBytes) + kATileBytes + l_sw;
           const float *wsrc = a.W + (size_t)(cl.n0 + lrow) * a.ldw + kofs + lchunk * 4;
 #pragma unroll
           for (int i = 0; i < BN / 8; ++i) {
             const bool ok = kin && cl.n0 + lrow + 8 * i < a.N;
-            cp_async16(sb + i * 1024, ok ? wsrc + i * w8 : a.W, ok);
+            cp_async16(sa + kATileBytes + i * 1024, ok ? wsrc + i * w8 : a.W, ok);
           }
         }
         cp_async_arrive_noinc(&bar_full[stage]);
@@ -325,7 +321,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           derive_l(cl);
         }
         if (++stage == S) { stage = 0; phase ^= 1; }
-        if (++slot == kRawDepth) { slot = 0; rphase ^= 1; }
       }
     } else {
       // ---- transform mode, TRANSFORMERS (warps 8..15): raw ring -> GroupNorm/ReLU/embedding/residual -> TF32 ->
@@ -336,8 +331,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       //      the tile and the K tail need no test (the loaders zero-filled them, sc/sh/e default to 1/0/0 there,
       //      rows are independent in the MMA and the epilogue never reads the padding rows).  sc/sh/e of the NEXT
       //      chunk are fetched before the current one is processed. ----
-      const uint32_t t_raw = (uint32_t)(arow * 128 + (chunk << 4));          // rows arow + 32*i, i < 4
-      const uint32_t t_sw = sw_off;
+      const uint32_t t_sw = sw_off;                                          // rows arow + 32*i, i < 4
       const float ninf = __int_as_float(0xff800000);
       const float lo1 = a.pro_mode == PDR_PRO_RELU_GN ? 0.f : ninf;
       const float lo2 = a.pro_mode == PDR_PRO_GN_RELU ? 0.f : ninf;
@@ -357,7 +351,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       };
       float4 s4, h4, e4;
       if (my_chunks > 0) fetch(ct, s4, h4, e4);
-      int stage = 0, phase = 0, slot = 0, rphase = 0;
+      int stage = 0, phase = 0;
       for (int j = 0; j < my_chunks; ++j) {
         if (++ct.kc == nk) {                                    // cursor of chunk j + 1
           ct.kc = 0; ct.item += G;
@@ -366,10 +360,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         }
         float4 ns4 = s4, nh4 = h4, ne4 = e4;
         if (j + 1 < my_chunks) fetch(ct, ns4, nh4, ne4);
-        mbar_wait(&bar_rfull[slot], (uint32_t)rphase);
-        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
-        const uint8_t *sr = s_raw + (size_t)slot * plan.raw_bytes + t_raw;
+        mbar_wait(&bar_rfull[stage], (uint32_t)phase);
+        // in place: the loaders land raw A (and R) at the swizzled position the tensor core expects, so every
+        // thread rewrites exactly the 16-byte pieces it read
         uint8_t *sa = s_stages + (size_t)stage * kStageBytes + t_sw;
+        const uint8_t *sr = sa;
         auto xf = [&](float x, float sc, float sh, float e) {
           return fmaxf(fmaf(fmaxf(x, lo1), sc, sh), lo2) + e;
         };
@@ -377,7 +372,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float4 v = *reinterpret_cast<const float4 *>(sr + i * 4096);
-            const float4 r = *reinterpret_cast<const float4 *>(sr + kATileBytes + i * 4096);
+            const float4 r = *reinterpret_cast<const float4 *>(sr + plan.r_off + i * 4096);
             v.x = xf(v.x, s4.x, h4.x, e4.x) + r.x; v.y = xf(v.y, s4.y, h4.y, e4.y) + r.y;
             v.z = xf(v.z, s4.z, h4.z, e4.z) + r.z; v.w = xf(v.w, s4.w, h4.w, e4.w) + r.w;
             *reinterpret_cast<float4 *>(sa + i * 4096) = tf32x4(v);
@@ -393,10 +388,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&bar_full[stage]);
-        mbar_arrive(&bar_rempty[slot]);
         s4 = ns4; h4 = nh4; e4 = ne4;
         if (++stage == S) { stage = 0; phase ^= 1; }
-        if (++slot == kRawDepth) { slot = 0; rphase ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -604,15 +597,17 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   plan.nk = ceil_div(a.K, kTcBK);
   const size_t epi = (size_t)4 * BN * 16;   // column partials; the transpose tiles are static shared memory
   const size_t static_smem = (size_t)(kEpiWarps * 32 * 33) * sizeof(float) + 256;
-  const size_t stage = WRES ? kATileBytes : kATileBytes + BN * 128;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;
   bool planned = false;
-  // prefer the direct (no-transform) producer when the GEMM has no prologue and depth+1 stages fit
+  // prefer the direct (no-transform) producer when the GEMM has no prologue
   for (int direct = (a.pro_mode == PDR_PRO_NONE && !a.add && !a.R) ? 1 : 0; direct >= 0 && !planned; --direct) {
     plan.direct = direct;
-    plan.raw_bytes = direct ? 0 : kATileBytes * (a.R ? 2 : 1);
-    const size_t fixed = 1024 + epi + (WRES ? (size_t)plan.nk * BN * 128 : 0) + (size_t)kRawDepth * plan.raw_bytes;
+    const size_t w_tile = WRES ? 0 : (size_t)BN * 128;
+    const size_t stage = kATileBytes + w_tile + ((!direct && a.R) ? kATileBytes : 0);
+    plan.stage_bytes = (int)stage;
+    plan.r_off = (int)(kATileBytes + w_tile);
+    const size_t fixed = 1024 + epi + (WRES ? (size_t)plan.nk * BN * 128 : 0);
     if (fixed + 2 * stage > budget) continue;
     int stages = (int)((budget - fixed) / stage);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -641,7 +636,10 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
 template <int BN>
 int dispatch_wres(const PdrGemmArgs &a, cudaStream_t stream) {
   const int nk = ceil_div(a.K, kTcBK);
-  const bool wres = ceil_div(a.N, BN) == 1 && (size_t)nk * BN * 128 <= (size_t)kWResidentBytes;
+  // resident weights pay off once a CTA reuses them over several row tiles; with about one tile per CTA the
+  // up-front staging is pure latency and streaming (overlapped with the MMAs) wins
+  const long long row_tiles = (long long)a.batch * ceil_div(a.rows_per_sample, kTcTileM);
+  const bool wres = ceil_div(a.N, BN) == 1 && (size_t)nk * BN * 128 <= (size_t)kWResidentBytes && row_tiles > kNumSMs;
   if (wres) {
     const int rc = launch_tc<BN, true>(a, stream);
     if (rc != kPlanDoesNotFit) return rc;

@@ -221,7 +221,7 @@ class FusedDenoiser:
             tiles = (rows_per_sample + self.tile_rows - 1) // self.tile_rows
             st = Stats(self._zeros(batch * tiles, N, 4), tiles, N, rows_per_sample)
             g.stats = st.t.data_ptr()
-        g.use_tf32 = self.use_tf32 if rows_per_sample * batch >= 4096 else 0
+        g.use_tf32 = self.use_tf32 if rows_per_sample * batch >= 512 else 0
         if g.use_tf32:
             W = tf32_round(W)
             g.W = W.data_ptr()
