@@ -101,6 +101,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool p
 }
 // the mbarrier receives one arrival from this thread once ALL its earlier cp.async copies have landed; the
 // thread itself does not wait (and, unlike wait_group + fence, is not stalled behind younger copies)
+__device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void *src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -246,17 +249,35 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         const bool kin = kofs + chunk * 4 < a.K;
         const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes) + sw_off;
         const float *src = c.pa + kofs;
+        // interior chunks (full rows, full K chunk, full column tile) take a predicate-free path: the copy loops
+        // are what the producer warps spend their issue slots on
+        // (K tail: this thread's 16-byte piece is either wholly inside K or wholly zero-filled)
+        const int ksz = kin ? 16 : 0;
+        if (c.rows_valid == kTcTileM) {
+          const float *p = kin ? src : a.A;
+          const size_t st = kin ? a_step : 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool ok = kin && arow + 32 * i < c.rows_valid;
-          cp_async16(sa + i * 4096, ok ? src + i * a_step : a.A, ok);
+          for (int i = 0; i < 4; ++i) { cp_async16_sz(sa + i * 4096, p, ksz); p += st; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool ok = kin && arow + 32 * i < c.rows_valid;
+            cp_async16(sa + i * 4096, ok ? src + i * a_step : a.A, ok);
+          }
         }
         if (!WRES) {
           const float *wsrc = a.W + (size_t)(c.n0 + arow) * a.ldw + kofs + chunk * 4;
+          if (c.n0 + BN <= a.N) {
+            const float *p = kin ? wsrc : a.W;
+            const size_t st = kin ? w_step : 0;
 #pragma unroll
-          for (int i = 0; i < kWLoads; ++i) {
-            const bool ok = kin && c.n0 + arow + 32 * i < a.N;
-            cp_async16(sa + kATileBytes + i * 4096, ok ? wsrc + i * w_step : a.W, ok);
+            for (int i = 0; i < kWLoads; ++i) { cp_async16_sz(sa + kATileBytes + i * 4096, p, ksz); p += st; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < kWLoads; ++i) {
+              const bool ok = kin && c.n0 + arow + 32 * i < a.N;
+              cp_async16(sa + kATileBytes + i * 4096, ok ? wsrc + i * w_step : a.W, ok);
+            }
           }
         }
       };
@@ -292,25 +313,49 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         const bool kin = kofs + lchunk * 4 < a.K;
         mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));      // the MMAs that read this stage have retired
         const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes) + l_sw;
+        // interior chunks take a predicate-free path (see the direct producer)
+        const int ksz = kin ? 16 : 0;
+        const bool afull = cl.rows_valid == kTcTileM;
+        if (afull) {
+          const float *src = kin ? cl.pa + kofs : a.A;
+          const size_t st = kin ? a8 : 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool ok = kin && lrow + 8 * i < cl.rows_valid;
-          cp_async16(sa + i * 1024, ok ? cl.pa + kofs + i * a8 : a.A, ok);
-        }
-        if (a.R) {
+          for (int i = 0; i < 16; ++i) { cp_async16_sz(sa + i * 1024, src, ksz); src += st; }
+        } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const bool ok = kin && lrow + 8 * i < cl.rows_valid;
-            cp_async16(sa + plan.r_off + i * 1024, ok ? cl.pr + kofs + i * r8 : a.R, ok);
+            cp_async16(sa + i * 1024, ok ? cl.pa + kofs + i * a8 : a.A, ok);
+          }
+        }
+        if (a.R) {
+          if (afull) {
+            const float *src = kin ? cl.pr + kofs : a.R;
+            const size_t st = kin ? r8 : 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { cp_async16_sz(sa + plan.r_off + i * 1024, src, ksz); src += st; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool ok = kin && lrow + 8 * i < cl.rows_valid;
+              cp_async16(sa + plan.r_off + i * 1024, ok ? cl.pr + kofs + i * r8 : a.R, ok);
+            }
           }
         }
         cp_async_arrive_noinc(&bar_rfull[stage]);
         if (!WRES) {
           const float *wsrc = a.W + (size_t)(cl.n0 + lrow) * a.ldw + kofs + lchunk * 4;
+          if (cl.n0 + BN <= a.N) {
+            const float *src = kin ? wsrc : a.W;
+            const size_t st = kin ? w8 : 0;
 #pragma unroll
-          for (int i = 0; i < BN / 8; ++i) {
-            const bool ok = kin && cl.n0 + lrow + 8 * i < a.N;
-            cp_async16(sa + kATileBytes + i * 1024, ok ? wsrc + i * w8 : a.W, ok);
+            for (int i = 0; i < BN / 8; ++i) { cp_async16_sz(sa + kATileBytes + i * 1024, src, ksz); src += st; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 8; ++i) {
+              const bool ok = kin && cl.n0 + lrow + 8 * i < a.N;
+              cp_async16(sa + kATileBytes + i * 1024, ok ? wsrc + i * w8 : a.W, ok);
+            }
           }
         }
         cp_async_arrive_noinc(&bar_full[stage]);
