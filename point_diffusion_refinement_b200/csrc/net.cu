@@ -449,7 +449,11 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   PDR_REQUIRE(!a.rowadd || a.rowadd_div > 0, "gemm_fused: rowadd_div");
   PDR_REQUIRE(((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.W % 16) == 0 && (!a.R || ((uintptr_t)a.R % 16) == 0),
               "gemm_fused: A/W/R must be 16-byte aligned");
-  if (a.use_tf32) return launch_gemm_tf32(a, stream);
+  // the tensor-core epilogue stores float4s: it needs 16-byte aligned output rows (and broadcast rows); anything
+  // else takes the SIMT kernel
+  const bool tc_aligned = a.ldc % 4 == 0 && ((uintptr_t)a.C % 16) == 0 &&
+                          (!a.rowadd || (a.ld_rowadd % 4 == 0 && ((uintptr_t)a.rowadd % 16) == 0));
+  if (a.use_tf32 && tc_aligned) return launch_gemm_tf32(a, stream);
   const int tiles_per_sample = ceil_div(a.rows_per_sample, kTileM);
   const long long tiles = (long long)a.batch * tiles_per_sample;
   PDR_REQUIRE(tiles <= 65535ll * 32768, "gemm_fused: too many tiles");

@@ -5,7 +5,7 @@ from point_diffusion_refinement_b200 import _lib
 from point_diffusion_refinement_b200.fused import tf32_round
 from tests.test_gemm_gpu import _run
 lib = _lib.lib(); dev = "cuda"
-for (B, rps, K, N, pro) in [(32, 2048, 256, 256, 1), (32, 2048, 256, 256, 0)]:
+for (B, rps, K, N, pro) in [(32, 16384, 172, 128, 1), (32, 16384, 172, 428, 0)]:
     M = B * rps
     A = torch.randn(M, K, device=dev); W = tf32_round(torch.randn(N, K, device=dev) / K ** 0.5); bias = torch.randn(N, device=dev)
     sc = torch.ones(B, K, device=dev); sh = torch.zeros(B, K, device=dev)
