@@ -52,6 +52,9 @@ def parse():
     p.add_argument("--dump-ops", default="", help="write the per-op timing of one eager program replay to this JSON file")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-eval-kernels", action="store_true", help="skip the Chamfer / EMD Mpairs/s lines (configs[3])")
+    p.add_argument("--profiler-range", action="store_true",
+                   help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     return p.parse_args()
 
 
@@ -236,6 +239,49 @@ def run_reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------------
+# BASELINE configs[3]: Chamfer / EMD evaluation kernels, Mpairs/s (SURVEY 8d cfg 4)
+# ------------------------------------------------------------------------------------------------------
+def eval_kernel_lines(dev, sm_mhz):
+    """Chamfer_F1 and EMD_distance through the reference-facing modules, B=256.  1 pair = one (i,j) squared
+    distance of one cloud pair, counted once.  Both kernels are FP32-ALU/MUFU bound, not HBM bound
+    (inputs are 6-100 MB, L2 or not is irrelevant), so the fraction quoted is of the FP32 lane rate
+    148 SM x 128 lanes x clk: Chamfer evaluates each pair in both directions (2 evals/pair, ~7 instr each),
+    EMD runs 30 exp-weighted passes per pair."""
+    from point_diffusion_refinement_b200.chamfer_loss_new import Chamfer_F1
+    from point_diffusion_refinement_b200.emd import EMD_distance
+    g = torch.Generator().manual_seed(7)
+    lanes_per_s = 148 * 128 * (sm_mhz or 1965) * 1e6
+    out = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for name, Bq, n, reps in (("chamfer_f1_256x2048x2048", 256, 2048, 10), ("chamfer_f1_256x16384x16384", 256, 16384, 3)):
+        a = (torch.rand(Bq, n, 3, generator=g) * 2 - 1).to(dev); b = (torch.rand(Bq, n, 3, generator=g) * 2 - 1).to(dev)
+        cf = Chamfer_F1()
+        ms = timed(lambda: cf(a, b), reps)
+        pairs = Bq * n * n
+        out[name] = {"ms": ms, "mpairs_per_s": pairs / ms / 1e3, "algorithmic_GBps": Bq * 16 * 2 * n / ms / 1e6,
+                     "pair_evals_per_lane_clk": 2 * pairs / (ms * 1e-3) / lanes_per_s}
+        del a, b
+    a = (torch.rand(256, 2048, 3, generator=g)).to(dev); b = (torch.rand(256, 2048, 3, generator=g)).to(dev)
+    em = EMD_distance()
+    ms = timed(lambda: em(a, b), 3)
+    pairs = 256 * 2048 * 2048
+    out["emd_256x2048x2048"] = {"ms": ms, "mpairs_per_s": pairs / ms / 1e3,
+                                "exp_pair_evals_per_lane_clk": 30 * pairs / (ms * 1e-3) / lanes_per_s}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -300,11 +346,15 @@ def main():
         clocks.start()
         launches0 = _lib.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.profiler_range:
+            torch.cuda.cudart().cudaProfilerStart()
         e0.record()
         for _ in range(args.steps):
             one_step(t); t -= 1
         e1.record()
         sync()
+        if args.profiler_range:
+            torch.cuda.cudart().cudaProfilerStop()
         clock_info = clocks.stop()
         launches = _lib.launch_count - launches0
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -361,6 +411,10 @@ def main():
                    "note": "util.sampling(use_a_precomputed_XT, step=%d): %d reverse steps incl. the cold one, "
                            "pinned-host condition/label/x_T in, generated cloud out; scaled by T/steps" % (Ke, Ke)}
 
+    eval_kernels = None
+    if rank == 0 and not args.no_eval_kernels:
+        with torch.no_grad():
+            eval_kernels = eval_kernel_lines(dev, clock_info.get("sm_mhz"))
     if rank != 0:
         return
     value = world * B / (T_CHAIN * ms_per_step / 1e3)
@@ -385,6 +439,14 @@ def main():
                     "share_of_step": d["ms"] / ms_per_step,
                     "own_kernels_share_of_step": own_ms / ms_per_step,
                     "per_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}}
+    if roofline:
+        # dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), not measured live
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            roofline["traffic"] = tr[roofline["kernel"]]["dram_bytes_per_launch"]
+            roofline["traffic_source"] = tr[roofline["kernel"]]["source"]
+        except Exception:
+            pass
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = cpu_threads(args.cpu_threads)
@@ -404,7 +466,7 @@ def main():
                    "l2": "per-step activation working set (>1 GB at B=32) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": "dp%d: shapes sharded by rank, no collective inside the chain, one final all_gather" % world},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info, "e2e": e2e,
-        "gpu_launches": launches,
+        "gpu_launches": launches, "eval_kernels": eval_kernels,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
