@@ -139,6 +139,16 @@ int pdr_affine_noise_update(size_t count, float *x, const float *eps, float scal
 /* fill with N(0,1) (x_T), same generator. */
 int pdr_normal_fill(size_t count, float *x, uint64_t seed, uint64_t offset, void *stream);
 
+/* point_upsample (pointnet2/models/point_upsample_module.py:4-27), the output stage of the refinement
+ * network.  coarse (b,n,3); displacement (b,n,3*factor) when include_centre != 0, else (b,n,3*(factor+1));
+ * columns 0:3 move the coarse point (mid = coarse + d*out_scale), the remaining reps = factor-1 / factor
+ * triples are grid offsets: up[j] = mid + (d_j*grid_scale)*out_scale with grid_scale = 1/sqrt(factor).
+ * refined (b, n*reps [+ n], 3): point-major copies, then (include_centre) the n mid points;
+ * intermediate (b,n,3) = mid, may be NULL.  Separate roundings (no FMA), bit-identical to the reference. */
+int pdr_point_upsample(int b, int n, int factor, int include_centre, const float *coarse,
+                       const float *displacement, float grid_scale, float out_scale, float *refined,
+                       float *intermediate, void *stream);
+
 /* ================================================================================================
  * Fused denoiser primitives (channels-LAST activations: a tensor (B, P, K, C) is the row-major matrix
  * [B*P*K, ld] with ld >= C, ld % 4 == 0 and pad columns holding zeros).

@@ -190,3 +190,34 @@ def chamfer_f1(xyz1, xyz2, f1_threshold=1e-4):
     f1 = 2 * p1 * p2 / (p1 + p2)
     f1[torch.isnan(f1)] = 0
     return cd_p, cd_t, f1
+
+
+def point_upsample(coarse, displacement, factor, include_centre, out_scale):
+    """pointnet2/models/point_upsample_module.py:4-27 restated with explicit fp32 roundings (numpy float32
+    arithmetic rounds every product and sum separately, as the reference's chain of torch kernels does)."""
+    import numpy as np
+    c = coarse.numpy().astype(np.float32)
+    d = displacement.numpy().astype(np.float32)
+    B, N, _ = c.shape
+    g = np.float32(1 / np.sqrt(factor))            # :8 -- float64 scalar rounded to fp32 by the tensor op
+    s = np.float32(out_scale)
+    mid = c + d[:, :, 0:3] * s                     # :10-11
+    reps = factor - 1 if include_centre else factor
+    grid = (d[:, :, 3:] * g).reshape(B, N, reps, 3)    # :9, :15-18
+    up = (mid[:, :, None, :] + grid * s).reshape(B, -1, 3)   # :20-22
+    refined = np.concatenate([up, mid], axis=1) if include_centre else up   # :23-26
+    return torch.from_numpy(np.ascontiguousarray(refined)), torch.from_numpy(np.ascontiguousarray(mid))
+
+
+def mirror_and_concat(partial, axis=2, num_points=(2048, 3072)):
+    """pointnet2/data_utils/mirror_partial.py:5-37 on the oracle's FPS / gather."""
+    B, N, _ = partial.shape
+    mirrored = partial.clone()
+    mirrored[:, :, axis] = -mirrored[:, :, axis]                                   # :5-9
+    ones = torch.ones(B, N, 1)
+    concat = torch.cat([torch.cat([partial, ones], 2), torch.cat([mirrored, -ones], 2)], 1)   # :28-31
+    out = [concat]
+    for n in num_points:                                                           # :34-36, :11-20
+        idx = furthest_point_sampling(concat[:, :, 0:3].contiguous(), n)
+        out.append(gather_points(concat.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous())
+    return tuple(out)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "pdr_affine_noise_update": [_c_size_t, _ptr, _ptr, _c_float, _c_float, _c_float, _ptr, _c_u64, _c_u64,
                                 _ptr],
     "pdr_normal_fill": [_c_size_t, _ptr, _c_u64, _c_u64, _ptr],
+    "pdr_point_upsample": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _c_float, _c_float, _ptr, _ptr, _ptr],
     # fused denoiser primitives (struct arguments are passed by address)
     "pdr_gemm_tile_rows": [],
     "pdr_gemm_fused": [_ptr, _ptr],

@@ -74,10 +74,51 @@ normal_fill_kernel(size_t count, float *__restrict__ x, uint64_t seed, uint64_t 
     if (i0 + t < count) x[i0 + t] = z[t];
 }
 
+// point_upsample (pointnet2/models/point_upsample_module.py:4-27) as ONE pass: thread per output coordinate.
+//   mid = coarse + centre_disp*s;  up[j] = mid + (grid_disp[j]*g)*s,  g = 1/sqrt(factor)
+// Every product/sum is rounded separately (__fmul_rn/__fadd_rn) -- the reference is a chain of separate
+// elementwise torch kernels, so no FMA contraction happens there; this keeps the result bit-identical.
+__global__ void __launch_bounds__(256)
+point_upsample_kernel(int b, int n, int reps, int with_centre, const float *__restrict__ coarse,
+                      const float *__restrict__ disp, int ld_disp, float grid_scale, float out_scale,
+                      float *__restrict__ refined, float *__restrict__ mid_out) {
+  const long long total = (long long)b * n * 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (cloud, point, xyz)
+  if (i >= total) return;
+  const int c = (int)(i % 3);
+  const long long bp = i / 3;                                              // cloud*n + point
+  const int pt = (int)(bp % n);
+  const long long cloud = bp / n;
+  const float *d = disp + bp * ld_disp;
+  const float mid = __fadd_rn(__ldg(coarse + i), __fmul_rn(__ldg(d + c), out_scale));
+  if (mid_out) mid_out[i] = mid;
+  const long long rows_out = (long long)n * (reps + (with_centre ? 1 : 0));
+  float *o = refined + cloud * rows_out * 3;
+  for (int j = 0; j < reps; ++j) {
+    const float g = __fmul_rn(__ldg(d + 3 + 3 * j + c), grid_scale);
+    o[((long long)pt * reps + j) * 3 + c] = __fadd_rn(mid, __fmul_rn(g, out_scale));
+  }
+  if (with_centre) o[((long long)n * reps + pt) * 3 + c] = mid;
+}
+
 }  // namespace
 }  // namespace pdr
 
 using namespace pdr;
+
+extern "C" int pdr_point_upsample(int b, int n, int factor, int include_centre, const float *coarse,
+                                  const float *displacement, float grid_scale, float out_scale, float *refined,
+                                  float *intermediate, void *stream) {
+  PDR_REQUIRE(b >= 0 && n >= 0 && factor >= 1, "point_upsample: bad sizes b=%d n=%d factor=%d", b, n, factor);
+  if (b == 0 || n == 0) return PDR_OK;
+  PDR_REQUIRE(coarse && displacement && refined, "point_upsample: null pointer");
+  const int reps = include_centre ? factor - 1 : factor;
+  const int ld = 3 * (reps + 1);
+  const long long total = (long long)b * n * 3;
+  point_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      b, n, reps, include_centre ? 1 : 0, coarse, displacement, ld, grid_scale, out_scale, refined, intermediate);
+  return check_launch("point_upsample");
+}
 
 extern "C" int pdr_ddpm_update(size_t count, float *x, const float *eps, float c_eps, float inv_sqrt_alpha,
                                float sigma, const float *noise, uint64_t seed, uint64_t offset, void *stream) {

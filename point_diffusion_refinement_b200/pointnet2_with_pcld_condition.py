@@ -149,25 +149,30 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
         self.fc_lyaer = self._build_head(head_in, copy.deepcopy(self.network_activation_function), bn=self.bn)
 
     # -- fused warm path --------------------------------------------------------------------------------
-    def enable_fused(self, enabled=True, use_tf32=False, use_graph=True):
+    def enable_fused(self, enabled=True, use_tf32=False, use_graph=True, fuse_cold=False):
         """Route warm calls (``use_retained_condition_feature=True`` with a retained state) through the
         compiled sm_100a program of :mod:`fused` instead of the per-layer module path.  The first (cold) call
-        of a chain still runs the modules: it encodes the condition cloud once."""
+        of a chain still runs the modules for the condition branch: it encodes the condition cloud once.
+        ``fuse_cold=True`` additionally sends the x-branch of cold calls (every call of the refinement network,
+        completion_eval.py:159-163) through the compiled program, right after the condition branch."""
         self._fused_cfg = dict(use_tf32=use_tf32, use_graph=use_graph) if enabled else None
+        self._fuse_cold = bool(enabled and fuse_cold)
         self._fused_engine = None
         return self
 
-    def _fused_step(self, pointcloud, ts):
+    def _fused_step(self, pointcloud, ts, cs=None, label=None):
         from .fused import FusedDenoiser
         B, N, _ = pointcloud.shape
+        cs = self._cond_state if cs is None else cs
+        label = self._cond_label if label is None else label
         eng = getattr(self, "_fused_engine", None)
         if eng is None or (eng.B, eng.N) != (B, N):
             eng = FusedDenoiser(self, B, N, **self._fused_cfg)
             self._fused_engine = eng
             self._fused_bound = None
-        if self._fused_bound is not self._cond_state:
-            eng.set_condition(self._cond_state, self._cond_label)
-            self._fused_bound = self._cond_state
+        if self._fused_bound is not cs:
+            eng.set_condition(cs, label)
+            self._fused_bound = cs
         return eng.step(pointcloud, ts)
 
     # -- retained condition state -------------------------------------------------------------------
@@ -224,6 +229,14 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
         if (use_retained_condition_feature and self._cond_state is not None
                 and getattr(self, "_fused_cfg", None) is not None and pointcloud.is_cuda and not torch.is_grad_enabled()):
             return self._fused_step(pointcloud, ts).clone()
+        if (getattr(self, "_fuse_cold", False) and getattr(self, "_fused_cfg", None) is not None and pointcloud.is_cuda
+                and not torch.is_grad_enabled() and self.include_local_feature):
+            cs = self.encode_condition(condition)
+            if use_retained_condition_feature:
+                cs.global_feature = None if cs.global_feature is None else cs.global_feature.detach().clone()
+                self._cond_state = cs
+                self._cond_label = label
+            return self._fused_step(pointcloud, ts, cs=cs, label=label).clone()
         with torch.no_grad():
             if self.attach_position_to_input_feature:
                 pointcloud = torch.cat([pointcloud, pointcloud[:, :, 0:3] / self.scale_factor], dim=2)

@@ -13,7 +13,7 @@ if [ -z "$SKIP_NCU" ]; then
 ( timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-eval-kernels --profiler-range ) > $out/ncu_launches.log 2>&1
-( timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:gemm -f -o $out/gemm_full \
+( timeout 480 ncu --profile-from-start off --set full --clock-control none -k regex:gemm -f -o $out/gemm_full \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-eval-kernels --profiler-range ) > $out/ncu_full.log 2>&1
 fi
 tail -3 $out/pytest_gpu.log; tail -2 $out/smoke.log; cat $out/bench.json; cat $out/bench_reference.json

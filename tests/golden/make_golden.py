@@ -7,6 +7,7 @@ Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 
 Outputs (small, committed): tests/golden/*.pt, tests/golden/state_dict_keys.json
+(`--only-refinement-io` regenerates refinement_io.pt alone.)
 """
 import json
 import os
@@ -44,8 +45,38 @@ def bind_reference_to_oracle():
             sys.path.insert(0, p)
 
 
+def refinement_io_fixtures():
+    """8f rows 1-2: point_upsample (models/point_upsample_module.py:4-27) and mirror_and_concat
+    (data_utils/mirror_partial.py:22-37), run from the reference's own files."""
+    from pointnet2.models.point_upsample_module import point_upsample as ref_upsample
+    from pointnet2.data_utils.mirror_partial import mirror_and_concat as ref_mirror
+    g = torch.Generator().manual_seed(11)
+    cases = []
+    for factor, centre, scale in ((8, False, 0.001), (8, True, 0.001), (2, False, 0.01), (1, False, 1.0), (3, True, 0.5)):
+        coarse = torch.rand(3, 50, 3, generator=g) * 2 - 1
+        reps = factor - 1 if centre else factor
+        disp = torch.randn(3, 50, 3 * (reps + 1), generator=g)
+        refined, mid = ref_upsample(coarse, disp, factor, centre, scale)
+        cases.append({"factor": factor, "centre": centre, "scale": scale, "coarse": coarse, "disp": disp,
+                      "refined": refined.clone(), "mid": mid.clone()})
+    partial = torch.rand(2, 300, 3, generator=g) * 2 - 1
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self      # mirror_partial.py:32 calls .cuda()
+    try:
+        mirrored = [t.clone() for t in ref_mirror(partial, axis=2, num_points=[256, 384])]
+        mirrored_ax1 = [t.clone() for t in ref_mirror(partial, axis=1, num_points=[128])]
+    finally:
+        torch.Tensor.cuda = real_cuda
+    torch.save({"upsample": cases, "partial": partial, "mirror_axis2_256_384": mirrored, "mirror_axis1_128": mirrored_ax1},
+               os.path.join(HERE, "refinement_io.pt"))
+    print("refinement_io.pt written")
+
+
 def main():
     bind_reference_to_oracle()
+    if "--only-refinement-io" in sys.argv:
+        refinement_io_fixtures()
+        return
     from pointnet2.models.pointnet2_with_pcld_condition import PointNet2CloudCondition as RefNet
     from pointnet2.models.pointnet2_ssg_sem import PointNet2SemSegSSG as RefSSG
     import pointnet2.util as ref_util  # reference util.py (schedule)
@@ -133,6 +164,7 @@ def main():
     P = ((p1.double()[:, :, None, :] - p2.double()[:, None, :, :]) ** 2).sum(-1)
     torch.save({"p1": p1, "p2": p2, "dist1": P.min(2)[0].float(), "dist2": P.min(1)[0].float(),
                 "idx1": P.min(2)[1].int(), "idx2": P.min(1)[1].int()}, os.path.join(HERE, "chamfer_f64.pt"))
+    refinement_io_fixtures()
     print("golden fixtures written to", HERE)
 
 

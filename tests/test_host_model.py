@@ -116,3 +116,23 @@ def test_query_and_group_fill_rule(oracle):
     assert out[0, 2:5, 1].abs().sum() == 0                     # relative xyz = 0
     assert torch.equal(out[0, 5:8, 1, 0], centres[0, 1])       # abs xyz = the centre itself
     assert out[0, 0, 0].tolist() == [1.0, 2.0, 1.0, 1.0]       # hits 0,1 then padded with the first hit
+
+
+def test_result_formats_round_trip(tmp_path):
+    """SURVEY 8f row 3: file names of completion_eval.py:283-315 and the pickled dict of
+    generate_samples.py:247-252 / generate_samples_distributed.py:84-93."""
+    import numpy as np
+    from point_diffusion_refinement_b200 import results_io as R
+    assert R.generated_file_name("mvp_dataset", 2048) == "mvp_generated_data_2048pts.h5"
+    assert R.generated_file_name("shapenet_chunk", 16384, 100) == "shapenet_generated_data_16384pts_T100.h5"
+    data = np.random.RandomState(0).rand(5, 64, 3).astype(np.float32)
+    path = str(tmp_path / R.generated_file_name("mvp40", 64))
+    R.save_generated(path, data)
+    assert np.array_equal(R.load_generated(path), data)
+    parts = [R.eval_result_dict(np.arange(3) + 3 * r, np.full(3, 0.1 * (r + 1), np.float32), np.full(3, 0.2, np.float32),
+                                np.full(3, 0.5, np.float32), 545999) for r in range(2)]
+    assert set(parts[0]) == {"meta", "cd_distance", "emd_distance", "f1", "avg_cd", "avg_emd", "iter"}
+    files = [R.save_eval_result(str(tmp_path / ("eval_result_rank_%d.pkl" % r)), p) for r, p in enumerate(parts)]
+    merged = R.gather_eval_results([R.load_eval_result(f) for f in files])
+    assert merged["meta"].tolist() == list(range(6)) and merged["iter"] == 545999
+    assert abs(merged["avg_cd"] - 0.15) < 1e-6 and merged["cd_distance"].shape == (6,)

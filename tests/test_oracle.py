@@ -123,3 +123,18 @@ def test_gather_group_are_pure_copies(oracle):
     ref = f.gather(2, idx.long().reshape(2, 1, 28).expand(-1, 5, -1)).reshape(2, 5, 7, 4)
     assert torch.equal(out, ref)
     assert torch.equal(oracle.gather_points(f, idx[:, :, 0].contiguous()), ref[..., 0])
+
+
+def test_point_upsample_and_mirror_partial_against_reference_fixture(oracle, golden_dir):
+    """the oracle's restatements against outputs of the reference's own
+    point_upsample_module.py / mirror_partial.py (tests/golden/make_golden.py), bit for bit."""
+    g = torch.load(golden_dir + "/refinement_io.pt")
+    for case in g["upsample"]:
+        refined, mid = oracle.point_upsample(case["coarse"], case["disp"], case["factor"], case["centre"], case["scale"])
+        assert torch.equal(refined, case["refined"]) and torch.equal(mid, case["mid"]), case["factor"]
+        assert refined.shape == (3, 50 * case["factor"], 3)
+    out = oracle.mirror_and_concat(g["partial"], axis=2, num_points=[256, 384])
+    assert len(out) == 3 and all(torch.equal(a, b) for a, b in zip(out, g["mirror_axis2_256_384"]))
+    out = oracle.mirror_and_concat(g["partial"], axis=1, num_points=[128])
+    assert all(torch.equal(a, b) for a, b in zip(out, g["mirror_axis1_128"]))
+    assert (out[0][:, 300:, 3] == -1).all() and (out[0][:, :300, 3] == 1).all()
