@@ -154,6 +154,11 @@ class FusedDenoiser:
         self.tile_rows = self.lib.pdr_gemm_tile_rows()
         self.ops = []          # compiled program: list of zero-argument callables
         self.meta = []         # per op: (entry point, {"bytes": algorithmic HBM bytes, "flops": ...})
+        self.cond_ops = []     # second program: the condition branch (SA_modules_condition / FP_modules_condition)
+        self.cond_meta = []
+        self._ops, self._meta = self.ops, self.meta    # where _emit appends
+        self.cond_graph = None
+        self.n_cond_kernel_calls = 0
         self.keep = []         # keeps ctypes structs / tensors alive
         self.graph = None
         self.cond_key = None
@@ -175,7 +180,7 @@ class FusedDenoiser:
         return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _emit(self, fn_name, *args, info=None):
-        self.meta.append((fn_name, info or {}))
+        self._meta.append((fn_name, info or {}))
         fn = getattr(self.lib, fn_name)
         stream_of = self._stream
         lib = self.lib
@@ -184,12 +189,15 @@ class FusedDenoiser:
             rc = fn(*args, stream_of())
             if rc != 0:
                 raise PdrError("%s failed (%d): %s" % (fn_name, rc, lib.pdr_last_error_string().decode()))
-        self.ops.append(op)
-        self.n_kernel_calls += 1
+        self._ops.append(op)
+        if self._ops is self.ops:
+            self.n_kernel_calls += 1
+        else:
+            self.n_cond_kernel_calls += 1
 
     def _torch(self, fn):
-        self.meta.append(("torch", {}))
-        self.ops.append(fn)
+        self._meta.append(("torch", {}))
+        self._ops.append(fn)
 
     def gemm(self, A, W, bias, out, rows_per_sample, batch=None, pro=PRO_NONE, scsh=None, add=None, R=None,
              rowadd=None, rowadd_div=1, want_stats=False, K=None, zero_to=None):
@@ -454,8 +462,17 @@ class FusedDenoiser:
     # ------------------------------------------------------------------------------------------------
     # program construction
     # ------------------------------------------------------------------------------------------------
-    def build(self, cs):
-        """Compile the warm step for the condition state `cs` (ConditionState of the module path)."""
+    def condition_shapes(self, M):
+        """(points per level, encoder channels per level, decoder channels per level) of the condition branch for an
+        M-point condition cloud (pointnet2_with_pcld_condition.py:84-88,113-120)."""
+        c_arch = self.hp["condition_net_architecture"]
+        m_lvl = [M] + list(c_arch["npoint"])
+        enc_C = [self.net.partial_in_fea_dim] + list(c_arch["feature_dim"][1:])
+        dec_C = list(c_arch["decoder_feature_dim"][:-1]) + [enc_C[-1]]
+        return m_lvl, enc_C, dec_C
+
+    def build(self, M):
+        """Compile the warm step (and the condition-branch program) for M-point condition clouds."""
         net, hp, B, N, dev = self.net, self.hp, self.B, self.N, self.dev
         arch, marc = hp["architecture"], hp["feature_mapper_architecture"]
         npoint = arch["npoint"]
@@ -491,11 +508,12 @@ class FusedDenoiser:
         self.x_in = self._zeros(B, N, 3)
         self.ts_in = self._zeros(B)
         self.eps_out = self._zeros(B, N, 3)
-        uvw = [u.contiguous().clone() for u in cs.l_uvw]
-        enc_cl = [self._to_cl(f) for f in cs.encoder]
-        dec_cl = [self._to_cl(f) for f in cs.decoder]
+        m_lvl, enc_C, dec_C = self.condition_shapes(M)
+        uvw = [self._zeros(B, m, 3) for m in m_lvl]
+        enc_cl = [self._mat(B * m, C) for m, C in zip(m_lvl, enc_C)]
+        dec_cl = [self._mat(B * m, C) for m, C in zip(m_lvl, dec_C)]
         self._uvw, self._enc_cl, self._dec_cl = uvw, enc_cl, dec_cl
-        m_lvl = [u.shape[1] for u in uvw]
+        self.M = M
 
         # ---- t embedding (tiny; torch) + one GEMM for every Linear(t_emb) of the net --------------------
         if self.include_t and self.t_cols:
@@ -637,34 +655,141 @@ class FusedDenoiser:
         self.gemm(Ya, _pack([(_conv_w(conv_b), [(0, conv_b.in_channels, r4(conv_b.in_channels))])], dev),
                   _bias(conv_b, out_dim, dev), View(self.eps_out.view(B * N, out_dim)), N, pro=PRO_GN_RELU, scsh=scsh,
                   zero_to=out_dim)
+        self._build_condition_program(m_lvl, enc_C, dec_C)
         self._built = True
 
-    def _to_cl(self, f):
-        """(B, C, n) channels-first retained condition feature -> channels-last View (B*n, r4(C))."""
-        Bc, C, n = f.shape
-        t = self._zeros(Bc * n, r4(C))
-        t[:, :C] = f.transpose(1, 2).reshape(Bc * n, C)
-        return View(t, C)
+    def _build_condition_program(self, m_lvl, enc_C, dec_C):
+        """The condition branch as a second static program writing straight into the channels-last buffers the
+        mappers of the main program read (encode_condition of the module path: SA_modules_condition with
+        subset=True, then FP_modules_condition top-down; pointnet2_with_pcld_condition.py:364-369 of the reference).
+        Same building blocks as the x-branch, no embeddings anywhere (include_t / conditions are off for these
+        modules, :84-88, :113-120)."""
+        net, hp, B = self.net, self.hp, self.B
+        c_arch = hp["condition_net_architecture"]
+        ok = (c_arch.get("use_knn_FP", False) and not c_arch.get("include_grouper", False)
+              and c_arch["neighbor_definition"] == "radius")
+        if not ok:
+            raise NotImplementedError("fused condition branch: ball-query encoder + kNN decoder only")
+        self._ops, self._meta = self.cond_ops, self.cond_meta
+        try:
+            L = len(c_arch["npoint"])
+            Kknn = c_arch.get("K", 3)
+            uvw, Fc, Dc = self._uvw, self._enc_cl, self._dec_cl
+            ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+            fps_idx = []
+            for i in range(L):
+                sa = net.SA_modules_condition[i]
+                n, P, K = m_lvl[i], m_lvl[i + 1], c_arch["nsample"][i]
+                idx = self._zeros(B, P, dtype=torch.int32)
+                self._emit("pdr_furthest_point_sampling", B, n, P, ptr(uvw[i]), None, ptr(idx))
+                self._emit("pdr_gather_rows", B, n, P, 3, ptr(uvw[i]), 3, ptr(idx), ptr(uvw[i + 1]), 3)
+                fps_idx.append(idx)
+                bidx = self._zeros(B, P, K, dtype=torch.int32)
+                cnt = self._zeros(B, P, dtype=torch.int32)
+                self._emit("pdr_ball_query", B, n, P, ctypes.c_float(c_arch["radius"][i]), K, ptr(uvw[i + 1]), ptr(uvw[i]),
+                           ptr(bidx), ptr(cnt))
+                Cin = enc_C[i]
+                X0 = self._mat(B * P * K, Cin + 9)
+                self._emit("pdr_group_ball", B, n, P, K, Cin, ctypes.c_void_p(Fc[i].ptr), Fc[i].ld, ptr(uvw[i]),
+                           ptr(uvw[i + 1]), ptr(bidx), ptr(cnt), 0, ctypes.c_void_p(X0.ptr), X0.ld)
+                Qf = self._mat(B * P, Cin)
+                self._emit("pdr_gather_rows", B, n, P, Cin, ctypes.c_void_p(Fc[i].ptr), Fc[i].ld, ptr(idx),
+                           ctypes.c_void_p(Qf.ptr), Qf.ld)
+                m = sa.mlps[0]
+                self.grouped_block("cond_sa%d" % i, X0, Cin + 9, K, P * K, m, sa.attention_modules[0], Qf, cnt,
+                                   Fc[i + 1], [None] * len(self._mlp_layers(m)))
+            # decoder: dec[L] = enc[L]; dec[i] = KnnFP_i(uvw[i], uvw[i+1], enc[i], dec[i+1])
+            self._emit("pdr_gather_rows", B, m_lvl[L], m_lvl[L], enc_C[L], ctypes.c_void_p(Fc[L].ptr), Fc[L].ld, None,
+                       ctypes.c_void_p(Dc[L].ptr), Dc[L].ld)
+            for i in range(L - 1, -1, -1):
+                fp = net.FP_modules_condition[i]
+                n_u, n_k = m_lvl[i], m_lvl[i + 1]
+                kidx = self._zeros(B, n_u, Kknn, dtype=torch.int64)
+                kd = self._zeros(B, n_u, Kknn)
+                self._emit("pdr_knn_points", B, n_u, n_k, Kknn, ptr(uvw[i]), ptr(uvw[i + 1]), ptr(kd), ptr(kidx))
+                Ck = dec_C[i + 1]
+                X0 = self._mat(B * n_u * Kknn, Ck + 11)
+                self._emit("pdr_group_knn", B, n_k, n_u, Kknn, Ck, ctypes.c_void_p(Dc[i + 1].ptr), Dc[i + 1].ld,
+                           ptr(uvw[i + 1]), ptr(uvw[i]), ptr(kidx), ptr(kd), ctypes.c_void_p(X0.ptr), X0.ld)
+                D, cskip = dec_C[i], enc_C[i]
+                H = self._mat(B * n_u, D + cskip + 3)
+                self.grouped_block("cond_fp%d.mlp1" % i, X0, Ck + 11, Kknn, n_u * Kknn, fp.mlp1, fp.attention_module,
+                                   Fc[i], None, H.cols(0, D), [None] * len(self._mlp_layers(fp.mlp1)))
+                self._emit("pdr_gather_rows", B, n_u, n_u, cskip, ctypes.c_void_p(Fc[i].ptr), Fc[i].ld, None,
+                           ctypes.c_void_p(H.cols(D, cskip).ptr), H.ld)
+                self._emit("pdr_gather_rows", B, n_u, n_u, 3, ptr(uvw[i]), 3, None,
+                           ctypes.c_void_p(H.cols(D + cskip, 3).ptr), H.ld)
+                self.pointwise_mlp("cond_fp%d.mlp2" % i, H, D + cskip + 3, n_u, fp.mlp2, Dc[i],
+                                   [None] * len(self._mlp_layers(fp.mlp2)))
+        finally:
+            self._ops, self._meta = self.ops, self.meta
 
     # ------------------------------------------------------------------------------------------------
     def set_condition(self, cs, label):
         """Bind a retained condition state: compile on first use, afterwards refresh the static condition
         buffers in place (same shapes), then precompute the condition-only embeddings."""
         if not self._built:
-            self.build(cs)
-        else:
-            for dst, src in zip(self._uvw, cs.l_uvw):
-                dst.copy_(src)
-            for views, feats in ((self._enc_cl, cs.encoder), (self._dec_cl, cs.decoder)):
-                for v, f in zip(views, feats):
-                    v.t[:, :v.C] = f.transpose(1, 2).reshape(-1, v.C)
+            self.build(cs.l_uvw[0].shape[1])
+        assert cs.l_uvw[0].shape[1] == self.M, "compiled for %d condition points, got %d" % (self.M, cs.l_uvw[0].shape[1])
+        for dst, src in zip(self._uvw, cs.l_uvw):
+            dst.copy_(src)
+        for views, feats in ((self._enc_cl, cs.encoder), (self._dec_cl, cs.decoder)):
+            for v, f in zip(views, feats):
+                v.t[:, :v.C] = f.transpose(1, 2).reshape(-1, v.C)
+        self._condition_embeddings(cs.global_feature, label)
+
+    def encode_condition(self, condition, label):
+        """Cold path: the condition cloud (B, M, 3 + partial features) through the compiled condition program;
+        fills the static buffers of the main program in place.  Returns the global feature (B, G)."""
+        B, M, _ = condition.shape
+        if not self._built:
+            self.build(M)
+        assert (B, M) == (self.B, self.M), "compiled for %s, got %s" % ((self.B, self.M), (B, M))
+        net = self.net
+        n_in = net.partial_in_fea_dim - 3
+        with torch.no_grad():
+            uvw = condition[:, :, 0:3]
+            self._uvw[0].copy_(uvw)
+            F0 = self._enc_cl[0].t.view(B, M, -1)           # level-0 condition features: [partial feats | uvw]
+            if n_in > 0:
+                F0[:, :, 0:n_in] = condition[:, :, 3:3 + n_in]
+            F0[:, :, n_in:n_in + 3] = uvw
+            if self.use_graph:
+                if self.cond_graph is None:
+                    for op in self.cond_ops:                 # warm-up outside capture
+                        op()
+                    torch.cuda.synchronize(self.dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for op in self.cond_ops:
+                            op()
+                    self.cond_graph = g
+                self.cond_graph.replay()
+            else:
+                for op in self.cond_ops:
+                    op()
+            g_in = torch.cat([uvw, condition[:, :, 3:3 + n_in]], dim=2) if n_in > 0 else uvw
+            global_feature = net.global_pnet(g_in.transpose(1, 2))
+        self._condition_embeddings(global_feature, label)
+        return global_feature
+
+    def export_condition_state(self, global_feature):
+        """The retained tensors in the module path's layout (l_uvw (B,m,3); features (B,C,m)), copied out of the
+        static buffers -- what ``net.l_uvw`` / ``net.encoder_cond_features`` expose to callers."""
+        from .pointnet2_with_pcld_condition import ConditionState
+        B = self.B
+        cf = lambda v: v.t.view(B, -1, v.ld)[:, :, :v.C].transpose(1, 2).clone()
+        return ConditionState([u.clone() for u in self._uvw], [cf(v) for v in self._enc_cl],
+                              [cf(v) for v in self._dec_cl], global_feature)
+
+    def _condition_embeddings(self, global_feature, label):
         with torch.no_grad():
             class_emb = self.net.class_emb(label)
             col = 0
             for srcs in self.c_lin:
                 acc = None
                 for kind, lin in srcs:
-                    v = lin(cs.global_feature if kind == "g" else class_emb)
+                    v = lin(global_feature if kind == "g" else class_emb)
                     acc = v if acc is None else acc + v
                 self.C_all[:, col:col + acc.shape[1]] = acc
                 col += acc.shape[1]

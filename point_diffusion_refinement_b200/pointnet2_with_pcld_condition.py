@@ -151,28 +151,47 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
     # -- fused warm path --------------------------------------------------------------------------------
     def enable_fused(self, enabled=True, use_tf32=False, use_graph=True, fuse_cold=False):
         """Route warm calls (``use_retained_condition_feature=True`` with a retained state) through the
-        compiled sm_100a program of :mod:`fused` instead of the per-layer module path.  The first (cold) call
-        of a chain still runs the modules for the condition branch: it encodes the condition cloud once.
-        ``fuse_cold=True`` additionally sends the x-branch of cold calls (every call of the refinement network,
-        completion_eval.py:159-163) through the compiled program, right after the condition branch."""
+        compiled sm_100a program of :mod:`fused` instead of the per-layer module path.  By default the first
+        (cold) call of a chain still runs the modules: it encodes the condition cloud once.
+        ``fuse_cold=True`` sends cold calls (every call of the refinement network, completion_eval.py:159-163; the
+        first call of a sampling chain) through the compiled programs as well: the condition branch
+        (SA_modules_condition / FP_modules_condition) is a second static program that writes straight into the
+        buffers the x-branch program reads; only the PointNet global feature stays on torch modules."""
         self._fused_cfg = dict(use_tf32=use_tf32, use_graph=use_graph) if enabled else None
         self._fuse_cold = bool(enabled and fuse_cold)
         self._fused_engine = None
         return self
 
-    def _fused_step(self, pointcloud, ts, cs=None, label=None):
+    def _engine(self, B, N):
         from .fused import FusedDenoiser
-        B, N, _ = pointcloud.shape
-        cs = self._cond_state if cs is None else cs
-        label = self._cond_label if label is None else label
         eng = getattr(self, "_fused_engine", None)
         if eng is None or (eng.B, eng.N) != (B, N):
             eng = FusedDenoiser(self, B, N, **self._fused_cfg)
             self._fused_engine = eng
             self._fused_bound = None
-        if self._fused_bound is not cs:
-            eng.set_condition(cs, label)
-            self._fused_bound = cs
+        return eng
+
+    def _fused_step(self, pointcloud, ts):
+        B, N, _ = pointcloud.shape
+        eng = self._engine(B, N)
+        if self._fused_bound is not self._cond_state:
+            eng.set_condition(self._cond_state, self._cond_label)
+            self._fused_bound = self._cond_state
+        return eng.step(pointcloud, ts)
+
+    def _fused_cold(self, pointcloud, condition, ts, label, retain):
+        """Condition branch AND x-branch on the compiled programs (every call of the refinement network;
+        the first call of a sampling chain)."""
+        B, N, _ = pointcloud.shape
+        eng = self._engine(B, N)
+        if getattr(eng, "M", condition.shape[1]) != condition.shape[1]:
+            self._fused_engine = None
+            eng = self._engine(B, N)
+        global_feature = eng.encode_condition(condition.float().contiguous(), label)
+        self._fused_bound = None
+        if retain:
+            cs = eng.export_condition_state(global_feature.detach().clone())
+            self._cond_state, self._cond_label, self._fused_bound = cs, label, cs
         return eng.step(pointcloud, ts)
 
     # -- retained condition state -------------------------------------------------------------------
@@ -230,13 +249,8 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
                 and getattr(self, "_fused_cfg", None) is not None and pointcloud.is_cuda and not torch.is_grad_enabled()):
             return self._fused_step(pointcloud, ts).clone()
         if (getattr(self, "_fuse_cold", False) and getattr(self, "_fused_cfg", None) is not None and pointcloud.is_cuda
-                and not torch.is_grad_enabled() and self.include_local_feature):
-            cs = self.encode_condition(condition)
-            if use_retained_condition_feature:
-                cs.global_feature = None if cs.global_feature is None else cs.global_feature.detach().clone()
-                self._cond_state = cs
-                self._cond_label = label
-            return self._fused_step(pointcloud, ts, cs=cs, label=label).clone()
+                and not torch.is_grad_enabled() and self.include_local_feature and self.include_global_feature):
+            return self._fused_cold(pointcloud, condition, ts, label, use_retained_condition_feature).clone()
         with torch.no_grad():
             if self.attach_position_to_input_feature:
                 pointcloud = torch.cat([pointcloud, pointcloud[:, :, 0:3] / self.scale_factor], dim=2)

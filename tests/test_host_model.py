@@ -136,3 +136,23 @@ def test_result_formats_round_trip(tmp_path):
     merged = R.gather_eval_results([R.load_eval_result(f) for f in files])
     assert merged["meta"].tolist() == list(range(6)) and merged["iter"] == 545999
     assert abs(merged["avg_cd"] - 0.15) < 1e-6 and merged["cd_distance"].shape == (6,)
+
+
+def test_compiled_programs_construct_without_a_gpu(cuda_lib):
+    """Host logic of fused.py: both static programs (x-branch, condition branch) are laid out from the module tree
+    alone -- every channel-width / alignment assertion of the builder runs here; nothing is launched."""
+    import collections
+    from point_diffusion_refinement_b200 import configs
+    from point_diffusion_refinement_b200.fused import FusedDenoiser
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    for cfg, n_gemm in ((configs.tiny_pointnet_config(), 134), (dict(configs.tiny_pointnet_config(), include_t=False), 133)):
+        net = PointNet2CloudCondition(cfg).eval()
+        eng = FusedDenoiser(net, 2, 256, use_tf32=False, use_graph=False)
+        eng.build(384)
+        main = collections.Counter(n for n, _ in eng.meta)
+        cond = collections.Counter(n for n, _ in eng.cond_meta)
+        assert main["pdr_gemm_fused"] == n_gemm and main["pdr_furthest_point_sampling"] == 4
+        assert main["pdr_ball_query"] == 9 and main["pdr_attention_pool"] == 17        # 13 queries in the reference
+        assert cond["pdr_gemm_fused"] == 68 and cond["pdr_attention_pool"] == 8 and cond["pdr_group_knn"] == 4
+        assert eng.condition_shapes(384) == ([384, 128, 64, 32, 16], [4, 32, 64, 64, 128], [32, 32, 64, 64, 128])
+        assert [v.C for v in eng._enc_cl] == [4, 32, 64, 64, 128] and eng.eps_out.shape == (2, 256, 3)

@@ -123,3 +123,35 @@ def test_evaluate_loop_refine_and_completion(tmp_path, oracle):
                                    T_step=3, compute_emd=False, return_all_metrics=True, seed=4, use_tf32=False)
     assert out[3]["emd_distance"].abs().max() == 0 and torch.isfinite(out[3]["cd_distance"]).all()
     assert set(out[3]) == {"cd_distance", "emd_distance", "cd_p", "f1"}
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_cold_step_on_compiled_condition_program(golden_dir, tag):
+    """fuse_cold: the condition branch (SA_modules_condition / FP_modules_condition) as a compiled program feeding
+    the x-branch program -- cold and warm eps against the reference-Python fixture, fp32."""
+    from point_diffusion_refinement_b200 import configs
+    gold = torch.load(golden_dir + "/denoiser_%s.pt" % tag)
+    cfg = configs.tiny_pointnet_config() if tag == "tiny" else configs.ddpm_pointnet_config()
+    net = _net(cfg, gold["param_seed"])
+    x, cond, ts, label = [t.to(DEV) for t in C.denoiser_inputs(gold["B"], gold["N"], gold["M"], seed=gold["input_seed"])]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            net.enable_fused(True, use_tf32=False, use_graph=True, fuse_cold=True)
+            cold = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+            assert net.l_uvw is not None and len(net.encoder_cond_features) == 5
+            fused_state = [f.clone() for f in net.encoder_cond_features + net.decoder_cond_features]
+            x2 = x + 0.05 * gold["eps_cold"].to(DEV)
+            warm = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+            net.reset_cond_features()
+            net.enable_fused(False)
+            net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+            mod_state = net.encoder_cond_features + net.decoder_cond_features
+            for a, b in zip(fused_state, mod_state):       # retained condition features, layer by layer
+                torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
+            net.reset_cond_features()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    torch.testing.assert_close(cold.cpu(), gold["eps_cold"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(warm.cpu(), gold["eps_warm"], rtol=1e-4, atol=1e-4)
