@@ -55,6 +55,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-eval-kernels", action="store_true", help="skip the Chamfer / EMD Mpairs/s lines (configs[3])")
+    p.add_argument("--fast-ddpm", action="store_true",
+                   help="also run configs[4]: FastDPM 50-step VAR chain vs the full T=1000 chain (adds ~15 s)")
     p.add_argument("--profiler-range", action="store_true",
                    help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     return p.parse_args()
@@ -283,6 +285,81 @@ def eval_kernel_lines(dev, sm_mhz):
     return out
 
 
+def geometry_kernel_lines(dev, sm_mhz):
+    """BASELINE configs[0] (SURVEY 8d cfg 1): FPS 4096 -> 1024 on one cloud + ball query of the picks, and the same two
+    kernels at the sampler's batch.  FPS is a serial chain of m-1 argmax rounds (latency-bound): quoted as distance
+    evaluations per FP32 lane-clock; ball query as centre-point tests per lane-clock (early exit makes it an upper
+    bound on work)."""
+    from point_diffusion_refinement_b200 import _ext
+    g = torch.Generator().manual_seed(0)
+    lanes_per_s = 148 * 128 * (sm_mhz or 1965) * 1e6
+    out = {}
+    for name, Bq, n, m, reps in (("fps_1x4096_to_1024", 1, 4096, 1024, 20), ("fps_32x2048_to_1024", 32, 2048, 1024, 20)):
+        xyz = (torch.rand(Bq, n, 3, generator=g) * 2 - 1).to(dev)
+        for _ in range(3):
+            idx = _ext.furthest_point_sampling(xyz, m)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            idx = _ext.furthest_point_sampling(xyz, m)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        evals = Bq * (m - 1) * n
+        out[name] = {"ms": ms, "us_per_round": ms * 1e3 / (m - 1), "dist_evals_per_s": evals / (ms * 1e-3),
+                     "dist_evals_per_lane_clk": evals / (ms * 1e-3) / lanes_per_s,
+                     "algorithmic_GBps": Bq * (12 * n + 4 * m) / ms / 1e6}
+        centres = _ext.gather_points(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+        for _ in range(3):
+            _ext.ball_query(centres, xyz, 0.2, 32)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            _ext.ball_query(centres, xyz, 0.2, 32)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name.replace("fps", "ball_query_r0.2_ns32").replace("_to_", "_x_")] = {
+            "ms": ms, "tests_per_lane_clk_upper": Bq * m * n / (ms * 1e-3) / lanes_per_s,
+            "algorithmic_GBps": Bq * (12 * (n + m) + 4 * m * 33) / ms / 1e6}
+    return out
+
+
+def fast_ddpm_lines(net, dev, B, dh, cond, label, rank):
+    """BASELINE configs[4]: fast_sampling_function_v2(length=50, 'var', 'quadratic', kappa=0.5) (README.md:95) against
+    the full T=1000 chain for the same condition clouds and network: shapes/s of each and cd_t between the outputs,
+    with the cd_t between two T=1000 seeds as the noise floor of a random-init network."""
+    from point_diffusion_refinement_b200 import util, util_fastdpmv2
+    from point_diffusion_refinement_b200.chamfer_loss_new import Chamfer_F1
+    import contextlib, io
+    size = (B, N_POINTS, 3)
+    dcfg = {"T": T_CHAIN, "beta_0": 1e-4, "beta_T": 0.02}
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            e0.record(); r = fn(); e1.record()
+        torch.cuda.synchronize()
+        return r, e0.elapsed_time(e1) / 1e3
+
+    fast = lambda seed: util_fastdpmv2.fast_sampling_function_v2(
+        net, size, dh, dcfg, length=50, sampling_method="var", schedule="quadratic", kappa=0.5, print_every_n_steps=0,
+        label=label, verbose=False, condition=cond, seed=seed)
+    full = lambda seed: util.sampling(net, size, dh, print_every_n_steps=0, label=label, verbose=False, condition=cond,
+                                      seed=seed)
+    fast(0)                                                     # warm-up of the schedule / API path
+    xf, t_fast = timed(lambda: fast(1 + rank))
+    x1, t_full = timed(lambda: full(1 + rank))
+    x2, _ = timed(lambda: full(1001 + rank))
+    cf = Chamfer_F1()
+    cd = lambda a, b: float(cf(a / 2, b / 2)[1].mean().item())
+    return {"fast50_var_quadratic_kappa0.5": {"seconds": t_fast, "shapes_per_s_per_gpu": B / t_fast, "net_calls": 50},
+            "ddpm_T1000": {"seconds": t_full, "shapes_per_s_per_gpu": B / t_full, "net_calls": 1000},
+            "cd_t_fast_vs_T1000": cd(xf, x1), "cd_t_T1000_seed_vs_seed": cd(x1, x2), "batch_per_gpu": B,
+            "note": "random-init network: the CD values only show that the 50-step chain lands as close to a T=1000 "
+                    "sample as another T=1000 sample does"}
+
+
 # ------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -420,10 +497,15 @@ def main():
                    "note": "util.sampling(use_a_precomputed_XT, step=%d): %d reverse steps incl. the cold one, "
                            "pinned-host condition/label/x_T in, generated cloud out; scaled by T/steps" % (Ke, Ke)}
 
-    eval_kernels = None
+    fast_ddpm = None
+    if args.fast_ddpm:
+        with torch.no_grad():
+            fast_ddpm = fast_ddpm_lines(net, dev, B, dh, cond, label, rank)
+    eval_kernels = geometry_kernels = None
     if rank == 0 and not args.no_eval_kernels:
         with torch.no_grad():
             eval_kernels = eval_kernel_lines(dev, clock_info.get("sm_mhz"))
+            geometry_kernels = geometry_kernel_lines(dev, clock_info.get("sm_mhz"))
     if rank != 0:
         return
     value = world * B / (T_CHAIN * ms_per_step / 1e3)
@@ -476,7 +558,8 @@ def main():
                    "l2": "per-step activation working set (>1 GB at B=32) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": "dp%d: shapes sharded by rank, no collective inside the chain, one final all_gather" % world},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info, "e2e": e2e,
-        "gpu_launches": launches, "eval_kernels": eval_kernels,
+        "gpu_launches": launches, "eval_kernels": eval_kernels, "geometry_kernels": geometry_kernels,
+        "fast_ddpm": fast_ddpm,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

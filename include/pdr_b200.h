@@ -184,6 +184,9 @@ typedef struct PdrGemmArgs {
    * sum y, sum y^2, sum relu(y), sum relu(y)^2 over the tile's valid rows; NULL = not needed */
   float *stats;
   int use_tf32;                          /* 0: fp32 SIMT FMA; 1: tensor cores (TF32 inputs, fp32 accumulate) */
+  /* hint: statistics nobody will read.  bit 0: the consumer does not need (sum y, sum y^2); bit 1: it does not need
+   * the relu pair.  Slots a kernel skips hold zeros; a kernel may ignore the hint and compute everything. */
+  int stats_skip;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);

@@ -23,6 +23,10 @@
 //                           tmem_empty[a].
 //   When the whole weight matrix fits in 64 KiB of shared memory it is staged once per CTA (W-resident mode)
 //   and the ring carries A only.
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pdr {
@@ -124,7 +128,7 @@ struct TcPlan {
   int r_off;            // offset of the residual tile inside a stage (transform mode with R)
 };
 
-template <int BN, bool WRES>
+template <int BN, bool WRES, bool VEC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   constexpr int kBTileBytes = BN * 128;
@@ -138,7 +142,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
   // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
-  __shared__ float s_epi[kEpiWarps][32 * 33];
+  __shared__ __align__(16) float s_epi[kEpiWarps][32 * 36];
   // the column partials (4 lane quarters x BN x 4 sums) live in the dynamic region and are touched only through
   // explicit ld/st.shared (a handful of accesses per block), which keeps static shared memory under 48 KB
 
@@ -470,7 +474,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     const int half = warp >> 2;                   // which of the two warps sharing this lane quarter
     constexpr int CW = BN == 32 ? 16 : 32;   // epilogue block width
-    constexpr int kTs = CW + 1;              // transpose tile stride
+    // transpose tile row stride (floats): odd for the scalar phase pair, CW + 4 keeps float4 alignment (VEC)
+    constexpr int kTs = VEC ? CW + 4 : CW + 1;
     float *s_t = s_epi[warp];
     int acc = 0, acc_phase = 0;
     // item geometry: divisions only when the item sequence is irregular (several column tiles, or fewer row
@@ -531,72 +536,256 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
               : "r"(taddr));
         }
-        // per-column constants are fetched while the TMEM load is in flight
-        const int hi = lane / CW, cl = lane % CW;
-        const int n = n0 + cb + cl;
-        const bool nin = n < a.N;
-        const bool nstore = nin || n < a.ldc_zero_to;
-        const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // park my row (lane = row) in the transpose tile; the odd stride keeps both phases bank-conflict free
-#pragma unroll
-        for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        // from here on lane = (row group hi, column cl): a store instruction writes 32 / CW row segments of CW
-        // consecutive floats; bias and the broadcast row-add are per column
-        constexpr int kRowsPer = CW;                  // rows walked by one lane group (32 rows * CW / 32 lanes)
-        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-        const size_t ldc = (size_t)a.ldc;
-        float *cp = a.C + (wrow0 + kRowsPer * hi) * ldc + n;
-        const float *st = s_t + (kRowsPer * hi) * kTs + cl;
-        const int my_rows = max(0, min(kRowsPer, wrows - kRowsPer * hi));
-        // the loops below are the hot path of the epilogue warps: keep them branch-free and free of 64-bit
-        // index arithmetic (running pointers only)
-        if (!a.rowadd) {
-#pragma unroll 8
-          for (int r = 0; r < my_rows; ++r) {
-            float t = st[r * kTs] + bias_n;
-            t = nin ? t : 0.f;
-            if (nstore) *cp = t;
-            cp += ldc;
-            const float p = fmaxf(t, 0.f);
-            q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
+        if constexpr (VEC) {
+          // lane mapping of the store phase: LPR lanes cover one row of the block as float4s, a store instruction
+          // writes RPI rows, a lane walks ITERS consecutive rows.  The per-column loads are issued before the TMEM
+          // load is waited for.
+          constexpr int LPR = CW / 4, RPI = 32 / LPR, ITERS = 32 / RPI;
+          const int rsub = lane / LPR, cg = lane % LPR;
+          const int n = n0 + cb + 4 * cg;                   // first of this lane's 4 columns
+          const int lim = max(a.N, a.ldc_zero_to);          // columns < lim are written (values or zero padding)
+          const bool in0 = n < a.N, in1 = n + 1 < a.N, in2 = n + 2 < a.N, in3 = n + 3 < a.N;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) {
+            if (in0) bias4.x = __ldg(a.bias + n);
+            if (in1) bias4.y = __ldg(a.bias + n + 1);
+            if (in2) bias4.z = __ldg(a.bias + n + 2);
+            if (in3) bias4.w = __ldg(a.bias + n + 3);
+          }
+          const int my_rows = max(0, min(ITERS, wrows - rsub * ITERS));
+          // broadcast row-add: rows (wrow0 + r) / div share one row of `rowadd` (the query term of AttentionModule,
+          // expanded over the K neighbours)
+          const float *rp = nullptr;
+          int rem = 0;
+          float4 cur = bias4;
+          if (a.rowadd) {
+            const int first = radd_rem0 + rsub * ITERS;
+            const int gskip = first / a.rowadd_div;
+            rem = first - gskip * a.rowadd_div;
+            rp = a.rowadd + (radd_g0 + gskip) * a.ld_rowadd + n;
+            if (in0 && my_rows > 0) {
+              const float4 q = __ldg(reinterpret_cast<const float4 *>(rp));
+              cur.x += q.x; cur.y += q.y; cur.z += q.z; cur.w += q.w;
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // park my row (lane = row) in the transpose tile as float4s; the row stride CW + 4 floats keeps 16-byte
+          // alignment and both phases bank-conflict free
+  #pragma unroll
+          for (int j = 0; j < CW / 4; ++j)
+            *reinterpret_cast<float4 *>(s_t + lane * kTs + 4 * j) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+          __syncwarp();
+          const size_t ldc = (size_t)a.ldc;
+          float *cp = a.C + (wrow0 + rsub * ITERS) * ldc + n;
+          const float *st = s_t + (rsub * ITERS) * kTs + 4 * cg;
+          const bool st_all = n + 3 < lim, st_any = n < lim;
+          // statistics of the 4 columns as packed pairs (columns 0|1 and 2|3): sum, sum of squares, relu-sum,
+          // relu-sum of squares -- one FADD2 / FFMA2 serves two columns
+          unsigned long long s01 = 0ull, s23 = 0ull, q01 = 0ull, q23 = 0ull, rs01 = 0ull, rs23 = 0ull, rq01 = 0ull, rq23 = 0ull;
+          auto accum2 = [&](float x, float y, unsigned long long &sm, unsigned long long &sq, unsigned long long &rs,
+                            unsigned long long &rq) {
+            unsigned long long t2, p2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(x), "f"(y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(fmaxf(x, 0.f)), "f"(fmaxf(y, 0.f)));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sm) : "l"(t2));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(sq) : "l"(t2));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rs) : "l"(p2));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(rq) : "l"(p2));
+          };
+          // fast path (warp-uniform): full rows, one broadcast row per lane, no float4 straddling the column limit
+          const bool one_group = !a.rowadd || rem + ITERS <= a.rowadd_div;
+          const bool fast = __all_sync(0xffffffffu, my_rows == ITERS && one_group && (st_all || !st_any));
+          if (fast) {
+            // the hot loop of the epilogue warps (they are issue-bound: profiles/r01_ncu_gemm_epilogue_hotspots.txt),
+            // specialised at compile time on what is needed: P = (sum, sum^2), R = the relu pair, AI = all four columns
+            // of every lane are inside N (no select, packed bias add).  ~3-5 instructions per element.
+            const bool all_in = __all_sync(0xffffffffu, in3);
+            const bool needP = a.stats && !(a.stats_skip & 1), needR = a.stats && !(a.stats_skip & 2);
+            unsigned long long cur01, cur23;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(cur01) : "f"(cur.x), "f"(cur.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(cur23) : "f"(cur.z), "f"(cur.w));
+            auto loop = [&](auto p_c, auto r_c, auto ai_c) {
+              constexpr bool P = decltype(p_c)::value, R = decltype(r_c)::value, AI = decltype(ai_c)::value;
+  #pragma unroll
+              for (int r = 0; r < ITERS; ++r) {
+                float4 t = *reinterpret_cast<const float4 *>(st + r * kTs);
+                unsigned long long t01, t23;
+                if constexpr (AI) {
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(t01) : "f"(t.x), "f"(t.y));
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(t23) : "f"(t.z), "f"(t.w));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(t01) : "l"(cur01));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(t23) : "l"(cur23));
+                  asm("mov.b64 {%0, %1}, %2;" : "=f"(t.x), "=f"(t.y) : "l"(t01));
+                  asm("mov.b64 {%0, %1}, %2;" : "=f"(t.z), "=f"(t.w) : "l"(t23));
+                  *reinterpret_cast<float4 *>(cp) = t;
+                } else {
+                  t.x = in0 ? t.x + cur.x : 0.f; t.y = in1 ? t.y + cur.y : 0.f;
+                  t.z = in2 ? t.z + cur.z : 0.f; t.w = in3 ? t.w + cur.w : 0.f;
+                  if (st_all) *reinterpret_cast<float4 *>(cp) = t;
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(t01) : "f"(t.x), "f"(t.y));
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(t23) : "f"(t.z), "f"(t.w));
+                }
+                cp += ldc;
+                if constexpr (P) {
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s01) : "l"(t01));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q01) : "l"(t01));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s23) : "l"(t23));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q23) : "l"(t23));
+                }
+                if constexpr (R) {
+                  unsigned long long p01, p23;
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(fmaxf(t.x, 0.f)), "f"(fmaxf(t.y, 0.f)));
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(fmaxf(t.z, 0.f)), "f"(fmaxf(t.w, 0.f)));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rs01) : "l"(p01));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(rq01) : "l"(p01));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rs23) : "l"(p23));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(rq23) : "l"(p23));
+                }
+              }
+            };
+            using T = std::true_type; using F = std::false_type;
+            const int variant = (needP ? 4 : 0) | (needR ? 2 : 0) | (all_in ? 1 : 0);
+            switch (variant) {
+              case 7: loop(T{}, T{}, T{}); break;
+              case 6: loop(T{}, T{}, F{}); break;
+              case 5: loop(T{}, F{}, T{}); break;
+              case 4: loop(T{}, F{}, F{}); break;
+              case 3: loop(F{}, T{}, T{}); break;
+              case 2: loop(F{}, T{}, F{}); break;
+              case 1: loop(F{}, F{}, T{}); break;
+              default: loop(F{}, F{}, F{}); break;
+            }
+          } else {
+  #pragma unroll 1
+            for (int r = 0; r < my_rows; ++r) {
+              if (a.rowadd && rem == a.rowadd_div) {          // next broadcast row
+                rem = 0;
+                rp += a.ld_rowadd;
+                cur = bias4;
+                if (in0) {
+                  const float4 q = __ldg(reinterpret_cast<const float4 *>(rp));
+                  cur.x += q.x; cur.y += q.y; cur.z += q.z; cur.w += q.w;
+                }
+              }
+              ++rem;
+              float4 t = *reinterpret_cast<const float4 *>(st + r * kTs);
+              t.x = in0 ? t.x + cur.x : 0.f; t.y = in1 ? t.y + cur.y : 0.f;
+              t.z = in2 ? t.z + cur.z : 0.f; t.w = in3 ? t.w + cur.w : 0.f;
+              if (st_all) {
+                *reinterpret_cast<float4 *>(cp) = t;
+              } else if (st_any) {
+                cp[0] = t.x;
+                if (n + 1 < lim) cp[1] = t.y;
+                if (n + 2 < lim) cp[2] = t.z;
+              }
+              cp += ldc;
+              accum2(t.x, t.y, s01, q01, rs01, rq01);
+              accum2(t.z, t.w, s23, q23, rs23, rq23);
+            }
+          }
+          __syncwarp();                                         // every lane is done with the transpose tile
+          if (a.stats) {
+            // fold the RPI row sub-groups through the (now free) transpose tile in a fixed order: quad index
+            // rsub * CW + c * LPR + cg holds (sum, sumsq, relu-sum, relu-sumsq) of column 4 * cg + c
+            {
+              float sa, sb, qa, qb, ra, rb, ua, ub;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(s01));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(qa), "=f"(qb) : "l"(q01));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(rs01));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(ua), "=f"(ub) : "l"(rq01));
+              *reinterpret_cast<float4 *>(s_t + (rsub * CW + 0 * LPR + cg) * 4) = make_float4(sa, qa, ra, ua);
+              *reinterpret_cast<float4 *>(s_t + (rsub * CW + 1 * LPR + cg) * 4) = make_float4(sb, qb, rb, ub);
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(sa), "=f"(sb) : "l"(s23));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(qa), "=f"(qb) : "l"(q23));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(rs23));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(ua), "=f"(ub) : "l"(rq23));
+              *reinterpret_cast<float4 *>(s_t + (rsub * CW + 2 * LPR + cg) * 4) = make_float4(sa, qa, ra, ua);
+              *reinterpret_cast<float4 *>(s_t + (rsub * CW + 3 * LPR + cg) * 4) = make_float4(sb, qb, rb, ub);
+            }
+            __syncwarp();
+            if (lane < CW) {
+              float4 tot = *reinterpret_cast<const float4 *>(s_t + lane * 4);
+  #pragma unroll
+              for (int rs = 1; rs < RPI; ++rs) {
+                const float4 q = *reinterpret_cast<const float4 *>(s_t + (rs * CW + lane) * 4);
+                tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
+              }
+              const int col = 4 * (lane % LPR) + lane / LPR;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part + (uint32_t)((quarter * BN + cb + col) * 16)),
+                           "f"(tot.x), "f"(tot.y), "f"(tot.z), "f"(tot.w) : "memory");
+            }
+            __syncwarp();                                       // before the next block overwrites the tile
           }
         } else {
-          // rows (wrow0 + r) / div share one broadcast row (the query term of AttentionModule, expanded over
-          // the K neighbours): one load per group of rows, issued one group ahead of its use
-          const int first = radd_rem0 + kRowsPer * hi;
-          const int gskip = first / a.rowadd_div;
-          int rem = first - gskip * a.rowadd_div;
-          const float *rp = a.rowadd + (radd_g0 + gskip) * a.ld_rowadd + (nin ? n : 0);
-          int r = 0;
-          float nxt = (nin && my_rows > 0) ? __ldg(rp) : 0.f;
-          while (r < my_rows) {
-            const float cur = bias_n + nxt;
-            const int rend = min(my_rows, r + (a.rowadd_div - rem));
-            rp += a.ld_rowadd;
-            if (nin && rend < my_rows) nxt = __ldg(rp);
-#pragma unroll 8
-            for (; r < rend; ++r) {
-              float t = st[r * kTs] + cur;
+          // per-column constants are fetched while the TMEM load is in flight
+          const int hi = lane / CW, cl = lane % CW;
+          const int n = n0 + cb + cl;
+          const bool nin = n < a.N;
+          const bool nstore = nin || n < a.ldc_zero_to;
+          const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // park my row (lane = row) in the transpose tile; the odd stride keeps both phases bank-conflict free
+  #pragma unroll
+          for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          // from here on lane = (row group hi, column cl): a store instruction writes 32 / CW row segments of CW
+          // consecutive floats; bias and the broadcast row-add are per column
+          constexpr int kRowsPer = CW;                  // rows walked by one lane group (32 rows * CW / 32 lanes)
+          float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+          const size_t ldc = (size_t)a.ldc;
+          float *cp = a.C + (wrow0 + kRowsPer * hi) * ldc + n;
+          const float *st = s_t + (kRowsPer * hi) * kTs + cl;
+          const int my_rows = max(0, min(kRowsPer, wrows - kRowsPer * hi));
+          // the loops below are the hot path of the epilogue warps: keep them branch-free and free of 64-bit
+          // index arithmetic (running pointers only)
+          if (!a.rowadd) {
+  #pragma unroll 8
+            for (int r = 0; r < my_rows; ++r) {
+              float t = st[r * kTs] + bias_n;
               t = nin ? t : 0.f;
               if (nstore) *cp = t;
               cp += ldc;
               const float p = fmaxf(t, 0.f);
               q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
             }
-            rem = 0;
+          } else {
+            // rows (wrow0 + r) / div share one broadcast row (the query term of AttentionModule, expanded over
+            // the K neighbours): one load per group of rows, issued one group ahead of its use
+            const int first = radd_rem0 + kRowsPer * hi;
+            const int gskip = first / a.rowadd_div;
+            int rem = first - gskip * a.rowadd_div;
+            const float *rp = a.rowadd + (radd_g0 + gskip) * a.ld_rowadd + (nin ? n : 0);
+            int r = 0;
+            float nxt = (nin && my_rows > 0) ? __ldg(rp) : 0.f;
+            while (r < my_rows) {
+              const float cur = bias_n + nxt;
+              const int rend = min(my_rows, r + (a.rowadd_div - rem));
+              rp += a.ld_rowadd;
+              if (nin && rend < my_rows) nxt = __ldg(rp);
+  #pragma unroll 8
+              for (; r < rend; ++r) {
+                float t = st[r * kTs] + cur;
+                t = nin ? t : 0.f;
+                if (nstore) *cp = t;
+                cp += ldc;
+                const float p = fmaxf(t, 0.f);
+                q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
+              }
+              rem = 0;
+            }
           }
-        }
-        __syncwarp();
-        if (a.stats) {
-          if constexpr (CW == 16) {
-            q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-            q2 += __shfl_xor_sync(0xffffffffu, q2, 16); q3 += __shfl_xor_sync(0xffffffffu, q3, 16);
+          __syncwarp();
+          if (a.stats) {
+            if constexpr (CW == 16) {
+              q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+              q2 += __shfl_xor_sync(0xffffffffu, q2, 16); q3 += __shfl_xor_sync(0xffffffffu, q3, 16);
+            }
+            if (hi == 0)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part + (uint32_t)((quarter * BN + cb + cl) * 16)),
+                           "f"(q0), "f"(q1), "f"(q2), "f"(q3) : "memory");
           }
-          if (hi == 0)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part + (uint32_t)((quarter * BN + cb + cl) * 16)),
-                         "f"(q0), "f"(q1), "f"(q2), "f"(q3) : "memory");
         }
       }
       // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
@@ -632,6 +821,15 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
 
 constexpr int kPlanDoesNotFit = 12345;
 
+bool vec_epilogue() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("PDR_GEMM_EPILOGUE");
+    mode = (e && e[0] == 's') ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 template <int BN, bool WRES>
 int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   TcPlan plan;
@@ -642,7 +840,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   plan.total_items = (int)items;
   plan.nk = ceil_div(a.K, kTcBK);
   const size_t epi = (size_t)4 * BN * 16;   // column partials; the transpose tiles are static shared memory
-  const size_t static_smem = (size_t)(kEpiWarps * 32 * 33) * sizeof(float) + 256;
+  const size_t static_smem = (size_t)(kEpiWarps * 32 * 36) * sizeof(float) + 512;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;
   bool planned = false;
@@ -667,12 +865,14 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N);
     return PDR_ERR_UNSUPPORTED;
   }
-  auto kern = gemm_tf32_persistent<BN, WRES>;
-  static bool configured = false;
-  if (!configured) {
+  // epilogue flavour: float4 stores + packed f32x2 statistics (default) or the scalar one (PDR_GEMM_EPILOGUE=scalar)
+  const bool vec = vec_epilogue();
+  auto kern = vec ? gemm_tf32_persistent<BN, WRES, true> : gemm_tf32_persistent<BN, WRES, false>;
+  static bool configured[2] = {false, false};
+  if (!configured[vec]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
-    configured = true;
+    configured[vec] = true;
   }
   const int grid = plan.total_items < kNumSMs ? plan.total_items : kNumSMs;
   kern<<<grid, kTcThreads, smem, stream>>>(a, plan);

@@ -224,8 +224,19 @@ gn_finalize_kernel(const PdrGnArgs a) {
       if (cl < ncs) {
         const float *p = src.stats + ((size_t)b * src.tiles_per_sample * src.ld_stats + src.col0 + (v - src_off)) * 4 +
                          (src.use_relu ? 2 : 0);
-        for (int t = slice; t < src.tiles_per_sample; t += nsl) {
-          const float2 q = *reinterpret_cast<const float2 *>(p + (size_t)t * src.ld_stats * 4);
+        // 8 loads in flight per thread (the loop is latency-bound: one L2 round trip per tile partial otherwise);
+        // the partials are still folded in the same fixed order, so the result is unchanged bit for bit
+        const size_t tstride = (size_t)src.ld_stats * 4;
+        int t = slice;
+        for (; t + 7 * nsl < src.tiles_per_sample; t += 8 * nsl) {
+          float2 q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) q[u] = *reinterpret_cast<const float2 *>(p + (size_t)(t + u * nsl) * tstride);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { sum += (double)q[u].x; sq += (double)q[u].y; }
+        }
+        for (; t < src.tiles_per_sample; t += nsl) {
+          const float2 q = *reinterpret_cast<const float2 *>(p + (size_t)t * tstride);
           sum += (double)q.x;
           sq += (double)q.y;
         }

@@ -48,7 +48,8 @@ class GemmArgs(ctypes.Structure):
                 ("R", c_float_p), ("ldr", ctypes.c_int),
                 ("rowadd", c_float_p), ("ld_rowadd", ctypes.c_int), ("rowadd_div", ctypes.c_int),
                 ("stats", c_float_p),
-                ("use_tf32", ctypes.c_int)]
+                ("use_tf32", ctypes.c_int),
+                ("stats_skip", ctypes.c_int)]
 
 
 class GnSource(ctypes.Structure):
@@ -86,8 +87,12 @@ class View:
 
 
 class Stats:
-    def __init__(self, t, tiles_per_sample, N, rows):
-        self.t, self.tiles_per_sample, self.N, self.rows = t, tiles_per_sample, N, rows
+    """Per-tile column statistics of one GEMM output.  `g` is the GemmArgs of the producing call: consumers
+    registered later (FusedDenoiser.gn) clear the bits of g.stats_skip for the pair they read, so the epilogue
+    only accumulates what some GroupNorm will actually use."""
+
+    def __init__(self, t, tiles_per_sample, N, rows, g=None):
+        self.t, self.tiles_per_sample, self.N, self.rows, self.g = t, tiles_per_sample, N, rows, g
 
 
 def _conv_w(conv):
@@ -227,8 +232,9 @@ class FusedDenoiser:
         st = None
         if want_stats:
             tiles = (rows_per_sample + self.tile_rows - 1) // self.tile_rows
-            st = Stats(self._zeros(batch * tiles, N, 4), tiles, N, rows_per_sample)
+            st = Stats(self._zeros(batch * tiles, N, 4), tiles, N, rows_per_sample, g)
             g.stats = st.t.data_ptr()
+            g.stats_skip = 3                   # until a consumer registers (gn)
         g.use_tf32 = self.use_tf32 if rows_per_sample * batch >= 512 else 0
         if g.use_tf32:
             W = tf32_round(W)
@@ -259,6 +265,8 @@ class FusedDenoiser:
             s.stats, s.tiles_per_sample, s.ld_stats = st.t.data_ptr(), st.tiles_per_sample, st.N
             s.col0, s.ncols, s.out_col0 = col0, ncols, off
             s.use_relu, s.rows, s.mult = int(use_relu), st.rows, float(mult)
+            if st.g is not None:
+                st.g.stats_skip &= ~(2 if use_relu else 1)
             off += r4(ncols)
         a.nsrc, a.batch, a.channels, a.gn_channels, a.groups = len(sources), batch, channels, gn_channels, groups
         gamma = gnm.weight.detach().float().contiguous()

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _run(lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32, want_stats=True, ldc=None):
+def _run(lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32, want_stats=True, ldc=None, stats_skip=0):
     from point_diffusion_refinement_b200.fused import GemmArgs
     M, K = A.shape
     ldc = ldc or (N + 3) // 4 * 4
@@ -32,6 +32,7 @@ def _run(lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32,
         g.rowadd, g.ld_rowadd, g.rowadd_div = rowadd.data_ptr(), rowadd.stride(0), div
     g.stats = stats.data_ptr() if want_stats else None
     g.use_tf32 = int(use_tf32)
+    g.stats_skip = stats_skip
     rc = lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(g)), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.pdr_last_error_string()
     torch.cuda.synchronize()
@@ -133,3 +134,27 @@ def test_gemm_tcgen05_matches_simt(cuda_lib, case):
     assert ((st1[..., 3] - st0[..., 3]).abs() <= 5e-3 * l2 + 1e-2).all()
     C2, _ = _run(cuda_lib, A, Wt, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True)
     assert torch.equal(C1[:, :N], C2[:, :N])                          # deterministic
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[3], CASES[5], CASES[12]])
+def test_gemm_stats_skip_hint(cuda_lib, case):
+    """PdrGemmArgs.stats_skip: the pair a consumer asked for is bit-identical to the full computation, the output
+    matrix does not change, whichever pair the epilogue leaves out."""
+    B, rps, K, N, pro, use_add, use_R, div = case
+    g = torch.Generator().manual_seed(K * N + rps + 2)
+    M = B * rps
+    A = torch.randn(M, K, generator=g).to(DEV)
+    from point_diffusion_refinement_b200.fused import tf32_round
+    W = tf32_round((torch.randn(N, K, generator=g) / K ** 0.5).to(DEV))
+    bias = torch.randn(N, generator=g).to(DEV)
+    sc = (1 + 0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    sh = (0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    add = torch.randn(B, K, generator=g).to(DEV) if use_add else None
+    R = torch.randn(M, K, generator=g).to(DEV) if use_R else None
+    rowadd = torch.randn(M // div, (N + 3) // 4 * 4, generator=g).to(DEV) if div else None
+    C0, st0 = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True)
+    C1, st1 = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True, stats_skip=2)
+    C2, st2 = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True, stats_skip=1)
+    C3, _ = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True, stats_skip=3)
+    assert torch.equal(C0, C1) and torch.equal(C0, C2) and torch.equal(C0, C3)
+    assert torch.equal(st1[..., :2], st0[..., :2]) and torch.equal(st2[..., 2:], st0[..., 2:])
