@@ -598,7 +598,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           const bool one_group = !a.rowadd || rem + ITERS <= a.rowadd_div;
           const bool fast = __all_sync(0xffffffffu, my_rows == ITERS && one_group && (st_all || !st_any));
           if (fast) {
-            // the hot loop of the epilogue warps (they are issue-bound: profiles/r01_ncu_gemm_epilogue_hotspots.txt),
+            // the hot loop of the epilogue warps (they are issue-bound: profiles/r01_ncu_gemm_epilogue_hotspots_v5.txt),
             // specialised at compile time on what is needed: P = (sum, sum^2), R = the relu pair, AI = all four columns
             // of every lane are inside N (no select, packed bias add).  ~3-5 instructions per element.
             const bool all_in = __all_sync(0xffffffffu, in3);
@@ -741,15 +741,25 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           // the loops below are the hot path of the epilogue warps: keep them branch-free and free of 64-bit
           // index arithmetic (running pointers only)
           if (!a.rowadd) {
+            // specialised on the statistics pairs some GroupNorm will read (PdrGemmArgs.stats_skip)
+            auto rows_loop = [&](auto p_c, auto r_c) {
+              constexpr bool P = decltype(p_c)::value, R = decltype(r_c)::value;
   #pragma unroll 8
-            for (int r = 0; r < my_rows; ++r) {
-              float t = st[r * kTs] + bias_n;
-              t = nin ? t : 0.f;
-              if (nstore) *cp = t;
-              cp += ldc;
-              const float p = fmaxf(t, 0.f);
-              q0 += t; q1 = fmaf(t, t, q1); q2 += p; q3 = fmaf(p, p, q3);
-            }
+              for (int r = 0; r < my_rows; ++r) {
+                float t = st[r * kTs] + bias_n;
+                t = nin ? t : 0.f;
+                if (nstore) *cp = t;
+                cp += ldc;
+                if constexpr (P) { q0 += t; q1 = fmaf(t, t, q1); }
+                if constexpr (R) { const float p = fmaxf(t, 0.f); q2 += p; q3 = fmaf(p, p, q3); }
+              }
+            };
+            using T = std::true_type; using F = std::false_type;
+            const bool needP = a.stats && !(a.stats_skip & 1), needR = a.stats && !(a.stats_skip & 2);
+            if (needP && needR) rows_loop(T{}, T{});
+            else if (needP) rows_loop(T{}, F{});
+            else if (needR) rows_loop(F{}, T{});
+            else rows_loop(F{}, F{});
           } else {
             // rows (wrow0 + r) / div share one broadcast row (the query term of AttentionModule, expanded over
             // the K neighbours): one load per group of rows, issued one group ahead of its use
@@ -821,13 +831,17 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
 
 constexpr int kPlanDoesNotFit = 12345;
 
-bool vec_epilogue() {
+// Epilogue flavour.  Measured on B200 (profiles/r01_epilogue_ab_v7.txt): the float4 / packed-f32x2 epilogue wins
+// where the broadcast row-add is used (one float4 of the query term per lane and block instead of a dependent scalar
+// load per row group: 0.240 -> 0.177 ms on the 524288 x 172 x 128 score GEMM), the scalar one wins everywhere else
+// (its per-block fixed cost is lower).  auto = pick per call; PDR_GEMM_EPILOGUE=scalar|vec4 forces one (tests, A/B).
+int epilogue_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char *e = getenv("PDR_GEMM_EPILOGUE");
-    mode = (e && e[0] == 's') ? 0 : 1;
+    mode = !e ? 2 : (e[0] == 's' ? 0 : (e[0] == 'v' ? 1 : 2));
   }
-  return mode == 1;
+  return mode;
 }
 
 template <int BN, bool WRES>
@@ -865,8 +879,8 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N);
     return PDR_ERR_UNSUPPORTED;
   }
-  // epilogue flavour: float4 stores + packed f32x2 statistics (default) or the scalar one (PDR_GEMM_EPILOGUE=scalar)
-  const bool vec = vec_epilogue();
+  const int mode = epilogue_mode();
+  const bool vec = mode == 2 ? a.rowadd != nullptr : mode == 1;
   auto kern = vec ? gemm_tf32_persistent<BN, WRES, true> : gemm_tf32_persistent<BN, WRES, false>;
   static bool configured[2] = {false, false};
   if (!configured[vec]) {

@@ -22,6 +22,7 @@ Reference semantics implemented: pointnet2_ops/pointnet2_modules.py:69-174 (Mlp_
 487-514; pointnet2/models/pointnet2_with_pcld_condition.py:380-476.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -66,6 +67,8 @@ class GnArgs(ctypes.Structure):
 
 
 PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
+# A/B switch for profiling only: PDR_STATS_SKIP=0 makes every GEMM epilogue accumulate both statistics pairs
+_STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
 
 
 def r4(c):
@@ -234,7 +237,7 @@ class FusedDenoiser:
             tiles = (rows_per_sample + self.tile_rows - 1) // self.tile_rows
             st = Stats(self._zeros(batch * tiles, N, 4), tiles, N, rows_per_sample, g)
             g.stats = st.t.data_ptr()
-            g.stats_skip = 3                   # until a consumer registers (gn)
+            g.stats_skip = 3 if _STATS_SKIP_HINT else 0     # until a consumer registers (gn)
         g.use_tf32 = self.use_tf32 if rows_per_sample * batch >= 512 else 0
         if g.use_tf32:
             W = tf32_round(W)

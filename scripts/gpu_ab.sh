@@ -1,10 +1,23 @@
 #!/bin/bash
-# A/B of the GEMM epilogue flavours on one box: parity tests, then bench with each (short form for the B arm).
-tag=${1:-ab}
+# Quick A/B on one box: parity tests, then short bench arms selected by environment switches.
+# usage: bash scripts/gpu_ab.sh <tag> "<pytest args>" "ENV1=.. ENV2=.." "ENVb=.." ...   (one bench arm per extra argument; "-" = default env)
+tag=${1:-ab}; shift
+pyt=${1:-tests -m gpu}; shift
 out=gpurun_out/$tag
 mkdir -p $out
-( timeout 900 python -m pytest tests -m gpu -x -q ) > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
-( PDR_GEMM_EPILOGUE=scalar timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_model_gpu.py -m gpu -x -q ) > $out/pytest_scalar.log 2>&1; echo "pytest exit $?" >> $out/pytest_scalar.log
-( timeout 600 python bench.py --dump-ops $out/ops_vec.json --no-cpu-baseline ) > $out/bench_vec.json 2> $out/bench_vec.err
-( PDR_GEMM_EPILOGUE=scalar timeout 600 python bench.py --dump-ops $out/ops_scalar.json --no-cpu-baseline --no-eval-kernels --no-e2e ) > $out/bench_scalar.json 2> $out/bench_scalar.err
-tail -4 $out/pytest_gpu.log; tail -2 $out/pytest_scalar.log; cat $out/bench_vec.json; cat $out/bench_scalar.json; tail -5 $out/*.err
+( timeout 900 python -m pytest $pyt -x -q ) > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
+tail -4 $out/pytest_gpu.log
+i=0
+for arm in "$@"; do
+  i=$((i+1))
+  envs=""; [ "$arm" != "-" ] && envs="$arm"
+  ( env $envs timeout 600 python bench.py --dump-ops $out/ops_$i.json --no-cpu-baseline --no-eval-kernels --no-e2e ) > $out/bench_$i.json 2> $out/bench_$i.err
+  echo "== arm $i: $arm"; python - <<PY
+import json
+try:
+    d=json.loads(open("$out/bench_$i.json").read().strip().splitlines()[-1])
+    print("ms_per_step %.3f  frac %.3f  %s" % (d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["per_kernel_ms"]))
+except Exception as e:
+    print("bench failed", e); print(open("$out/bench_$i.err").read()[-1500:])
+PY
+done
