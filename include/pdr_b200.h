@@ -187,6 +187,13 @@ typedef struct PdrGemmArgs {
   /* hint: statistics nobody will read.  bit 0: the consumer does not need (sum y, sum y^2); bit 1: it does not need
    * the relu pair.  Slots a kernel skips hold zeros; a kernel may ignore the hint and compute everything. */
   int stats_skip;
+  /* gathered A operand (tensor-core path, no prologue / add / R): when a_rows != NULL, row r of A is
+   *   [ A[a_rows[r], 0:k_split] | A2[r, 0:K-k_split] ]        (a_rows[r] < 0: the first part is zeros)
+   * i.e. the grouped tensor of QueryAndGroup / group_knn is assembled while the GEMM loads its operand instead of
+   * being written to and re-read from HBM: A is the (points, lda) feature table, a_rows the flat neighbour row of
+   * every grouped row (pdr_group_src_rows), A2 the (M, lda2) geometric channels (pdr_group_ball / _knn with C = 0).
+   * k_split, lda2 multiples of 4; A2 16-byte aligned. */
+  const int *a_rows; const float *A2; int lda2; int k_split;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);
@@ -234,6 +241,11 @@ int pdr_group_ball(int batch, int n, int P, int K, int C, const float *feat, int
  * (pointnet2_utils.py:487-514).  idx (B, P, K) int64 and dists (B, P, K) from pdr_knn_points. */
 int pdr_group_knn(int batch, int n, int P, int K, int C, const float *feat, int ldf, const float *y,
                   const float *x, const int64_t *idx, const float *dists, float *out, int ldo, void *stream);
+/* Flat feature-table row of every grouped row: src_row[(b*P+p)*K+k] = b*n + idx[b,p,k], or -1 where the subset=False
+ * fill rule zeroes the features (fill_missing != 0 and counts[b,p] == 0).  idx is int32 (ball query) or, with
+ * idx_is_int64 != 0, int64 (pdr_knn_points).  Feeds PdrGemmArgs.a_rows. */
+int pdr_group_src_rows(int batch, int n, int P, int K, const void *idx, int idx_is_int64, const int *counts,
+                       int fill_missing, int *src_row, void *stream);
 /* out[b, j, 0:C] = src[b, idx[b,j], 0:C] (rows); idx == NULL copies row j.  Used for FPS centre features and
  * for placing a feature block into a column slice of a wider buffer (free concatenation). */
 int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, const int *idx, float *out,

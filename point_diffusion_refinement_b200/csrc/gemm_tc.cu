@@ -213,6 +213,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       int item, kc, b, tis, n0, rows_valid;
       const float *pa;           // &A[row_base + arow][chunk*4]
       const float *pr;           // same for the residual
+      const float *pg[4];        // gathered A: &A[a_rows[row_base + arow + 32 i]][chunk*4], nullptr = zero row
+      const float *p2;           // gathered A: &A2[row_base + arow][chunk*4]
     };
     auto locate = [&](Cur &c) {  // full (division) geometry of c.item
       const int tile = c.item / plan.n_tiles_n;
@@ -220,12 +222,29 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       c.b = tile / plan.tiles_per_sample;
       c.tis = tile - c.b * plan.tiles_per_sample;
     };
+    // gathered A (PdrGemmArgs.a_rows): the neighbour rows of the CURRENT item sit in cidx, those of the NEXT item of
+    // this CTA are already in flight in nidx, so the index loads never stall the copy loop
+    const bool gath = a.a_rows != nullptr;
+    int cidx[4] = {-1, -1, -1, -1}, nidx[4] = {-1, -1, -1, -1};
+    auto fetch_idx = [&](int item, int (&out)[4]) {
+      if (item >= plan.total_items) return;
+      const int tile = item / plan.n_tiles_n;
+      const int b = tile / plan.tiles_per_sample, r0 = (tile - b * plan.tiles_per_sample) * kTcTileM;
+      const int *p = a.a_rows + (size_t)b * a.rows_per_sample + r0 + arow;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[i] = (r0 + arow + 32 * i < a.rows_per_sample) ? __ldg(p + 32 * i) : -1;
+    };
     auto derive = [&](Cur &c) {  // pointers and row count from (b, tis)
       const int r0 = c.tis * kTcTileM;
       c.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
       const size_t row = (size_t)c.b * a.rows_per_sample + r0 + arow;
       c.pa = a.A + row * a.lda + chunk * 4;
       c.pr = a.R ? a.R + row * a.ldr + chunk * 4 : nullptr;
+      if (gath) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.pg[i] = cidx[i] >= 0 ? a.A + (size_t)cidx[i] * a.lda + chunk * 4 : nullptr;
+        c.p2 = a.A2 + row * a.lda2 + chunk * 4;
+      }
     };
     auto advance = [&](Cur &c) {
       if (++c.kc < nk) return;
@@ -233,6 +252,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       c.item += G;
       if (fast_adv) { c.tis += G; if (c.tis >= plan.tiles_per_sample) { c.tis -= plan.tiles_per_sample; ++c.b; } }
       else locate(c);
+      if (gath) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cidx[i] = nidx[i];
+        fetch_idx(c.item + G, nidx);
+      }
       derive(c);
     };
     const uint32_t sw_off = (uint32_t)(arow * 128 + ((chunk ^ (arow & 7)) << 4));   // row arow+32i: + i*4096
@@ -241,6 +265,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     const size_t w_step = (size_t)32 * a.ldw;
     Cur ci;
     ci.item = (int)blockIdx.x; ci.kc = 0;
+    if (gath && !is_loader) { fetch_idx(ci.item, cidx); fetch_idx(ci.item + G, nidx); }
     locate(ci); derive(ci);
 
     if (plan.direct) {
@@ -257,7 +282,23 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         // are what the producer warps spend their issue slots on
         // (K tail: this thread's 16-byte piece is either wholly inside K or wholly zero-filled)
         const int ksz = kin ? 16 : 0;
-        if (c.rows_valid == kTcTileM) {
+        if (gath) {
+          if (kofs + chunk * 4 < a.k_split) {          // feature part: one table row per grouped row
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float *p = c.pg[i];
+              cp_async16_sz(sa + i * 4096, p ? p + kofs : a.A, p ? 16 : 0);
+            }
+          } else {                                       // geometric channels, dense (M, lda2)
+            const float *p2 = c.p2 + (kofs - a.k_split);
+            const size_t st2 = (size_t)32 * a.lda2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const bool ok = kin && arow + 32 * i < c.rows_valid;
+              cp_async16_sz(sa + i * 4096, ok ? p2 + i * st2 : a.A, ok ? 16 : 0);
+            }
+          }
+        } else if (c.rows_valid == kTcTileM) {
           const float *p = kin ? src : a.A;
           const size_t st = kin ? a_step : 0;
 #pragma unroll
@@ -832,9 +873,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
 constexpr int kPlanDoesNotFit = 12345;
 
 // Epilogue flavour.  Measured on B200 (profiles/r01_epilogue_ab_v7.txt): the float4 / packed-f32x2 epilogue wins
-// where the broadcast row-add is used (one float4 of the query term per lane and block instead of a dependent scalar
-// load per row group: 0.240 -> 0.177 ms on the 524288 x 172 x 128 score GEMM), the scalar one wins everywhere else
-// (its per-block fixed cost is lower).  auto = pick per call; PDR_GEMM_EPILOGUE=scalar|vec4 forces one (tests, A/B).
+// where the broadcast row-add is used on 32-column blocks (one float4 of the query term per lane and block instead of a
+// dependent scalar load per row group: 0.240 -> 0.177 ms on the 524288 x 172 x 128 score GEMM), the scalar one wins
+// everywhere else (lower per-block fixed cost; 15-20 % faster on the 16-column blocks of the narrowest tile).  auto = pick per call; PDR_GEMM_EPILOGUE=scalar|vec4 forces one (tests, A/B).
 int epilogue_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -860,6 +901,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   bool planned = false;
   // prefer the direct (no-transform) producer when the GEMM has no prologue
   for (int direct = (a.pro_mode == PDR_PRO_NONE && !a.add && !a.R) ? 1 : 0; direct >= 0 && !planned; --direct) {
+    if (a.a_rows && !direct) break;               // gathered A exists in the cp.async (direct) producer only
     plan.direct = direct;
     const size_t w_tile = WRES ? 0 : (size_t)BN * 128;
     const size_t stage = kATileBytes + w_tile + ((!direct && a.R) ? kATileBytes : 0);
@@ -875,12 +917,13 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     planned = true;
   }
   if (!planned) {
-    if (WRES || BN > 128) return kPlanDoesNotFit;   // caller retries with streamed weights / narrower column tiles
+    if (WRES || BN > 128) return kPlanDoesNotFit;
+    if (a.a_rows) { set_error("gemm_tf32: gathered A does not fit (K=%d N=%d)", a.K, a.N); return PDR_ERR_UNSUPPORTED; }   // caller retries with streamed weights / narrower column tiles
     set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N);
     return PDR_ERR_UNSUPPORTED;
   }
   const int mode = epilogue_mode();
-  const bool vec = mode == 2 ? a.rowadd != nullptr : mode == 1;
+  const bool vec = mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1;
   auto kern = vec ? gemm_tf32_persistent<BN, WRES, true> : gemm_tf32_persistent<BN, WRES, false>;
   static bool configured[2] = {false, false};
   if (!configured[vec]) {

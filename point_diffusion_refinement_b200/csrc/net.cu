@@ -434,6 +434,18 @@ gather_rows_kernel2(int n, int P, int C, const float *__restrict__ src, int lds,
   out[bp * ldo + c] = __ldg(src + ((size_t)b * n + j) * lds + c);
 }
 
+__global__ void __launch_bounds__(256)
+group_src_rows_kernel(int n, int P, int K, const int *__restrict__ idx32, const long long *__restrict__ idx64,
+                      const int *__restrict__ counts, int fill_missing, int *__restrict__ src_row, long long rows) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b*P + p)*K + k
+  if (row >= rows) return;
+  const long long bp = row / K;
+  const int b = (int)(bp / P);
+  const int j = idx64 ? (int)__ldg(idx64 + row) : __ldg(idx32 + row);
+  const bool miss = fill_missing && counts && __ldg(counts + bp) == 0;
+  src_row[row] = miss ? -1 : b * n + j;
+}
+
 inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 
 }  // namespace
@@ -449,7 +461,7 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   PDR_REQUIRE(a.A && a.W && a.C, "gemm_fused: null pointer");
   PDR_REQUIRE(a.K > 0 && a.N > 0 && a.batch > 0 && a.rows_per_sample > 0, "gemm_fused: bad sizes");
-  PDR_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && a.lda >= a.K && a.ldw >= a.K,
+  PDR_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && (a.a_rows || a.lda >= a.K) && a.ldw >= a.K,
               "gemm_fused: K/lda/ldw must be multiples of 4 (K=%d lda=%d ldw=%d)", a.K, a.lda, a.ldw);
   PDR_REQUIRE(a.ldc >= a.N && a.ldc_zero_to <= a.ldc, "gemm_fused: ldc=%d < N=%d", a.ldc, a.N);
   PDR_REQUIRE(a.pro_mode == PDR_PRO_NONE || (a.sc && a.sh && a.ld_scsh % 4 == 0 && ((uintptr_t)a.sc % 16) == 0 &&
@@ -464,6 +476,16 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   // else takes the SIMT kernel
   const bool tc_aligned = a.ldc % 4 == 0 && ((uintptr_t)a.C % 16) == 0 &&
                           (!a.rowadd || (a.ld_rowadd % 4 == 0 && ((uintptr_t)a.rowadd % 16) == 0));
+  if (a.a_rows) {
+    PDR_REQUIRE(a.A2 && a.k_split > 0 && a.k_split < a.K && a.k_split % 4 == 0 && a.lda2 % 4 == 0 &&
+                    a.lda >= a.k_split && a.lda2 >= a.K - a.k_split && ((uintptr_t)a.A2 % 16) == 0,
+                "gemm_fused: gathered A needs A2, k_split/lda2 multiples of 4, lda >= k_split, lda2 >= K - k_split");
+    PDR_REQUIRE(a.pro_mode == PDR_PRO_NONE && !a.add && !a.R, "gemm_fused: gathered A excludes prologue / add / R");
+    if (!(a.use_tf32 && tc_aligned)) {
+      set_error("gemm_fused: gathered A is implemented on the tensor-core path only (use_tf32, aligned output)");
+      return PDR_ERR_UNSUPPORTED;
+    }
+  }
   if (a.use_tf32 && tc_aligned) return launch_gemm_tf32(a, stream);
   const int tiles_per_sample = ceil_div(a.rows_per_sample, kTileM);
   const long long tiles = (long long)a.batch * tiles_per_sample;
@@ -544,6 +566,17 @@ extern "C" int pdr_group_knn(int batch, int n, int P, int K, int C, const float 
   group_knn_kernel<<<(unsigned)((rows + 7) / 8), dim3(32, 8), 0, (cudaStream_t)stream>>>(n, P, K, C, feat, ldf, y, x, idx,
                                                                                           dists, out, ldo, (int)rows);
   return check_launch("group_knn_kernel");
+}
+
+extern "C" int pdr_group_src_rows(int batch, int n, int P, int K, const void *idx, int idx_is_int64, const int *counts,
+                                  int fill_missing, int *src_row, void *stream) {
+  PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && idx && src_row, "group_src_rows: bad arguments");
+  PDR_REQUIRE((long long)batch * n < (1ll << 31), "group_src_rows: table too large");
+  const long long rows = (long long)batch * P * K;
+  group_src_rows_kernel<<<blocks_for(rows), 256, 0, (cudaStream_t)stream>>>(
+      n, P, K, idx_is_int64 ? nullptr : (const int *)idx, idx_is_int64 ? (const long long *)idx : nullptr, counts,
+      fill_missing, src_row, rows);
+  return check_launch("group_src_rows_kernel");
 }
 
 extern "C" int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, const int *idx, float *out,

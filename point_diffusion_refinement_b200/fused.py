@@ -50,7 +50,8 @@ class GemmArgs(ctypes.Structure):
                 ("rowadd", c_float_p), ("ld_rowadd", ctypes.c_int), ("rowadd_div", ctypes.c_int),
                 ("stats", c_float_p),
                 ("use_tf32", ctypes.c_int),
-                ("stats_skip", ctypes.c_int)]
+                ("stats_skip", ctypes.c_int),
+                ("a_rows", c_float_p), ("A2", c_float_p), ("lda2", ctypes.c_int), ("k_split", ctypes.c_int)]
 
 
 class GnSource(ctypes.Structure):
@@ -69,6 +70,8 @@ class GnArgs(ctypes.Structure):
 PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
 # A/B switch for profiling only: PDR_STATS_SKIP=0 makes every GEMM epilogue accumulate both statistics pairs
 _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
+# PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
+_FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
 
 
 def r4(c):
@@ -87,6 +90,23 @@ class View:
 
     def cols(self, col0, C):
         return View(self.t, C, self.col0 + col0)
+
+
+class GatheredA:
+    """A operand assembled inside the GEMM (PdrGemmArgs.a_rows): row r = [table[src_row[r], :Cp] | geo[r, :12]].
+    table: View of the (points, ld) feature table holding C channels (pad columns zero); src_row: int32 (rows,);
+    geo: View (rows, 12) = the 9 / 11 geometric channels of QueryAndGroup / group_knn."""
+
+    def __init__(self, table, src_row, geo, C, n_geo):
+        self.table, self.src_row, self.geo, self.C, self.n_geo = table, src_row, geo, C, n_geo
+        self.Cp = r4(C)
+        self.rows = geo.rows
+        self.K = self.Cp + geo.ld
+        assert table.ld % 4 == 0 and table.col0 % 4 == 0 and self.Cp <= table.ld - table.col0 and geo.ld % 4 == 0
+
+    def weight_layout(self):
+        """(src_col0, ncols, padded) segments mapping the reference's [feat(C) | geometric] input channels onto K."""
+        return [(0, self.C, self.Cp), (self.C, self.n_geo, self.geo.ld)]
 
 
 class Stats:
@@ -213,10 +233,19 @@ class FusedDenoiser:
         batch = self.B if batch is None else batch
         N, Kp = W.shape
         K = Kp if K is None else K
+        gathered = A if isinstance(A, GatheredA) else None
+        if gathered is not None:
+            assert pro == PRO_NONE and add is None and R is None and K == gathered.K, (K, gathered.K)
+            A = gathered.table
         assert K == Kp and K % 4 == 0 and A.ld % 4 == 0 and A.col0 % 4 == 0, (K, Kp, A.ld, A.col0)
-        assert A.rows == batch * rows_per_sample == out.rows, (A.rows, batch, rows_per_sample, out.rows)
+        rows_in = gathered.rows if gathered is not None else A.rows
+        assert rows_in == batch * rows_per_sample == out.rows, (rows_in, batch, rows_per_sample, out.rows)
         g = GemmArgs()
         g.A, g.lda, g.K = A.ptr, A.ld, K
+        if gathered is not None:
+            g.a_rows, g.A2 = gathered.src_row.data_ptr(), gathered.geo.ptr
+            g.lda2, g.k_split = gathered.geo.ld, gathered.Cp
+            self.keep.append(gathered)
         g.W, g.ldw = W.data_ptr(), Kp
         g.bias = bias.data_ptr() if bias is not None else None
         g.C, g.ldc, g.N = out.ptr, out.ld, N
@@ -244,7 +273,13 @@ class FusedDenoiser:
             g.W = W.data_ptr()
         self.keep += [g, W, bias]
         M = batch * rows_per_sample
-        nbytes = 4 * (M * K + M * N + (M * K if R is not None else 0) + N * K +
+        if gathered is not None:
+            assert g.use_tf32, "the gathered A operand exists on the tensor-core path only"
+            # algorithmic bytes: the feature table once (its rows are re-read from L2), geometric channels + row index
+            a_elems = min(M, A.rows) * gathered.Cp + M * (gathered.geo.ld + 1)
+        else:
+            a_elems = M * K
+        nbytes = 4 * (a_elems + M * N + (M * K if R is not None else 0) + N * K +
                       (M // rowadd_div * N if rowadd is not None else 0))
         self._emit("pdr_gemm_fused", ctypes.c_void_p(ctypes.addressof(g)),
                    info={"bytes": nbytes, "flops": 2 * M * N * K, "M": M, "N": N, "K": K})
@@ -336,6 +371,46 @@ class FusedDenoiser:
         table = self.T_all if v[0] == "t" else self.C_all
         return View(table, v[2], v[1])
 
+    def _gather_ok(self, feat, C, rows):
+        """The grouped tensor can stay virtual (assembled by the first GEMM's producers) on the tensor-core path."""
+        return (_FUSE_GATHER and self.use_tf32 and rows >= 512 and feat.ld % 4 == 0 and feat.col0 % 4 == 0
+                and r4(C) <= feat.ld - feat.col0)
+
+    def group_ball(self, feat, C, pts, n, centres, P, K, idx, cnt, fill):
+        """QueryAndGroup rows [feat(C) | rel | abs | centre] for the neighbour lists (idx, cnt): materialised
+        (pdr_group_ball) or, on the tensor-core path, as a GatheredA = (feature table, row index, geometric channels)."""
+        B = self.B
+        rows = B * P * K
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        if self._gather_ok(feat, C, rows):
+            geo = self._mat(rows, 12)
+            self._emit("pdr_group_ball", B, n, P, K, 0, None, 0, ptr(pts), ptr(centres), ptr(idx), ptr(cnt), int(fill),
+                       ctypes.c_void_p(geo.ptr), geo.ld)
+            src = self._zeros(rows, dtype=torch.int32)
+            self._emit("pdr_group_src_rows", B, n, P, K, ptr(idx), 0, ptr(cnt), int(fill), ptr(src))
+            return GatheredA(feat, src, geo, C, 9)
+        X0 = self._mat(rows, C + 9)
+        self._emit("pdr_group_ball", B, n, P, K, C, ctypes.c_void_p(feat.ptr), feat.ld, ptr(pts), ptr(centres), ptr(idx),
+                   ptr(cnt), int(fill), ctypes.c_void_p(X0.ptr), X0.ld)
+        return X0
+
+    def group_knn(self, feat, C, known_xyz, n_k, unknown_xyz, n_u, K, kidx, kd):
+        """group_knn rows [feat(C) | d2 | w | nn_abs | nn_rel | x] (pointnet2_utils.py:487-514), same two forms."""
+        B = self.B
+        rows = B * n_u * K
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        if self._gather_ok(feat, C, rows):
+            geo = self._mat(rows, 12)
+            self._emit("pdr_group_knn", B, n_k, n_u, K, 0, None, 0, ptr(known_xyz), ptr(unknown_xyz), ptr(kidx), ptr(kd),
+                       ctypes.c_void_p(geo.ptr), geo.ld)
+            src = self._zeros(rows, dtype=torch.int32)
+            self._emit("pdr_group_src_rows", B, n_k, n_u, K, ptr(kidx), 1, None, 0, ptr(src))
+            return GatheredA(feat, src, geo, C, 11)
+        X0 = self._mat(rows, C + 11)
+        self._emit("pdr_group_knn", B, n_k, n_u, K, C, ctypes.c_void_p(feat.ptr), feat.ld, ptr(known_xyz),
+                   ptr(unknown_xyz), ptr(kidx), ptr(kd), ctypes.c_void_p(X0.ptr), X0.ld)
+        return X0
+
     def grouped_block(self, name, X0, C0, K, rows_per_sample, mlp, att, query, counts, out, emb_views):
         """Mlp_plus_t_emb over grouped rows + AttentionModule pooling.
         X0: View (B*P*K, ld) holding C0 channels; query: View (B*P, ldq) with att.feat_conv.in_channels channels;
@@ -345,8 +420,13 @@ class FusedDenoiser:
         layers = self._mlp_layers(mlp)
         first_conv, first_gn = layers[0]
         assert first_conv.in_channels == C0, (name, first_conv.in_channels, C0)
-        Kp = r4(C0)
-        lay = [(0, C0, Kp)]
+        gathered = X0 if isinstance(X0, GatheredA) else None
+        if gathered is not None:
+            assert gathered.C + gathered.n_geo == C0
+            Kp, lay = gathered.K, gathered.weight_layout()
+        else:
+            Kp = r4(C0)
+            lay = [(0, C0, Kp)]
         c1 = first_conv.out_channels
         c_last = layers[-1][0].out_channels
         key_conv = att.grouped_feat_conv
@@ -379,14 +459,15 @@ class FusedDenoiser:
         b1 = torch.cat(b_parts, 0).contiguous()
         M = B * rows_per_sample
         Y1 = self._mat(M, col)
-        st1 = self.gemm(X0.cols(0, Kp) if X0.C != Kp else X0, W1, b1, Y1, rows_per_sample, want_stats=True)
+        A0 = gathered if gathered is not None else (X0.cols(0, Kp) if X0.C != Kp else X0)
+        st1 = self.gemm(A0, W1, b1, Y1, rows_per_sample, want_stats=True)
         y = Y1.cols(offs[0], r4(c1))
         y_cols = (offs[0], c1)
         if res_conv is not None:
             Rv = Y1.cols(offs[1], r4(c_last))
             key = Y1.cols(offs[2], r4(c_key)); key_col = offs[2]
         else:
-            assert C0 == c_last
+            assert C0 == c_last and gathered is None, "identity residual needs the materialised grouped tensor"
             Rv = X0
             key = Y1.cols(offs[1], r4(c_key)); key_col = offs[1]
         # remaining MLP layers
@@ -577,12 +658,7 @@ class FusedDenoiser:
             knn.append((lvl, kidx, kd))
         knn = {lvl: (a, b) for lvl, a, b in knn}
 
-        def group_ball(feat, C, pts, n, centres, P, K, idx, cnt, fill):
-            X0 = self._mat(B * P * K, C + 9)
-            self._emit("pdr_group_ball", B, n, P, K, C, ctypes.c_void_p(feat.ptr), feat.ld, ctypes.c_void_p(pts.data_ptr()),
-                       ctypes.c_void_p(centres.data_ptr()), ctypes.c_void_p(idx.data_ptr()),
-                       ctypes.c_void_p(cnt.data_ptr()), int(fill), ctypes.c_void_p(X0.ptr), X0.ld)
-            return X0
+        group_ball = self.group_ball
 
         # ---- encoder -----------------------------------------------------------------------------------
         Fl = []                                       # F[i]: [mapped(enc_map_dim[i]) | own(own_dim[i])]
@@ -632,10 +708,7 @@ class FusedDenoiser:
             kidx, kd = knn[lvl]
             n_u, n_k = n_lvl[lvl - 1], n_lvl[lvl]
             Ck = cdm + cd
-            X0 = self._mat(B * n_u * Kknn, Ck + 11)
-            self._emit("pdr_group_knn", B, n_k, n_u, Kknn, Ck, ctypes.c_void_p(Gl[lvl].ptr), Gl[lvl].ld,
-                       ctypes.c_void_p(xyz[lvl].data_ptr()), ctypes.c_void_p(xyz[lvl - 1].data_ptr()),
-                       ctypes.c_void_p(kidx.data_ptr()), ctypes.c_void_p(kd.data_ptr()), ctypes.c_void_p(X0.ptr), X0.ld)
+            X0 = self.group_knn(Gl[lvl], Ck, xyz[lvl], n_k, xyz[lvl - 1], n_u, Kknn, kidx, kd)
             D = dec_dim[lvl - 1]
             cskip = own_dim[lvl - 1]
             cm_prev = enc_map_dim[lvl - 1]
@@ -700,9 +773,7 @@ class FusedDenoiser:
                 self._emit("pdr_ball_query", B, n, P, ctypes.c_float(c_arch["radius"][i]), K, ptr(uvw[i + 1]), ptr(uvw[i]),
                            ptr(bidx), ptr(cnt))
                 Cin = enc_C[i]
-                X0 = self._mat(B * P * K, Cin + 9)
-                self._emit("pdr_group_ball", B, n, P, K, Cin, ctypes.c_void_p(Fc[i].ptr), Fc[i].ld, ptr(uvw[i]),
-                           ptr(uvw[i + 1]), ptr(bidx), ptr(cnt), 0, ctypes.c_void_p(X0.ptr), X0.ld)
+                X0 = self.group_ball(Fc[i], Cin, uvw[i], n, uvw[i + 1], P, K, bidx, cnt, False)
                 Qf = self._mat(B * P, Cin)
                 self._emit("pdr_gather_rows", B, n, P, Cin, ctypes.c_void_p(Fc[i].ptr), Fc[i].ld, ptr(idx),
                            ctypes.c_void_p(Qf.ptr), Qf.ld)
@@ -719,9 +790,7 @@ class FusedDenoiser:
                 kd = self._zeros(B, n_u, Kknn)
                 self._emit("pdr_knn_points", B, n_u, n_k, Kknn, ptr(uvw[i]), ptr(uvw[i + 1]), ptr(kd), ptr(kidx))
                 Ck = dec_C[i + 1]
-                X0 = self._mat(B * n_u * Kknn, Ck + 11)
-                self._emit("pdr_group_knn", B, n_k, n_u, Kknn, Ck, ctypes.c_void_p(Dc[i + 1].ptr), Dc[i + 1].ld,
-                           ptr(uvw[i + 1]), ptr(uvw[i]), ptr(kidx), ptr(kd), ctypes.c_void_p(X0.ptr), X0.ld)
+                X0 = self.group_knn(Dc[i + 1], Ck, uvw[i + 1], n_k, uvw[i], n_u, Kknn, kidx, kd)
                 D, cskip = dec_C[i], enc_C[i]
                 H = self._mat(B * n_u, D + cskip + 3)
                 self.grouped_block("cond_fp%d.mlp1" % i, X0, Ck + 11, Kknn, n_u * Kknn, fp.mlp1, fp.attention_module,

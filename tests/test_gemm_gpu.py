@@ -158,3 +158,77 @@ def test_gemm_stats_skip_hint(cuda_lib, case):
     C3, _ = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True, stats_skip=3)
     assert torch.equal(C0, C1) and torch.equal(C0, C2) and torch.equal(C0, C3)
     assert torch.equal(st1[..., :2], st0[..., :2]) and torch.equal(st2[..., 2:], st0[..., 2:])
+
+
+@pytest.mark.parametrize("shape", [(2, 4096, 35, 9, 140, 3000), (3, 1000, 4, 9, 96, 700), (2, 2048, 160, 11, 428, 512),
+                                   (1, 8320, 320, 11, 588, 64), (2, 640, 32, 9, 32, 5000)])
+def test_gemm_gathered_operand_equals_materialised(cuda_lib, shape):
+    """PdrGemmArgs.a_rows: A assembled by the producers from (feature table, row index, geometric channels) gives
+    bit for bit the GEMM over the materialised grouped tensor -- including rows whose index is -1 (zero features),
+    ragged last tiles and several column tiles."""
+    import ctypes
+    from point_diffusion_refinement_b200.fused import GemmArgs, tf32_round
+    B, rps, C, n_geo, N, table_rows = shape
+    g = torch.Generator().manual_seed(C * N + rps)
+    M, Cp = B * rps, (C + 3) // 4 * 4
+    K = Cp + 12
+    table = torch.zeros(table_rows, Cp + 4)                      # wider than Cp: a column slice of a wider buffer
+    table[:, :C] = torch.randn(table_rows, C, generator=g)
+    src = torch.randint(0, table_rows, (M,), generator=g, dtype=torch.int32)
+    src[torch.rand(M, generator=g) < 0.05] = -1
+    geo = torch.zeros(M, 12)
+    geo[:, :n_geo] = torch.randn(M, n_geo, generator=g)
+    W = tf32_round((torch.randn(N, K, generator=g) / K ** 0.5)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    X = torch.zeros(M, K)
+    ok = src >= 0
+    X[ok, :Cp] = table[src[ok].long(), :Cp]
+    X[:, Cp:] = geo
+    table, src, geo, X = table.to(DEV), src.to(DEV), geo.to(DEV), X.to(DEV)
+    C0, st0 = _run(cuda_lib, X, W, bias, B, rps, N, 0, None, None, None, None, None, 0, use_tf32=True)
+    ldc = (N + 3) // 4 * 4
+    Cg = torch.full((M, ldc), float("nan"), device=DEV)
+    tiles = (rps + cuda_lib.pdr_gemm_tile_rows() - 1) // cuda_lib.pdr_gemm_tile_rows()
+    stats = torch.zeros(B * tiles, N, 4, device=DEV)
+    a = GemmArgs()
+    a.A, a.lda, a.K = table.data_ptr(), table.stride(0), K
+    a.W, a.ldw, a.bias = W.data_ptr(), W.stride(0), bias.data_ptr()
+    a.C, a.ldc, a.N, a.ldc_zero_to = Cg.data_ptr(), ldc, N, ldc
+    a.batch, a.rows_per_sample, a.pro_mode = B, rps, 0
+    a.stats, a.use_tf32 = stats.data_ptr(), 1
+    a.a_rows, a.A2, a.lda2, a.k_split = src.data_ptr(), geo.data_ptr(), 12, Cp
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == 0, cuda_lib.pdr_last_error_string()
+    torch.cuda.synchronize()
+    assert torch.equal(Cg, C0)
+    assert torch.equal(stats.view(B, tiles, N, 4).sum(1), st0)
+    a.use_tf32 = 0                                               # the fp32 SIMT path has no gathered operand
+    assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == -4
+
+
+def test_group_src_rows_and_geometric_channels(cuda_lib):
+    """pdr_group_src_rows + pdr_group_ball(C = 0): together they carry exactly what the materialised grouping holds."""
+    import ctypes
+    from point_diffusion_refinement_b200 import _ext
+    from point_diffusion_refinement_b200._lib import call, dptr, stream_ptr
+    g = torch.Generator().manual_seed(4)
+    B, n, P, K, C = 2, 300, 64, 16, 8
+    xyz = (torch.rand(B, n, 3, generator=g) * 2 - 1).to(DEV)
+    centres = (torch.rand(B, P, 3, generator=g) * 2 - 1).to(DEV)
+    centres[0, 5] = 9.0                                          # a centre without neighbours
+    feat = torch.randn(B * n, C, generator=g).to(DEV)
+    idx, cnt = _ext.ball_query(centres, xyz, 0.4, K)
+    assert cnt[0, 5] == 0
+    for fill in (0, 1):
+        full = torch.zeros(B * P * K, C + 12, device=DEV)
+        call("pdr_group_ball", B, n, P, K, C, dptr(feat), C, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(full),
+             C + 12, stream_ptr(xyz))
+        geo = torch.zeros(B * P * K, 12, device=DEV)
+        call("pdr_group_ball", B, n, P, K, 0, None, 0, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(geo), 12,
+             stream_ptr(xyz))
+        src = torch.empty(B * P * K, dtype=torch.int32, device=DEV)
+        call("pdr_group_src_rows", B, n, P, K, dptr(idx), 0, dptr(cnt), fill, dptr(src), stream_ptr(xyz))
+        assert torch.equal(geo[:, :9], full[:, C:C + 9]) and geo[:, 9:].abs().sum() == 0
+        gathered = torch.where((src >= 0)[:, None], feat[src.clamp(min=0).long()], torch.zeros((), device=DEV))
+        assert torch.equal(gathered, full[:, :C])
+        assert (src.view(B, P, K)[0, 5] == -1).all() == bool(fill)
