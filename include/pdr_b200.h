@@ -241,6 +241,13 @@ int pdr_group_ball(int batch, int n, int P, int K, int C, const float *feat, int
  * (pointnet2_utils.py:487-514).  idx (B, P, K) int64 and dists (B, P, K) from pdr_knn_points. */
 int pdr_group_knn(int batch, int n, int P, int K, int C, const float *feat, int ldf, const float *y,
                   const float *x, const int64_t *idx, const float *dists, float *out, int ldo, void *stream);
+/* The two inputs of the gathered-A GEMM in one pass (thread per grouped row): geo (B*P*K, 12) =
+ * [rel(3) | abs(3) | centre(3) | 0 0 0] (ball) or [d2 | w | nn_abs(3) | nn_rel(3) | x(3) | 0] (kNN), bit-identical to
+ * the geometric channels pdr_group_ball / pdr_group_knn write, and src_row as pdr_group_src_rows. */
+int pdr_group_geo_ball(int batch, int n, int P, int K, const float *xyz, const float *centres, const int *idx,
+                       const int *counts, int fill_missing, float *geo, int *src_row, void *stream);
+int pdr_group_geo_knn(int batch, int n, int P, int K, const float *y, const float *x, const int64_t *idx,
+                      const float *dists, float *geo, int *src_row, void *stream);
 /* Flat feature-table row of every grouped row: src_row[(b*P+p)*K+k] = b*n + idx[b,p,k], or -1 where the subset=False
  * fill rule zeroes the features (fill_missing != 0 and counts[b,p] == 0).  idx is int32 (ball query) or, with
  * idx_is_int64 != 0, int64 (pdr_knn_points).  Feeds PdrGemmArgs.a_rows. */

@@ -59,6 +59,8 @@ SIGNATURES = {
     "pdr_group_ball": [_c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr,
                        _c_int, _ptr],
     "pdr_group_knn": [_c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
+    "pdr_group_geo_ball": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr],
+    "pdr_group_geo_knn": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "pdr_group_src_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _ptr],
     "pdr_gather_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr],
 }

@@ -434,6 +434,51 @@ gather_rows_kernel2(int n, int P, int C, const float *__restrict__ src, int lds,
   out[bp * ldo + c] = __ldg(src + ((size_t)b * n + j) * lds + c);
 }
 
+// Geometric channels + table row of every grouped row in one pass, thread per row (the form the gathered-A GEMM
+// consumes): geo[row] = [rel(3) | abs(3) | centre(3) | 0 0 0], src_row[row] = b*n + idx or -1 (fill rule).  Same
+// arithmetic as group_ball_kernel (rel = abs - centre, one rounding).
+__global__ void __launch_bounds__(256)
+group_geo_ball_kernel(int n, int P, int K, const float *__restrict__ xyz, const float *__restrict__ centres,
+                      const int *__restrict__ idx, const int *__restrict__ counts, int fill_missing,
+                      float *__restrict__ geo, int *__restrict__ src_row, int rows) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;             // (b*P + p)*K + k
+  if (row >= rows) return;
+  const int bp = row / K;
+  const int fb = (bp / P) * n + __ldg(idx + row);
+  const bool miss = fill_missing && counts && __ldg(counts + bp) == 0;
+  const float cx = __ldg(centres + (size_t)bp * 3), cy = __ldg(centres + (size_t)bp * 3 + 1),
+              cz = __ldg(centres + (size_t)bp * 3 + 2);
+  float ax = cx, ay = cy, az = cz;
+  if (!miss) { ax = __ldg(xyz + (size_t)fb * 3); ay = __ldg(xyz + (size_t)fb * 3 + 1); az = __ldg(xyz + (size_t)fb * 3 + 2); }
+  float4 *o = reinterpret_cast<float4 *>(geo + (size_t)row * 12);
+  o[0] = make_float4(ax - cx, ay - cy, az - cz, ax);
+  o[1] = make_float4(ay, az, cx, cy);
+  o[2] = make_float4(cz, 0.f, 0.f, 0.f);
+  src_row[row] = miss ? -1 : fb;
+}
+
+// kNN flavour: geo[row] = [d2 | w | nn_abs(3) | nn_rel(3) | x(3) | 0], w as in group_knn_kernel.
+__global__ void __launch_bounds__(256)
+group_geo_knn_kernel(int n, int P, int K, const float *__restrict__ y, const float *__restrict__ x,
+                     const long long *__restrict__ idx, const float *__restrict__ dists, float *__restrict__ geo,
+                     int *__restrict__ src_row, int rows) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int bp = row / K;
+  const int fb = (bp / P) * n + (int)__ldg(idx + row);
+  float norm = 0.f;
+  for (int k = 0; k < K; ++k) norm += 1.0f / (__ldg(dists + (size_t)bp * K + k) + 1e-8f);
+  const float d = __ldg(dists + row);
+  const float w = (1.0f / (d + 1e-8f)) / norm;
+  const float xx = __ldg(x + (size_t)bp * 3), xy = __ldg(x + (size_t)bp * 3 + 1), xz = __ldg(x + (size_t)bp * 3 + 2);
+  const float yx = __ldg(y + (size_t)fb * 3), yy = __ldg(y + (size_t)fb * 3 + 1), yz = __ldg(y + (size_t)fb * 3 + 2);
+  float4 *o = reinterpret_cast<float4 *>(geo + (size_t)row * 12);
+  o[0] = make_float4(d, w, yx, yy);
+  o[1] = make_float4(yz, yx - xx, yy - xy, yz - xz);
+  o[2] = make_float4(xx, xy, xz, 0.f);
+  src_row[row] = fb;
+}
+
 __global__ void __launch_bounds__(256)
 group_src_rows_kernel(int n, int P, int K, const int *__restrict__ idx32, const long long *__restrict__ idx64,
                       const int *__restrict__ counts, int fill_missing, int *__restrict__ src_row, long long rows) {
@@ -566,6 +611,28 @@ extern "C" int pdr_group_knn(int batch, int n, int P, int K, int C, const float 
   group_knn_kernel<<<(unsigned)((rows + 7) / 8), dim3(32, 8), 0, (cudaStream_t)stream>>>(n, P, K, C, feat, ldf, y, x, idx,
                                                                                           dists, out, ldo, (int)rows);
   return check_launch("group_knn_kernel");
+}
+
+extern "C" int pdr_group_geo_ball(int batch, int n, int P, int K, const float *xyz, const float *centres, const int *idx,
+                                  const int *counts, int fill_missing, float *geo, int *src_row, void *stream) {
+  PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && xyz && centres && idx && geo && src_row, "group_geo_ball: bad arguments");
+  const long long rows = (long long)batch * P * K;
+  PDR_REQUIRE(rows < (1ll << 31) && (long long)batch * n < (1ll << 31) && ((uintptr_t)geo % 16) == 0,
+              "group_geo_ball: too many rows or unaligned output");
+  group_geo_ball_kernel<<<blocks_for(rows), 256, 0, (cudaStream_t)stream>>>(n, P, K, xyz, centres, idx, counts, fill_missing,
+                                                                           geo, src_row, (int)rows);
+  return check_launch("group_geo_ball_kernel");
+}
+
+extern "C" int pdr_group_geo_knn(int batch, int n, int P, int K, const float *y, const float *x, const int64_t *idx,
+                                 const float *dists, float *geo, int *src_row, void *stream) {
+  PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && y && x && idx && dists && geo && src_row, "group_geo_knn: bad arguments");
+  const long long rows = (long long)batch * P * K;
+  PDR_REQUIRE(rows < (1ll << 31) && (long long)batch * n < (1ll << 31) && ((uintptr_t)geo % 16) == 0,
+              "group_geo_knn: too many rows or unaligned output");
+  group_geo_knn_kernel<<<blocks_for(rows), 256, 0, (cudaStream_t)stream>>>(n, P, K, y, x, (const long long *)idx, dists, geo,
+                                                                          src_row, (int)rows);
+  return check_launch("group_geo_knn_kernel");
 }
 
 extern "C" int pdr_group_src_rows(int batch, int n, int P, int K, const void *idx, int idx_is_int64, const int *counts,

@@ -384,10 +384,9 @@ class FusedDenoiser:
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
         if self._gather_ok(feat, C, rows):
             geo = self._mat(rows, 12)
-            self._emit("pdr_group_ball", B, n, P, K, 0, None, 0, ptr(pts), ptr(centres), ptr(idx), ptr(cnt), int(fill),
-                       ctypes.c_void_p(geo.ptr), geo.ld)
             src = self._zeros(rows, dtype=torch.int32)
-            self._emit("pdr_group_src_rows", B, n, P, K, ptr(idx), 0, ptr(cnt), int(fill), ptr(src))
+            self._emit("pdr_group_geo_ball", B, n, P, K, ptr(pts), ptr(centres), ptr(idx), ptr(cnt), int(fill),
+                       ctypes.c_void_p(geo.ptr), ptr(src))
             return GatheredA(feat, src, geo, C, 9)
         X0 = self._mat(rows, C + 9)
         self._emit("pdr_group_ball", B, n, P, K, C, ctypes.c_void_p(feat.ptr), feat.ld, ptr(pts), ptr(centres), ptr(idx),
@@ -401,10 +400,9 @@ class FusedDenoiser:
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
         if self._gather_ok(feat, C, rows):
             geo = self._mat(rows, 12)
-            self._emit("pdr_group_knn", B, n_k, n_u, K, 0, None, 0, ptr(known_xyz), ptr(unknown_xyz), ptr(kidx), ptr(kd),
-                       ctypes.c_void_p(geo.ptr), geo.ld)
             src = self._zeros(rows, dtype=torch.int32)
-            self._emit("pdr_group_src_rows", B, n_k, n_u, K, ptr(kidx), 1, None, 0, ptr(src))
+            self._emit("pdr_group_geo_knn", B, n_k, n_u, K, ptr(known_xyz), ptr(unknown_xyz), ptr(kidx), ptr(kd),
+                       ctypes.c_void_p(geo.ptr), ptr(src))
             return GatheredA(feat, src, geo, C, 11)
         X0 = self._mat(rows, C + 11)
         self._emit("pdr_group_knn", B, n_k, n_u, K, C, ctypes.c_void_p(feat.ptr), feat.ld, ptr(known_xyz),

@@ -1,0 +1,32 @@
+"""HBM ceilings by access mix on this GPU (CUDA events, best of 10): write-only (memset), read-only (reduction),
+copy (1:1) and a 1:3 read:write mix -- the mixes the GEMMs of the step actually have.  Prints one JSON line."""
+import json
+import torch
+
+dev = torch.device("cuda")
+n = 1 << 30                                   # 4 GiB of fp32
+a = torch.empty(n, dtype=torch.float32, device=dev)
+b = torch.empty(n, dtype=torch.float32, device=dev)
+a.fill_(1.0); b.fill_(2.0)
+
+
+def best(fn, nbytes, reps=10):
+    fn(); torch.cuda.synchronize()
+    t = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        t = min(t, e0.elapsed_time(e1))
+    return nbytes / t / 1e6
+
+
+q = n // 4
+out = {
+    "write_only_GBps": best(lambda: a.zero_(), 4 * n),
+    "read_only_GBps": best(lambda: torch.sum(a), 4 * n),
+    "copy_GBps": best(lambda: b.copy_(a), 8 * n),
+    # read n/4, write 3n/4 ... expand of a quarter-sized source into three quarter-sized destinations
+    "read1_write3_GBps": best(lambda: b[:3 * q].view(3, q).copy_(a[:q].unsqueeze(0).expand(3, q)), 4 * 4 * q),
+    "read2_write1_GBps": best(lambda: torch.add(a[:q], a[q:2 * q], out=b[:q]), 4 * 3 * q),
+}
+print(json.dumps(out))

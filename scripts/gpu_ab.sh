@@ -21,3 +21,4 @@ except Exception as e:
     print("bench failed", e); print(open("$out/bench_$i.err").read()[-1500:])
 PY
 done
+if [ -n "$BW_PROBE" ]; then python scripts/bw_probe.py | tee $out/bw_probe.json; fi

@@ -232,3 +232,33 @@ def test_group_src_rows_and_geometric_channels(cuda_lib):
         gathered = torch.where((src >= 0)[:, None], feat[src.clamp(min=0).long()], torch.zeros((), device=DEV))
         assert torch.equal(gathered, full[:, :C])
         assert (src.view(B, P, K)[0, 5] == -1).all() == bool(fill)
+
+
+def test_group_geo_kernels_match_the_grouping_kernels(cuda_lib):
+    """pdr_group_geo_ball / pdr_group_geo_knn (one pass, thread per row) against pdr_group_ball / pdr_group_knn with C = 0
+    and pdr_group_src_rows: bit-identical."""
+    from point_diffusion_refinement_b200 import _ext, knn
+    from point_diffusion_refinement_b200._lib import call, dptr, stream_ptr
+    g = torch.Generator().manual_seed(8)
+    B, n, P, K = 3, 500, 200, 32
+    xyz = (torch.rand(B, n, 3, generator=g) * 2 - 1).to(DEV)
+    centres = (torch.rand(B, P, 3, generator=g) * 2 - 1).to(DEV)
+    centres[1, 7] = 5.0
+    idx, cnt = _ext.ball_query(centres, xyz, 0.3, K)
+    rows = B * P * K
+    for fill in (0, 1):
+        ref = torch.zeros(rows, 12, device=DEV); src_ref = torch.empty(rows, dtype=torch.int32, device=DEV)
+        call("pdr_group_ball", B, n, P, K, 0, None, 0, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(ref), 12, stream_ptr(xyz))
+        call("pdr_group_src_rows", B, n, P, K, dptr(idx), 0, dptr(cnt), fill, dptr(src_ref), stream_ptr(xyz))
+        geo = torch.full((rows, 12), float("nan"), device=DEV); src = torch.empty(rows, dtype=torch.int32, device=DEV)
+        call("pdr_group_geo_ball", B, n, P, K, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(geo), dptr(src), stream_ptr(xyz))
+        assert torch.equal(geo, ref) and torch.equal(src, src_ref)
+    Kn = 8
+    kn = knn.knn_points(centres, xyz, K=Kn)
+    rows = B * P * Kn
+    ref = torch.zeros(rows, 12, device=DEV); src_ref = torch.empty(rows, dtype=torch.int32, device=DEV)
+    call("pdr_group_knn", B, n, P, Kn, 0, None, 0, dptr(xyz), dptr(centres), dptr(kn.idx), dptr(kn.dists), dptr(ref), 12, stream_ptr(xyz))
+    call("pdr_group_src_rows", B, n, P, Kn, dptr(kn.idx), 1, None, 0, dptr(src_ref), stream_ptr(xyz))
+    geo = torch.full((rows, 12), float("nan"), device=DEV); src = torch.empty(rows, dtype=torch.int32, device=DEV)
+    call("pdr_group_geo_knn", B, n, P, Kn, dptr(xyz), dptr(centres), dptr(kn.idx), dptr(kn.dists), dptr(geo), dptr(src), stream_ptr(xyz))
+    assert torch.equal(geo, ref) and torch.equal(src, src_ref)
