@@ -194,6 +194,13 @@ typedef struct PdrGemmArgs {
    * every grouped row (pdr_group_src_rows), A2 the (M, lda2) geometric channels (pdr_group_ball / _knn with C = 0).
    * k_split, lda2 multiples of 4; A2 16-byte aligned. */
   const int *a_rows; const float *A2; int lda2; int k_split;
+  /* pooling epilogue (tensor-core path): when pool_K > 0 this GEMM computes the attention SCORES and, instead of
+   * storing them (C may be NULL), pools straight away -- pdr_attention_pool fused into the epilogue:
+   *   pool_out[point, n] = sum_k softmax_k(score[point*K + k, n] masked to k < max(count[point], 1))
+   *                              * relu(pool_V[point*K + k, n] * pool_sc[b, n] + pool_sh[b, n])
+   * pool_K in {8, 16, 32} and divides rows_per_sample; stats and rowadd must be NULL. */
+  int pool_K; const float *pool_V; int pool_ldv; const float *pool_sc; const float *pool_sh; int pool_ld_scsh;
+  const int *pool_counts; float *pool_out; int pool_ldo;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);

@@ -128,7 +128,8 @@ struct TcPlan {
   int r_off;            // offset of the residual tile inside a stage (transform mode with R)
 };
 
-template <int BN, bool WRES, bool VEC>
+// EPI: 0 = scalar epilogue, 1 = float4 epilogue, 2 = attention pooling over the K neighbour rows (no C store)
+template <int BN, bool WRES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   constexpr int kBTileBytes = BN * 128;
@@ -514,7 +515,10 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     // =============================== EPILOGUE ================================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     const int half = warp >> 2;                   // which of the two warps sharing this lane quarter
-    constexpr int CW = BN == 32 ? 16 : 32;   // epilogue block width
+    constexpr bool VEC = EPI == 1, POOL = EPI == 2;
+    // epilogue block width: 32 columns; 16 for the narrowest tile so that all 8 warps have work there (the pooling
+    // epilogue keeps whole 32-row groups in one warp instead: lane = column, rows = the K neighbours of 32 / K points)
+    constexpr int CW = (BN == 32 && !POOL) ? 16 : 32;
     // transpose tile row stride (floats): odd for the scalar phase pair, CW + 4 keeps float4 alignment (VEC)
     constexpr int kTs = VEC ? CW + 4 : CW + 1;
     float *s_t = s_epi[warp];
@@ -556,7 +560,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       for (int cb = half * CW; cb < BN; cb += 2 * CW) {
         // the two warps of a lane quarter alternate CW-column blocks: CW = 32 normally, 16 for the narrowest tile
         // (BN = 32) so that all 8 warps have work there as well
-        if (n0 + cb >= a.ldc_zero_to && n0 + cb >= a.N) break;      // nothing to write in this or later blocks
+        if (n0 + cb >= a.N && (POOL || n0 + cb >= a.ldc_zero_to)) break;   // nothing to write in this or later blocks
         uint32_t v[CW];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cb);
         if constexpr (CW == 32) {
@@ -577,7 +581,44 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
               : "r"(taddr));
         }
-        if constexpr (VEC) {
+        if constexpr (POOL) {
+          // ---- soft-attention pooling fused into the score GEMM (AttentionModule, attention.py:85-96): this GEMM's
+          //      output IS the score tensor; instead of storing it, every lane (= output channel) runs the masked
+          //      softmax over the K neighbour rows of each point held by this warp and accumulates the GroupNorm-ed,
+          //      ReLU-ed values read from V.  Same operation order as attention_pool_kernel -> same bits. ----
+          const int n = n0 + cb + lane;
+          const bool nin = n < a.N;
+          const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
+          const float gs = nin ? __ldg(a.pool_sc + (size_t)b * a.pool_ld_scsh + n) : 0.f;
+          const float gh = nin ? __ldg(a.pool_sh + (size_t)b * a.pool_ld_scsh + n) : 0.f;
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  #pragma unroll
+          for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          const int PK = a.pool_K;
+          const float *st = s_t + lane;
+          const float *vp = a.pool_V + wrow0 * (size_t)a.pool_ldv + (nin ? n : 0);
+          for (int r0g = 0; r0g < wrows; r0g += PK) {             // wrows is a multiple of PK (rows_per_sample % PK == 0)
+            const size_t point = (wrow0 + r0g) / (size_t)PK;      // b*P + p
+            int cnt = PK;
+            if (a.pool_counts) { cnt = __ldg(a.pool_counts + point); cnt = cnt < 1 ? 1 : cnt; }
+            float mx = -3.0e38f;
+  #pragma unroll 8
+            for (int k = 0; k < PK; ++k) mx = fmaxf(mx, k < cnt ? st[(r0g + k) * kTs] + bias_n : -1e9f);
+            float den = 0.f, num = 0.f;
+            const float *vk = vp + (size_t)r0g * a.pool_ldv;
+  #pragma unroll 8
+            for (int k = 0; k < PK; ++k) {
+              const float sk = k < cnt ? st[(r0g + k) * kTs] + bias_n : -1e9f;
+              const float e = expf(sk - mx);
+              den += e;
+              num = fmaf(e, fmaxf(fmaf(__ldg(vk), gs, gh), 0.f), num);
+              vk += a.pool_ldv;
+            }
+            if (nin) a.pool_out[point * (size_t)a.pool_ldo + n] = num / den;
+          }
+          __syncwarp();                                         // before the next block overwrites the tile
+        } else if constexpr (VEC) {
           // lane mapping of the store phase: LPR lanes cover one row of the block as float4s, a store instruction
           // writes RPI rows, a lane walks ITERS consecutive rows.  The per-column loads are issued before the TMEM
           // load is waited for.
@@ -923,9 +964,10 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     return PDR_ERR_UNSUPPORTED;
   }
   const int mode = epilogue_mode();
-  const bool vec = mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1;
-  auto kern = vec ? gemm_tf32_persistent<BN, WRES, true> : gemm_tf32_persistent<BN, WRES, false>;
-  static bool configured[2] = {false, false};
+  const int vec = a.pool_K > 0 ? 2 : ((mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1) ? 1 : 0);
+  auto kern = vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
+                       : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
+  static bool configured[3] = {false, false, false};
   if (!configured[vec]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }

@@ -504,7 +504,7 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   PDR_REQUIRE(args, "gemm_fused: null args");
   const PdrGemmArgs &a = *args;
   cudaStream_t stream = (cudaStream_t)stream_;
-  PDR_REQUIRE(a.A && a.W && a.C, "gemm_fused: null pointer");
+  PDR_REQUIRE(a.A && a.W && (a.C || a.pool_K > 0), "gemm_fused: null pointer");
   PDR_REQUIRE(a.K > 0 && a.N > 0 && a.batch > 0 && a.rows_per_sample > 0, "gemm_fused: bad sizes");
   PDR_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && (a.a_rows || a.lda >= a.K) && a.ldw >= a.K,
               "gemm_fused: K/lda/ldw must be multiples of 4 (K=%d lda=%d ldw=%d)", a.K, a.lda, a.ldw);
@@ -521,6 +521,16 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   // else takes the SIMT kernel
   const bool tc_aligned = a.ldc % 4 == 0 && ((uintptr_t)a.C % 16) == 0 &&
                           (!a.rowadd || (a.ld_rowadd % 4 == 0 && ((uintptr_t)a.rowadd % 16) == 0));
+  if (a.pool_K > 0) {
+    PDR_REQUIRE((a.pool_K == 8 || a.pool_K == 16 || a.pool_K == 32) && a.rows_per_sample % a.pool_K == 0 && a.pool_V &&
+                    a.pool_sc && a.pool_sh && a.pool_out && !a.stats && !a.rowadd,
+                "gemm_fused: pooling epilogue needs K in {8,16,32} dividing rows_per_sample, V/sc/sh/out, no stats/rowadd");
+    if (!a.use_tf32) {
+      set_error("gemm_fused: the pooling epilogue is implemented on the tensor-core path only");
+      return PDR_ERR_UNSUPPORTED;
+    }
+    return launch_gemm_tf32(a, stream);
+  }
   if (a.a_rows) {
     PDR_REQUIRE(a.A2 && a.k_split > 0 && a.k_split < a.K && a.k_split % 4 == 0 && a.lda2 % 4 == 0 &&
                     a.lda >= a.k_split && a.lda2 >= a.K - a.k_split && ((uintptr_t)a.A2 % 16) == 0,

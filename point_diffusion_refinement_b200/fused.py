@@ -51,7 +51,10 @@ class GemmArgs(ctypes.Structure):
                 ("stats", c_float_p),
                 ("use_tf32", ctypes.c_int),
                 ("stats_skip", ctypes.c_int),
-                ("a_rows", c_float_p), ("A2", c_float_p), ("lda2", ctypes.c_int), ("k_split", ctypes.c_int)]
+                ("a_rows", c_float_p), ("A2", c_float_p), ("lda2", ctypes.c_int), ("k_split", ctypes.c_int),
+                ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
+                ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
+                ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int)]
 
 
 class GnSource(ctypes.Structure):
@@ -72,6 +75,8 @@ PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
 _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
 # PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
 _FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
+# PDR_FUSE_POOL=0 stores the attention scores and pools with pdr_attention_pool (what the fp32 path always does)
+_FUSE_POOL = os.environ.get("PDR_FUSE_POOL", "1") != "0"
 
 
 def r4(c):
@@ -228,7 +233,7 @@ class FusedDenoiser:
         self._ops.append(fn)
 
     def gemm(self, A, W, bias, out, rows_per_sample, batch=None, pro=PRO_NONE, scsh=None, add=None, R=None,
-             rowadd=None, rowadd_div=1, want_stats=False, K=None, zero_to=None):
+             rowadd=None, rowadd_div=1, want_stats=False, K=None, zero_to=None, pool=None):
         """out[:, :N] = pro(A[:, :K]) @ W^T + bias (+rowadd).  W: torch (N, Kpad).  Returns Stats or None."""
         batch = self.B if batch is None else batch
         N, Kp = W.shape
@@ -239,7 +244,8 @@ class FusedDenoiser:
             A = gathered.table
         assert K == Kp and K % 4 == 0 and A.ld % 4 == 0 and A.col0 % 4 == 0, (K, Kp, A.ld, A.col0)
         rows_in = gathered.rows if gathered is not None else A.rows
-        assert rows_in == batch * rows_per_sample == out.rows, (rows_in, batch, rows_per_sample, out.rows)
+        assert rows_in == batch * rows_per_sample, (rows_in, batch, rows_per_sample)
+        assert (out is None and pool is not None) or out.rows == rows_in
         g = GemmArgs()
         g.A, g.lda, g.K = A.ptr, A.ld, K
         if gathered is not None:
@@ -248,8 +254,20 @@ class FusedDenoiser:
             self.keep.append(gathered)
         g.W, g.ldw = W.data_ptr(), Kp
         g.bias = bias.data_ptr() if bias is not None else None
-        g.C, g.ldc, g.N = out.ptr, out.ld, N
-        g.ldc_zero_to = (out.ld - out.col0) if zero_to is None else zero_to
+        if out is not None:
+            g.C, g.ldc, g.N = out.ptr, out.ld, N
+            g.ldc_zero_to = (out.ld - out.col0) if zero_to is None else zero_to
+        else:
+            g.C, g.ldc, g.N, g.ldc_zero_to = None, r4(N), N, N
+        if pool is not None:
+            # (K, V View, scv View, shv View, counts tensor|None, out View): pdr_attention_pool in the epilogue
+            pK, pV, psc, psh, pcnt, pout = pool
+            assert not want_stats and rowadd is None and rows_per_sample % pK == 0 and pV.rows == rows_in
+            g.pool_K, g.pool_V, g.pool_ldv = pK, pV.ptr, pV.ld
+            g.pool_sc, g.pool_sh, g.pool_ld_scsh = psc.ptr, psh.ptr, psc.ld
+            g.pool_counts = pcnt.data_ptr() if pcnt is not None else None
+            g.pool_out, g.pool_ldo = pout.ptr, pout.ld
+            self.keep.append(pool)
         g.batch, g.rows_per_sample = batch, rows_per_sample
         g.pro_mode = pro
         if pro != PRO_NONE:
@@ -279,7 +297,8 @@ class FusedDenoiser:
             a_elems = min(M, A.rows) * gathered.Cp + M * (gathered.geo.ld + 1)
         else:
             a_elems = M * K
-        nbytes = 4 * (a_elems + M * N + (M * K if R is not None else 0) + N * K +
+        out_elems = M * N if pool is None else (M * N + M // pool[0] * N)     # pooled: V read + pooled rows written
+        nbytes = 4 * (a_elems + out_elems + (M * K if R is not None else 0) + N * K +
                       (M // rowadd_div * N if rowadd is not None else 0))
         self._emit("pdr_gemm_fused", ctypes.c_void_p(ctypes.addressof(g)),
                    info={"bytes": nbytes, "flops": 2 * M * N * K, "M": M, "N": N, "K": K})
@@ -502,14 +521,25 @@ class FusedDenoiser:
                           want_stats=True)
         scsh2 = self.gn([(st_s1, 0, inter, True, 1.0)], gn_w2)
         c_out = conv_w2.out_channels
-        S = self._mat(M, c_out)
-        self.gemm(S1, _pack([(_conv_w(conv_w2), [(0, inter, r4(inter))])], self.dev), _bias(conv_w2, c_out, self.dev), S,
-                  rows_per_sample, pro=PRO_RELU_GN, scsh=scsh2)
         fo = list(att.feat_out_conv)  # [Conv, GN, ReLU]
         conv_v, gn_v = fo[0], fo[1]
+        W_s = _pack([(_conv_w(conv_w2), [(0, inter, r4(inter))])], self.dev)
+        W_v = _pack([(_conv_w(conv_v), [(0, c_last, r4(c_last))])], self.dev)
         V = self._mat(M, c_out)
-        st_v = self.gemm(y, _pack([(_conv_w(conv_v), [(0, c_last, r4(c_last))])], self.dev), _bias(conv_v, c_out, self.dev),
-                         V, rows_per_sample, pro=PRO_GN_RELU, scsh=scsh_last, add=add_last, R=Rv, want_stats=True)
+        tc = self.use_tf32 and M >= 512
+        if _FUSE_POOL and tc and K in (8, 16, 32) and rows_per_sample % K == 0:
+            # values first (their GroupNorm statistics must be final), then the score GEMM pools in its epilogue:
+            # the score tensor is never written
+            st_v = self.gemm(y, W_v, _bias(conv_v, c_out, self.dev), V, rows_per_sample, pro=PRO_GN_RELU, scsh=scsh_last,
+                             add=add_last, R=Rv, want_stats=True)
+            scv, shv = self.gn([(st_v, 0, c_out, False, 1.0)], gn_v)
+            self.gemm(S1, W_s, _bias(conv_w2, c_out, self.dev), None, rows_per_sample, pro=PRO_RELU_GN, scsh=scsh2,
+                      pool=(K, V, scv, shv, counts, out))
+            return
+        S = self._mat(M, c_out)
+        self.gemm(S1, W_s, _bias(conv_w2, c_out, self.dev), S, rows_per_sample, pro=PRO_RELU_GN, scsh=scsh2)
+        st_v = self.gemm(y, W_v, _bias(conv_v, c_out, self.dev), V, rows_per_sample, pro=PRO_GN_RELU, scsh=scsh_last,
+                         add=add_last, R=Rv, want_stats=True)
         scv, shv = self.gn([(st_v, 0, c_out, False, 1.0)], gn_v)
         self._emit("pdr_attention_pool", B, P, K, c_out, ctypes.c_void_p(S.ptr), S.ld, ctypes.c_void_p(V.ptr), V.ld,
                    ctypes.c_void_p(scv.ptr), ctypes.c_void_p(shv.ptr), scv.ld,

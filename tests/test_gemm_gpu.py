@@ -262,3 +262,48 @@ def test_group_geo_kernels_match_the_grouping_kernels(cuda_lib):
     geo = torch.full((rows, 12), float("nan"), device=DEV); src = torch.empty(rows, dtype=torch.int32, device=DEV)
     call("pdr_group_geo_knn", B, n, P, Kn, dptr(xyz), dptr(centres), dptr(kn.idx), dptr(kn.dists), dptr(geo), dptr(src), stream_ptr(xyz))
     assert torch.equal(geo, ref) and torch.equal(src, src_ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 4096, 32, 32, 32, True), (2, 2048, 64, 128, 8, False), (3, 1024, 128, 300, 8, False),
+                                   (2, 4000, 32, 64, 32, True), (2, 640, 256, 256, 16, True)])
+def test_gemm_pooling_epilogue_equals_attention_pool(cuda_lib, shape):
+    """PdrGemmArgs.pool_*: the score GEMM that pools in its epilogue gives bit for bit what the stored scores +
+    pdr_attention_pool give (same tensor-core accumulators, same softmax operation order)."""
+    import ctypes
+    from point_diffusion_refinement_b200._lib import call, dptr, stream_ptr
+    from point_diffusion_refinement_b200.fused import GemmArgs, tf32_round
+    B, rps, K, N, PK, with_counts = shape
+    g = torch.Generator().manual_seed(K * N + rps + PK)
+    M, P = B * rps, rps // PK
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = tf32_round((torch.randn(N, K, generator=g) / K ** 0.5)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    sc = (1 + 0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    sh = (0.2 * torch.randn(B, K, generator=g)).to(DEV)
+    ldn = (N + 3) // 4 * 4
+    V = torch.randn(M, ldn, generator=g).to(DEV)
+    vsc = (1 + 0.2 * torch.randn(B, ldn, generator=g)).to(DEV)
+    vsh = (0.2 * torch.randn(B, ldn, generator=g)).to(DEV)
+    counts = torch.randint(0, PK + 1, (B * P,), generator=g, dtype=torch.int32).to(DEV) if with_counts else None
+    S, _ = _run(cuda_lib, A, W, bias, B, rps, N, 2, sc, sh, None, None, None, 0, use_tf32=True, want_stats=False)
+    ref = torch.zeros(B * P, ldn + 4, device=DEV)
+    call("pdr_attention_pool", B, P, PK, N, dptr(S), S.stride(0), dptr(V), ldn, dptr(vsc), dptr(vsh), ldn, dptr(counts),
+         dptr(ref), ldn + 4, stream_ptr(S))
+    out = torch.zeros(B * P, ldn + 4, device=DEV)
+    a = GemmArgs()
+    a.A, a.lda, a.K = A.data_ptr(), A.stride(0), K
+    a.W, a.ldw, a.bias = W.data_ptr(), W.stride(0), bias.data_ptr()
+    a.C, a.ldc, a.N, a.ldc_zero_to = None, ldn, N, N
+    a.batch, a.rows_per_sample, a.pro_mode = B, rps, 2
+    a.sc, a.sh, a.ld_scsh = sc.data_ptr(), sh.data_ptr(), sc.stride(0)
+    a.use_tf32 = 1
+    a.pool_K, a.pool_V, a.pool_ldv = PK, V.data_ptr(), ldn
+    a.pool_sc, a.pool_sh, a.pool_ld_scsh = vsc.data_ptr(), vsh.data_ptr(), ldn
+    a.pool_counts = counts.data_ptr() if counts is not None else None
+    a.pool_out, a.pool_ldo = out.data_ptr(), ldn + 4
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == 0, cuda_lib.pdr_last_error_string()
+    torch.cuda.synchronize()
+    assert torch.isfinite(ref).all() and torch.equal(out, ref)
+    a.use_tf32 = 0
+    assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == -4
