@@ -126,6 +126,8 @@ struct TcPlan {
   int direct;           // 1: no prologue -> cp.async lands straight in the MMA ring; 0: raw ring + transform
   int stage_bytes;      // bytes of one ring stage: A tile [+ W tile when streamed] [+ residual tile]
   int r_off;            // offset of the residual tile inside a stage (transform mode with R)
+  int epi_alt;          // 1: the two groups of 4 epilogue warps take alternate TILES (one accumulator each);
+                        // 0: both groups share every tile and alternate its column blocks
 };
 
 // EPI: 0 = scalar epilogue, 1 = float4 epilogue, 2 = attention pooling over the K neighbour rows (no C store)
@@ -161,7 +163,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     const int full_count = plan.direct ? kProdThreads : kProdThreads + kLoadThreads;
     for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], full_count); mbar_init(&bar_empty[s], 1); }
     mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
-    mbar_init(&bar_tempty[0], kEpiThreads); mbar_init(&bar_tempty[1], kEpiThreads);
+    const uint32_t tempty_count = plan.epi_alt ? kEpiThreads / 2 : kEpiThreads;
+    mbar_init(&bar_tempty[0], tempty_count); mbar_init(&bar_tempty[1], tempty_count);
     mbar_init(&bar_wready, kProdThreads);
     for (int r = 0; r < S; ++r) mbar_init(&bar_rfull[r], kLoadThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -522,22 +525,23 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     // transpose tile row stride (floats): odd for the scalar phase pair, CW + 4 keeps float4 alignment (VEC)
     constexpr int kTs = VEC ? CW + 4 : CW + 1;
     float *s_t = s_epi[warp];
-    int acc = 0, acc_phase = 0;
-    // item geometry: divisions only when the item sequence is irregular (several column tiles, or fewer row
-    // tiles per sample than CTAs); the common case advances (b, tile-in-sample) incrementally
+    // Two groups of 4 warps (one warp per TMEM lane quarter each).  epi_alt: group g owns accumulator g and every
+    // second tile of this CTA, so the epilogues of two tiles overlap -- the small-tile GEMMs are bound by the LATENCY
+    // of one tile's epilogue (TMEM load -> transpose -> stores -> statistics barrier), not by its instruction count.
+    // Otherwise both groups work on the same tile and alternate its column blocks.
+    const bool alt = plan.epi_alt != 0;
+    int acc = alt ? half : 0, acc_phase = 0;
     const int G = (int)gridDim.x;
-    const bool fast_adv = plan.n_tiles_n == 1 && plan.tiles_per_sample >= G;
+    const int item_step = alt ? 2 * G : G;
+    const int cb0 = alt ? 0 : half * CW, cb_step = alt ? CW : 2 * CW;
+    const uint32_t s_part_g = s_part + (alt ? (uint32_t)(half * 4 * BN * 16) : 0u);
+    const int stat_bar = alt ? 1 + half : 1, stat_threads = alt ? kEpiThreads / 2 : kEpiThreads;
+    const int stat_tid = alt ? (tid & (kEpiThreads / 2 - 1)) : tid;
     const bool radd_split = a.rowadd && a.rows_per_sample % a.rowadd_div == 0;   // groups never straddle samples
     const int groups_per_sample = a.rowadd ? a.rows_per_sample / a.rowadd_div : 0;
-    int b = 0, tis = 0, n0 = 0, tile = 0;
-    for (int item = blockIdx.x; item < plan.total_items; item += G) {
-      if (fast_adv && item != (int)blockIdx.x) {
-        tis += G; tile += G;
-        if (tis >= plan.tiles_per_sample) { tis -= plan.tiles_per_sample; ++b; }
-      } else {
-        tile = item / plan.n_tiles_n; n0 = (item - tile * plan.n_tiles_n) * BN;
-        b = tile / plan.tiles_per_sample; tis = tile - b * plan.tiles_per_sample;
-      }
+    for (int item = (int)blockIdx.x + (alt ? half * G : 0); item < plan.total_items; item += item_step) {
+      const int tile = item / plan.n_tiles_n, n0 = (item - tile * plan.n_tiles_n) * BN;
+      const int b = tile / plan.tiles_per_sample, tis = tile - b * plan.tiles_per_sample;
       const int r0 = tis * kTcTileM;
       const size_t row_base = (size_t)b * a.rows_per_sample + r0;
       const int rows_valid = min(kTcTileM, a.rows_per_sample - r0);
@@ -557,9 +561,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       mbar_wait(&bar_tfull[acc], (uint32_t)acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cb = half * CW; cb < BN; cb += 2 * CW) {
-        // the two warps of a lane quarter alternate CW-column blocks: CW = 32 normally, 16 for the narrowest tile
-        // (BN = 32) so that all 8 warps have work there as well
+      for (int cb = cb0; cb < BN; cb += cb_step) {
+        // CW-column blocks: CW = 32 normally, 16 for the narrowest tile (BN = 32)
         if (n0 + cb >= a.N && (POOL || n0 + cb >= a.ldc_zero_to)) break;   // nothing to write in this or later blocks
         uint32_t v[CW];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + cb);
@@ -795,7 +798,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
                 tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
               }
               const int col = 4 * (lane % LPR) + lane / LPR;
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part + (uint32_t)((quarter * BN + cb + col) * 16)),
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part_g + (uint32_t)((quarter * BN + cb + col) * 16)),
                            "f"(tot.x), "f"(tot.y), "f"(tot.z), "f"(tot.w) : "memory");
             }
             __syncwarp();                                       // before the next block overwrites the tile
@@ -875,7 +878,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
               q2 += __shfl_xor_sync(0xffffffffu, q2, 16); q3 += __shfl_xor_sync(0xffffffffu, q3, 16);
             }
             if (hi == 0)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part + (uint32_t)((quarter * BN + cb + cl) * 16)),
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part_g + (uint32_t)((quarter * BN + cb + cl) * 16)),
                            "f"(q0), "f"(q1), "f"(q2), "f"(q3) : "memory");
           }
         }
@@ -884,12 +887,12 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&bar_tempty[acc]);
       if (a.stats) {
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        for (int f = tid; f < BN * 4; f += kEpiThreads) {
+        asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
+        for (int f = stat_tid; f < BN * 4; f += stat_threads) {
           const int col = f >> 2, q = f & 3;
           if (n0 + col < a.N) {
             float p0, p1, p2, p3;
-            const uint32_t pa = s_part + (uint32_t)(f * 4);
+            const uint32_t pa = s_part_g + (uint32_t)(f * 4);
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p0) : "r"(pa) : "memory");
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p1) : "r"(pa + BN * 16) : "memory");
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(p2) : "r"(pa + 2 * BN * 16) : "memory");
@@ -897,9 +900,10 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
             a.stats[((size_t)tile * a.N + n0 + col) * 4 + q] = p0 + p1 + p2 + p3;
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (alt) acc_phase ^= 1;
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -926,6 +930,15 @@ int epilogue_mode() {
   return mode;
 }
 
+bool epilogue_alternates_tiles() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("PDR_GEMM_EPI_ALT");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 template <int BN, bool WRES>
 int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   TcPlan plan;
@@ -935,7 +948,8 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   if (items > 0x7fffffffll) { set_error("gemm_tf32: too many tiles"); return PDR_ERR_INVALID_ARGUMENT; }
   plan.total_items = (int)items;
   plan.nk = ceil_div(a.K, kTcBK);
-  const size_t epi = (size_t)4 * BN * 16;   // column partials; the transpose tiles are static shared memory
+  plan.epi_alt = epilogue_alternates_tiles() ? 1 : 0;
+  const size_t epi = (size_t)2 * 4 * BN * 16;   // column partials of both epilogue groups; the transpose tiles are static
   const size_t static_smem = (size_t)(kEpiWarps * 32 * 36) * sizeof(float) + 512;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;

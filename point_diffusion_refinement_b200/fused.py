@@ -75,8 +75,10 @@ PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
 _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
 # PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
 _FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
-# PDR_FUSE_POOL=0 stores the attention scores and pools with pdr_attention_pool (what the fp32 path always does)
-_FUSE_POOL = os.environ.get("PDR_FUSE_POOL", "1") != "0"
+# PDR_FUSE_POOL=1 pools inside the score GEMM's epilogue (PdrGemmArgs.pool_*; bit-identical, scores never stored).
+# Off by default: measured 0.7 ms/step SLOWER on B200 (profiles/r01_fusion_ab_v8.txt) -- the epilogue warps are the
+# bottleneck of these GEMMs already and the softmax makes them heavier, while pdr_attention_pool runs at 4.3 TB/s.
+_FUSE_POOL = os.environ.get("PDR_FUSE_POOL", "0") == "1"
 
 
 def r4(c):
