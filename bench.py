@@ -42,7 +42,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=32, help="shapes per GPU")
-    p.add_argument("--e2e-steps", type=int, default=50)
+    p.add_argument("--e2e-steps", type=int, default=200)
     p.add_argument("--cpu-batch", type=int, default=1, help="shapes per step of the CPU arm (bounded sample)")
     p.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = min(cores, 32))")
     p.add_argument("--no-tf32", action="store_true", help="fp32 SIMT GEMMs instead of TF32 tensor cores")

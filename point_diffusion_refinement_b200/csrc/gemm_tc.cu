@@ -534,7 +534,12 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     const int G = (int)gridDim.x;
     const int item_step = alt ? 2 * G : G;
     const int cb0 = alt ? 0 : half * CW, cb_step = alt ? CW : 2 * CW;
-    const uint32_t s_part_g = s_part + (alt ? (uint32_t)(half * 4 * BN * 16) : 0u);
+    // column partials: one buffer per group, and (narrow tiles) per tile parity, so that a tile's partials can be
+    // summed without a second barrier before the next tile's are written
+    constexpr bool kPartDB = BN <= 128;
+    constexpr uint32_t kPartBytes = 4u * BN * 16u;
+    const uint32_t s_part_base = s_part + (alt ? (uint32_t)half * (kPartDB ? 2u : 1u) * kPartBytes : 0u);
+    uint32_t part_parity = 0;
     const int stat_bar = alt ? 1 + half : 1, stat_threads = alt ? kEpiThreads / 2 : kEpiThreads;
     const int stat_tid = alt ? (tid & (kEpiThreads / 2 - 1)) : tid;
     const bool radd_split = a.rowadd && a.rows_per_sample % a.rowadd_div == 0;   // groups never straddle samples
@@ -542,6 +547,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     for (int item = (int)blockIdx.x + (alt ? half * G : 0); item < plan.total_items; item += item_step) {
       const int tile = item / plan.n_tiles_n, n0 = (item - tile * plan.n_tiles_n) * BN;
       const int b = tile / plan.tiles_per_sample, tis = tile - b * plan.tiles_per_sample;
+      const uint32_t s_part_g = s_part_base + (kPartDB ? part_parity * kPartBytes : 0u);
       const int r0 = tis * kTcTileM;
       const size_t row_base = (size_t)b * a.rows_per_sample + r0;
       const int rows_valid = min(kTcTileM, a.rows_per_sample - r0);
@@ -900,7 +906,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
             a.stats[((size_t)tile * a.N + n0 + col) * 4 + q] = p0 + p1 + p2 + p3;
           }
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
+        if constexpr (kPartDB) part_parity ^= 1u;
+        else asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
       }
       if (alt) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -949,7 +956,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   plan.total_items = (int)items;
   plan.nk = ceil_div(a.K, kTcBK);
   plan.epi_alt = epilogue_alternates_tiles() ? 1 : 0;
-  const size_t epi = (size_t)2 * 4 * BN * 16;   // column partials of both epilogue groups; the transpose tiles are static
+  const size_t epi = (size_t)(BN <= 128 ? 4 : 2) * 4 * BN * 16;   // column partials: 2 epilogue groups (x 2 tile parities)
   const size_t static_smem = (size_t)(kEpiWarps * 32 * 36) * sizeof(float) + 512;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;

@@ -21,8 +21,13 @@ def best(fn, nbytes, reps=10):
 
 
 q = n // 4
+h = n // 2
 out = {
-    "write_only_GBps": best(lambda: a.zero_(), 4 * n),
+    "write_only_zero_GBps": best(lambda: a.zero_(), 4 * n),
+    "write_only_const_GBps": best(lambda: a.fill_(1.2345), 4 * n),
+    "write_only_arange_GBps": best(lambda: torch.arange(0, n, dtype=torch.float32, out=a), 4 * n),
+    # read n/2 once, write it to two destinations: 1 read : 2 writes
+    "read1_write2_GBps": best(lambda: (b[:h].copy_(a[:h]), b[h:].copy_(a[:h])), 4 * 3 * h),
     "read_only_GBps": best(lambda: torch.sum(a), 4 * n),
     "copy_GBps": best(lambda: b.copy_(a), 8 * n),
     # read n/4, write 3n/4 ... expand of a quarter-sized source into three quarter-sized destinations
