@@ -522,8 +522,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     // epilogue block width: 32 columns; 16 for the narrowest tile so that all 8 warps have work there (the pooling
     // epilogue keeps whole 32-row groups in one warp instead: lane = column, rows = the K neighbours of 32 / K points)
     constexpr int CW = (BN == 32 && !POOL) ? 16 : 32;
-    // transpose tile row stride (floats): odd for the scalar phase pair, CW + 4 keeps float4 alignment (VEC)
-    constexpr int kTs = VEC ? CW + 4 : CW + 1;
+    // transpose tile row stride (floats).  CW + 4 keeps rows 16-byte aligned, so a lane parks its row with CW / 4
+    // STS.128 (conflict-free per quarter warp: lane * 36 floats = lane * 4 banks) and the column-wise read-back
+    // (bank = 4 r + lane) is conflict-free as well.  The 16-column blocks keep the odd stride: with 20 the two lane
+    // halves (rows r and r + 16) would collide.
+    constexpr int kTs = (VEC || CW == 32) ? CW + 4 : CW + 1;
     float *s_t = s_epi[warp];
     // Two groups of 4 warps (one warp per TMEM lane quarter each).  epi_alt: group g owns accumulator g and every
     // second tile of this CTA, so the epilogues of two tiles overlap -- the small-tile GEMMs are bound by the LATENCY
@@ -601,8 +604,16 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           const float gs = nin ? __ldg(a.pool_sc + (size_t)b * a.pool_ld_scsh + n) : 0.f;
           const float gh = nin ? __ldg(a.pool_sh + (size_t)b * a.pool_ld_scsh + n) : 0.f;
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if constexpr (kTs % 4 == 0) {
   #pragma unroll
-          for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < CW / 4; ++j)
+              *reinterpret_cast<float4 *>(s_t + lane * kTs + 4 * j) =
+                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                              __uint_as_float(v[4 * j + 3]));
+          } else {
+  #pragma unroll
+            for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
+          }
           __syncwarp();
           const int PK = a.pool_K;
           const float *st = s_t + lane;
@@ -818,8 +829,16 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           // park my row (lane = row) in the transpose tile; the odd stride keeps both phases bank-conflict free
+          if constexpr (kTs % 4 == 0) {
   #pragma unroll
-          for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < CW / 4; ++j)
+              *reinterpret_cast<float4 *>(s_t + lane * kTs + 4 * j) =
+                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                              __uint_as_float(v[4 * j + 3]));
+          } else {
+  #pragma unroll
+            for (int j = 0; j < CW; ++j) s_t[lane * kTs + j] = __uint_as_float(v[j]);
+          }
           __syncwarp();
           // from here on lane = (row group hi, column cl): a store instruction writes 32 / CW row segments of CW
           // consecutive floats; bias and the broadcast row-add are per column
