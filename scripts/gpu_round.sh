@@ -26,8 +26,13 @@ if [ -z "$SKIP_NCU" ]; then
     -c ${NFULL:-12} -f -o $out/gemm_full \
     python bench.py $COLD --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-eval-kernels --profiler-range ) > $out/ncu_full.log 2>&1
 ncu -i $out/gemm_full.ncu-rep --page raw --csv > $out/gemm_full_raw.csv 2>/dev/null
+( timeout 300 ncu --profile-from-start off --set full --import-source on --clock-control none -f -o $out/ops_full \
+    python scripts/ncu_ops.py ) > $out/ncu_ops.log 2>&1
+ncu -i $out/ops_full.ncu-rep --page raw --csv > $out/ops_full_raw.csv 2>/dev/null
+osz=$(stat -c %s $out/ops_full.ncu-rep 2>/dev/null || echo 0)
+if [ "$osz" -gt 15000000 ]; then rm -f $out/ops_full.ncu-rep; fi
 sz=$(stat -c %s $out/gemm_full.ncu-rep 2>/dev/null || echo 0)
-if [ "$sz" -gt 40000000 ]; then rm -f $out/gemm_full.ncu-rep; echo "report dropped ($sz bytes)" >> $out/ncu_full.log; fi
+if [ "$sz" -gt 30000000 ]; then rm -f $out/gemm_full.ncu-rep; echo "report dropped ($sz bytes)" >> $out/ncu_full.log; fi
 fi
 tail -3 $out/pytest_gpu.log; tail -2 $out/smoke.log; cat $out/bench.json
 [ -z "$SKIP_REF" ] && cat $out/bench_reference.json

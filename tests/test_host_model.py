@@ -119,6 +119,7 @@ def test_query_and_group_fill_rule(oracle):
 
 
 def test_result_formats_round_trip(tmp_path):
+    import os
     """SURVEY 8f row 3: file names of completion_eval.py:283-315 and the pickled dict of
     generate_samples.py:247-252 / generate_samples_distributed.py:84-93."""
     import numpy as np
@@ -127,8 +128,22 @@ def test_result_formats_round_trip(tmp_path):
     assert R.generated_file_name("shapenet_chunk", 16384, 100) == "shapenet_generated_data_16384pts_T100.h5"
     data = np.random.RandomState(0).rand(5, 64, 3).astype(np.float32)
     path = str(tmp_path / R.generated_file_name("mvp40", 64))
-    R.save_generated(path, data)
+    assert R.save_generated(path, data) == path and os.path.exists(path)
     assert np.array_equal(R.load_generated(path), data)
+    # the container itself: HDF5 signature, version-0 superblock with 8-byte offsets, end-of-file address = file size,
+    # dataset 'data' found through the root group's B-tree / heap / symbol node, raw data 8-byte aligned at the tail
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    assert int.from_bytes(raw[40:48], "little") == len(raw) and (len(raw) - data.nbytes) % 8 == 0
+    assert raw[len(raw) - data.nbytes:] == data.tobytes()
+    for shape in ((1, 2048, 3), (3, 16384, 3), (2, 5)):
+        arr = np.random.RandomState(1).randn(*shape).astype(np.float32)
+        p2 = str(tmp_path / ("t%d.h5" % len(shape)))
+        R.write_hdf5_dataset(p2, arr)
+        back = R.read_hdf5_dataset(p2)
+        assert back.dtype == np.float32 and np.array_equal(back, arr)
+    with __import__("pytest").raises(KeyError):
+        R.read_hdf5_dataset(path, "other")
     parts = [R.eval_result_dict(np.arange(3) + 3 * r, np.full(3, 0.1 * (r + 1), np.float32), np.full(3, 0.2, np.float32),
                                 np.full(3, 0.5, np.float32), 545999) for r in range(2)]
     assert set(parts[0]) == {"meta", "cd_distance", "emd_distance", "f1", "avg_cd", "avg_emd", "iter"}
