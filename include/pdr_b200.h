@@ -199,6 +199,13 @@ typedef struct PdrGemmArgs {
    *   pool_out[point, n] = sum_k softmax_k(score[point*K + k, n] masked to k < max(count[point], 1))
    *                              * relu(pool_V[point*K + k, n] * pool_sc[b, n] + pool_sh[b, n])
    * pool_K in {8, 16, 32} and divides rows_per_sample; stats and rowadd must be NULL. */
+  /* raw gathered K tail (tensor-core path, with a prologue, R == NULL): when tail_rows != NULL only the first k_pro
+   * columns of the operand are A with the prologue applied; columns [k_pro, K) are, untransformed,
+   *   [ T[tail_rows[r], 0:t_split] | T2[r, 0:K-k_pro-t_split] ]      (tail_rows[r] < 0: zeros)
+   * i.e. a second, gathered operand contracted in the same accumulator -- used to fold the residual convolution of
+   * Mlp_plus_t_emb into the values GEMM: V = Wv.act(y) + (Wv.Wres).X0.  k_pro multiple of 32; t_split, ldt, ldt2
+   * multiples of 4; T, T2 16-byte aligned. */
+  const int *tail_rows; const float *T; int ldt; const float *T2; int ldt2; int t_split; int k_pro;
   int pool_K; const float *pool_V; int pool_ldv; const float *pool_sc; const float *pool_sh; int pool_ld_scsh;
   const int *pool_counts; float *pool_out; int pool_ldo;
 } PdrGemmArgs;

@@ -356,16 +356,44 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       };
       locate(cl); derive_l(cl);
       const size_t a8 = (size_t)8 * a.lda, r8 = (size_t)8 * a.ldr, w8 = (size_t)8 * a.ldw;
+      // raw gathered K tail (PdrGemmArgs.tail_rows): the table rows of this thread's 16 tile rows are fetched when the
+      // item starts, i.e. k_pro / 32 chunks before they are needed
+      const bool has_tail = a.tail_rows != nullptr;
+      int tidx[16];
       int stage = 0, phase = 0;
       for (int j = 0; j < my_chunks; ++j) {
         const int kofs = cl.kc * kTcBK;
         const bool kin = kofs + lchunk * 4 < a.K;
+        if (has_tail && cl.kc == 0) {
+          const int r0 = cl.tis * kTcTileM;
+          const int *p = a.tail_rows + (size_t)cl.b * a.rows_per_sample + r0 + lrow;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tidx[i] = (lrow + 8 * i < cl.rows_valid) ? __ldg(p + 8 * i) : -1;
+        }
         mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));      // the MMAs that read this stage have retired
         const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes) + l_sw;
         // interior chunks take a predicate-free path (see the direct producer)
         const int ksz = kin ? 16 : 0;
         const bool afull = cl.rows_valid == kTcTileM;
-        if (afull) {
+        if (has_tail && kofs >= a.k_pro) {
+          const int t0 = kofs - a.k_pro + lchunk * 4;             // column inside the tail
+          if (t0 < a.t_split) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool ok = tidx[i] >= 0;
+              cp_async16_sz(sa + i * 1024, ok ? a.T + (size_t)tidx[i] * a.ldt + t0 : a.A, ok ? 16 : 0);
+            }
+          } else {
+            const size_t row = (size_t)cl.b * a.rows_per_sample + cl.tis * kTcTileM + lrow;
+            const float *src = a.T2 + row * a.ldt2 + (t0 - a.t_split);
+            const size_t st2 = (size_t)8 * a.ldt2;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool ok = kin && lrow + 8 * i < cl.rows_valid;
+              cp_async16_sz(sa + i * 1024, ok ? src + i * st2 : a.A, ok ? 16 : 0);
+            }
+          }
+        } else if (afull) {
           const float *src = kin ? cl.pa + kofs : a.A;
           const size_t st = kin ? a8 : 0;
 #pragma unroll
@@ -432,10 +460,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       Cur ct;
       ct.item = (int)blockIdx.x; ct.kc = 0;
       locate(ct);
+      const int k_pro = a.tail_rows ? a.k_pro : a.K;          // columns that get the prologue
       auto fetch = [&](const Cur &c, float4 &s4, float4 &h4, float4 &e4) {
         const int k = c.kc * kTcBK + chunk * 4;
         s4 = make_float4(1.f, 1.f, 1.f, 1.f); h4 = make_float4(0.f, 0.f, 0.f, 0.f); e4 = h4;
-        if (k < a.K) {
+        if (k < k_pro) {
           if (a.pro_mode != PDR_PRO_NONE) {
             s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)c.b * a.ld_scsh + k));
             h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)c.b * a.ld_scsh + k));
@@ -447,6 +476,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       if (my_chunks > 0) fetch(ct, s4, h4, e4);
       int stage = 0, phase = 0;
       for (int j = 0; j < my_chunks; ++j) {
+        const bool raw_chunk = ct.kc * kTcBK >= k_pro;          // gathered tail: lands ready for the tensor core
         if (++ct.kc == nk) {                                    // cursor of chunk j + 1
           ct.kc = 0; ct.item += G;
           if (fast_adv) { ct.tis += G; if (ct.tis >= plan.tiles_per_sample) { ct.tis -= plan.tiles_per_sample; ++ct.b; } }
@@ -454,6 +484,15 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
         }
         float4 ns4 = s4, nh4 = h4, ne4 = e4;
         if (j + 1 < my_chunks) fetch(ct, ns4, nh4, ne4);
+        if (raw_chunk) {
+          // nothing to transform.  The wait keeps this warp from running ahead of the ring (an arrival for the NEXT use
+          // of a stage must not land in the phase of the current one); the data needs no fence, cp.async wrote it.
+          mbar_wait(&bar_rfull[stage], (uint32_t)phase);
+          mbar_arrive(&bar_full[stage]);
+          s4 = ns4; h4 = nh4; e4 = ne4;
+          if (++stage == S) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_wait(&bar_rfull[stage], (uint32_t)phase);
         // in place: the loaders land raw A (and R) at the swizzled position the tensor core expects, so every
         // thread rewrites exactly the 16-byte pieces it read

@@ -506,7 +506,7 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   PDR_REQUIRE(a.A && a.W && (a.C || a.pool_K > 0), "gemm_fused: null pointer");
   PDR_REQUIRE(a.K > 0 && a.N > 0 && a.batch > 0 && a.rows_per_sample > 0, "gemm_fused: bad sizes");
-  PDR_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && (a.a_rows || a.lda >= a.K) && a.ldw >= a.K,
+  PDR_REQUIRE(a.K % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && (a.a_rows || a.tail_rows || a.lda >= a.K) && a.ldw >= a.K,
               "gemm_fused: K/lda/ldw must be multiples of 4 (K=%d lda=%d ldw=%d)", a.K, a.lda, a.ldw);
   PDR_REQUIRE(a.ldc >= a.N && a.ldc_zero_to <= a.ldc, "gemm_fused: ldc=%d < N=%d", a.ldc, a.N);
   PDR_REQUIRE(a.pro_mode == PDR_PRO_NONE || (a.sc && a.sh && a.ld_scsh % 4 == 0 && ((uintptr_t)a.sc % 16) == 0 &&
@@ -521,6 +521,18 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   // else takes the SIMT kernel
   const bool tc_aligned = a.ldc % 4 == 0 && ((uintptr_t)a.C % 16) == 0 &&
                           (!a.rowadd || (a.ld_rowadd % 4 == 0 && ((uintptr_t)a.rowadd % 16) == 0));
+  if (a.tail_rows) {
+    PDR_REQUIRE(a.T && a.T2 && a.k_pro > 0 && a.k_pro < a.K && a.k_pro % 32 == 0 && a.t_split > 0 && a.t_split % 4 == 0 &&
+                    a.t_split < a.K - a.k_pro && a.ldt % 4 == 0 && a.ldt2 % 4 == 0 && a.ldt >= a.t_split &&
+                    a.ldt2 >= a.K - a.k_pro - a.t_split && ((uintptr_t)a.T % 16) == 0 && ((uintptr_t)a.T2 % 16) == 0 &&
+                    a.lda >= a.k_pro,
+                "gemm_fused: raw K tail needs T/T2, k_pro %% 32 == 0, t_split/ldt/ldt2 multiples of 4");
+    PDR_REQUIRE(a.pro_mode != PDR_PRO_NONE && !a.R && !a.a_rows, "gemm_fused: raw K tail needs a prologue and excludes R / a_rows");
+    if (!(a.use_tf32 && tc_aligned)) {
+      set_error("gemm_fused: the raw K tail is implemented on the tensor-core path only");
+      return PDR_ERR_UNSUPPORTED;
+    }
+  }
   if (a.pool_K > 0) {
     PDR_REQUIRE((a.pool_K == 8 || a.pool_K == 16 || a.pool_K == 32) && a.rows_per_sample % a.pool_K == 0 && a.pool_V &&
                     a.pool_sc && a.pool_sh && a.pool_out && !a.stats && !a.rowadd,

@@ -52,6 +52,8 @@ class GemmArgs(ctypes.Structure):
                 ("use_tf32", ctypes.c_int),
                 ("stats_skip", ctypes.c_int),
                 ("a_rows", c_float_p), ("A2", c_float_p), ("lda2", ctypes.c_int), ("k_split", ctypes.c_int),
+                ("tail_rows", c_float_p), ("T", c_float_p), ("ldt", ctypes.c_int), ("T2", c_float_p), ("ldt2", ctypes.c_int),
+                ("t_split", ctypes.c_int), ("k_pro", ctypes.c_int),
                 ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
                 ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
                 ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int)]
@@ -79,6 +81,9 @@ _FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
 # Off by default: measured 0.7 ms/step SLOWER on B200 (profiles/r01_fusion_ab_v8.txt) -- the epilogue warps are the
 # bottleneck of these GEMMs already and the softmax makes them heavier, while pdr_attention_pool runs at 4.3 TB/s.
 _FUSE_POOL = os.environ.get("PDR_FUSE_POOL", "0") == "1"
+# PDR_FOLD_RES=0 keeps the residual convolution of Mlp_plus_t_emb as a section of the stage's first GEMM (written, then
+# re-read by the values GEMM) instead of folding it into the values GEMM through the raw gathered K tail
+_FOLD_RES = os.environ.get("PDR_FOLD_RES", "1") != "0"
 
 
 def r4(c):
@@ -235,7 +240,7 @@ class FusedDenoiser:
         self._ops.append(fn)
 
     def gemm(self, A, W, bias, out, rows_per_sample, batch=None, pro=PRO_NONE, scsh=None, add=None, R=None,
-             rowadd=None, rowadd_div=1, want_stats=False, K=None, zero_to=None, pool=None):
+             rowadd=None, rowadd_div=1, want_stats=False, K=None, zero_to=None, pool=None, tail=None):
         """out[:, :N] = pro(A[:, :K]) @ W^T + bias (+rowadd).  W: torch (N, Kpad).  Returns Stats or None."""
         batch = self.B if batch is None else batch
         N, Kp = W.shape
@@ -245,6 +250,10 @@ class FusedDenoiser:
             assert pro == PRO_NONE and add is None and R is None and K == gathered.K, (K, gathered.K)
             A = gathered.table
         assert K == Kp and K % 4 == 0 and A.ld % 4 == 0 and A.col0 % 4 == 0, (K, Kp, A.ld, A.col0)
+        if tail is not None:
+            # raw gathered K tail (a GatheredA): columns [K - tail.K, K) of the operand, no prologue
+            assert pro != PRO_NONE and R is None and gathered is None and tail.rows == A.rows
+            assert (K - tail.K) % 32 == 0 and K - tail.K <= A.ld - A.col0
         rows_in = gathered.rows if gathered is not None else A.rows
         assert rows_in == batch * rows_per_sample, (rows_in, batch, rows_per_sample)
         assert (out is None and pool is not None) or out.rows == rows_in
@@ -254,6 +263,10 @@ class FusedDenoiser:
             g.a_rows, g.A2 = gathered.src_row.data_ptr(), gathered.geo.ptr
             g.lda2, g.k_split = gathered.geo.ld, gathered.Cp
             self.keep.append(gathered)
+        if tail is not None:
+            g.tail_rows, g.T, g.ldt = tail.src_row.data_ptr(), tail.table.ptr, tail.table.ld
+            g.T2, g.ldt2, g.t_split, g.k_pro = tail.geo.ptr, tail.geo.ld, tail.Cp, K - tail.K
+            self.keep.append(tail)
         g.W, g.ldw = W.data_ptr(), Kp
         g.bias = bias.data_ptr() if bias is not None else None
         if out is not None:
@@ -297,6 +310,9 @@ class FusedDenoiser:
             assert g.use_tf32, "the gathered A operand exists on the tensor-core path only"
             # algorithmic bytes: the feature table once (its rows are re-read from L2), geometric channels + row index
             a_elems = min(M, A.rows) * gathered.Cp + M * (gathered.geo.ld + 1)
+        elif tail is not None:
+            assert g.use_tf32, "the raw K tail exists on the tensor-core path only"
+            a_elems = M * (K - tail.K) + min(M, tail.table.rows) * tail.Cp + M * (tail.geo.ld + 1)
         else:
             a_elems = M * K
         out_elems = M * N if pool is None else (M * N + M // pool[0] * N)     # pooled: V read + pooled rows written
@@ -452,13 +468,10 @@ class FusedDenoiser:
         c_key = key_conv.out_channels
         assert key_conv.in_channels == C0
         res_conv = mlp.res_connect if mlp.res_connect_bool else None
-        blocks = [(_conv_w(first_conv), lay)]
-        biases = [_bias(first_conv, c1, self.dev)]
-        col_res = None
-        if res_conv is not None:
-            col_res = r4(c1)
-            blocks.append((_conv_w(res_conv), lay))
-            biases.append(_bias(res_conv, c_last, self.dev))
+        # fold the residual convolution into the values GEMM (V = Wv.act(y) + (Wv.Wres).X0 through the raw gathered
+        # K tail): its c_last output channels are then neither written by this stage's first GEMM nor re-read
+        fold_res = (_FOLD_RES and gathered is not None and res_conv is not None and c_last % 32 == 0
+                    and self.use_tf32 and B * rows_per_sample >= 512)
         # pad each section to a multiple of 4 output columns by inserting zero rows
         def pad_rows(w, b, n_to):
             if w.shape[0] < n_to:
@@ -467,7 +480,7 @@ class FusedDenoiser:
             return w, b
         W_parts, b_parts, offs = [], [], []
         col = 0
-        secs = [(first_conv, c1)] + ([(res_conv, c_last)] if res_conv is not None else []) + [(key_conv, c_key)]
+        secs = [(first_conv, c1)] + ([(res_conv, c_last)] if (res_conv is not None and not fold_res) else []) + [(key_conv, c_key)]
         for conv, n in secs:
             w = _pack([(_conv_w(conv), lay)], self.dev)
             b = _bias(conv, n, self.dev)
@@ -482,7 +495,10 @@ class FusedDenoiser:
         st1 = self.gemm(A0, W1, b1, Y1, rows_per_sample, want_stats=True)
         y = Y1.cols(offs[0], r4(c1))
         y_cols = (offs[0], c1)
-        if res_conv is not None:
+        if fold_res:
+            Rv = None
+            key = Y1.cols(offs[1], r4(c_key)); key_col = offs[1]
+        elif res_conv is not None:
             Rv = Y1.cols(offs[1], r4(c_last))
             key = Y1.cols(offs[2], r4(c_key)); key_col = offs[2]
         else:
@@ -527,21 +543,29 @@ class FusedDenoiser:
         conv_v, gn_v = fo[0], fo[1]
         W_s = _pack([(_conv_w(conv_w2), [(0, inter, r4(inter))])], self.dev)
         W_v = _pack([(_conv_w(conv_v), [(0, c_last, r4(c_last))])], self.dev)
+        b_v = _bias(conv_v, c_out, self.dev)
+        tail = None
+        if fold_res:
+            w_res = _pack([(_conv_w(res_conv), lay)], self.dev).double()                     # (c_last, gathered.K)
+            wv64 = W_v[:, :c_last].double()
+            W_v = torch.cat([W_v[:, :c_last], (wv64 @ w_res).float()], dim=1).contiguous()    # (c_out, c_last + gathered.K)
+            b_v = (b_v.double() + wv64 @ _bias(res_conv, c_last, self.dev).double()).float()
+            tail = gathered
         V = self._mat(M, c_out)
         tc = self.use_tf32 and M >= 512
         if _FUSE_POOL and tc and K in (8, 16, 32) and rows_per_sample % K == 0:
             # values first (their GroupNorm statistics must be final), then the score GEMM pools in its epilogue:
             # the score tensor is never written
-            st_v = self.gemm(y, W_v, _bias(conv_v, c_out, self.dev), V, rows_per_sample, pro=PRO_GN_RELU, scsh=scsh_last,
-                             add=add_last, R=Rv, want_stats=True)
+            st_v = self.gemm(y, W_v, b_v, V, rows_per_sample, pro=PRO_GN_RELU, scsh=scsh_last,
+                             add=add_last, R=Rv, want_stats=True, tail=tail)
             scv, shv = self.gn([(st_v, 0, c_out, False, 1.0)], gn_v)
             self.gemm(S1, W_s, _bias(conv_w2, c_out, self.dev), None, rows_per_sample, pro=PRO_RELU_GN, scsh=scsh2,
                       pool=(K, V, scv, shv, counts, out))
             return
         S = self._mat(M, c_out)
         self.gemm(S1, W_s, _bias(conv_w2, c_out, self.dev), S, rows_per_sample, pro=PRO_RELU_GN, scsh=scsh2)
-        st_v = self.gemm(y, W_v, _bias(conv_v, c_out, self.dev), V, rows_per_sample, pro=PRO_GN_RELU, scsh=scsh_last,
-                         add=add_last, R=Rv, want_stats=True)
+        st_v = self.gemm(y, W_v, b_v, V, rows_per_sample, pro=PRO_GN_RELU, scsh=scsh_last,
+                         add=add_last, R=Rv, want_stats=True, tail=tail)
         scv, shv = self.gn([(st_v, 0, c_out, False, 1.0)], gn_v)
         self._emit("pdr_attention_pool", B, P, K, c_out, ctypes.c_void_p(S.ptr), S.ld, ctypes.c_void_p(V.ptr), V.ld,
                    ctypes.c_void_p(scv.ptr), ctypes.c_void_p(shv.ptr), scv.ld,

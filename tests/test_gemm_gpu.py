@@ -307,3 +307,71 @@ def test_gemm_pooling_epilogue_equals_attention_pool(cuda_lib, shape):
     assert torch.isfinite(ref).all() and torch.equal(out, ref)
     a.use_tf32 = 0
     assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == -4
+
+
+@pytest.mark.parametrize("shape", [(2, 4096, 64, 35, 9, 64, 2000, True), (3, 1000, 32, 4, 9, 32, 300, False),
+                                   (2, 2048, 128, 160, 11, 128, 512, True), (1, 8320, 256, 320, 11, 300, 64, True)])
+def test_gemm_raw_gathered_tail(cuda_lib, shape):
+    """PdrGemmArgs.tail_rows: C = pro(A[:, :k_pro]) W1^T + [T[rows] | T2] W2^T + bias against float64, TF32 tolerance;
+    deterministic; the fp32 path refuses."""
+    import ctypes
+    from point_diffusion_refinement_b200.fused import GemmArgs, tf32_round
+    B, rps, k_pro, C, n_geo, N, table_rows, use_add = shape
+    g = torch.Generator().manual_seed(k_pro * N + rps)
+    M, Cp = B * rps, (C + 3) // 4 * 4
+    K = k_pro + Cp + 12
+    A = torch.randn(M, k_pro, generator=g)
+    table = torch.zeros(table_rows, Cp)
+    table[:, :C] = torch.randn(table_rows, C, generator=g)
+    src = torch.randint(0, table_rows, (M,), generator=g, dtype=torch.int32)
+    src[torch.rand(M, generator=g) < 0.05] = -1
+    geo = torch.zeros(M, 12)
+    geo[:, :n_geo] = torch.randn(M, n_geo, generator=g)
+    W = tf32_round(torch.randn(N, K, generator=g) / K ** 0.5)
+    bias = torch.randn(N, generator=g)
+    sc = 1 + 0.2 * torch.randn(B, k_pro, generator=g)
+    sh = 0.2 * torch.randn(B, k_pro, generator=g)
+    add = torch.randn(B, k_pro, generator=g) if use_add else None
+    x = torch.relu(A.double().view(B, rps, k_pro) * sc.double()[:, None] + sh.double()[:, None])
+    if add is not None:
+        x = x + add.double()[:, None]
+    tail = torch.zeros(M, Cp + 12, dtype=torch.float64)
+    ok = src >= 0
+    tail[ok, :Cp] = table[src[ok].long()].double()
+    tail[:, Cp:] = geo.double()
+    y64 = x.reshape(M, k_pro) @ W.double()[:, :k_pro].t() + tail @ W.double()[:, k_pro:].t() + bias.double()
+    A, table, src, geo, W, bias, sc, sh = [t.to(DEV) for t in (A, table, src, geo, W, bias, sc, sh)]
+    add = add.to(DEV) if add is not None else None
+    ldc = (N + 3) // 4 * 4
+    tiles = (rps + cuda_lib.pdr_gemm_tile_rows() - 1) // cuda_lib.pdr_gemm_tile_rows()
+
+    def run():
+        Cg = torch.full((M, ldc), float("nan"), device=DEV)
+        stats = torch.zeros(B * tiles, N, 4, device=DEV)
+        a = GemmArgs()
+        a.A, a.lda, a.K = A.data_ptr(), A.stride(0), K
+        a.W, a.ldw, a.bias = W.data_ptr(), W.stride(0), bias.data_ptr()
+        a.C, a.ldc, a.N, a.ldc_zero_to = Cg.data_ptr(), ldc, N, ldc
+        a.batch, a.rows_per_sample, a.pro_mode = B, rps, 1
+        a.sc, a.sh, a.ld_scsh = sc.data_ptr(), sh.data_ptr(), sc.stride(0)
+        if add is not None:
+            a.add, a.ld_add = add.data_ptr(), add.stride(0)
+        a.stats, a.use_tf32 = stats.data_ptr(), 1
+        a.tail_rows, a.T, a.ldt = src.data_ptr(), table.data_ptr(), table.stride(0)
+        a.T2, a.ldt2, a.t_split, a.k_pro = geo.data_ptr(), 12, Cp, k_pro
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream)
+        torch.cuda.synchronize()
+        a.use_tf32 = 0
+        rc32 = cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream)
+        return rc, rc32, Cg, stats.view(B, tiles, N, 4).sum(1)
+
+    rc, rc32, C1, st1 = run()
+    assert rc == 0 and rc32 == -4, cuda_lib.pdr_last_error_string()
+    torch.testing.assert_close(C1[:, :N].double().cpu(), y64, rtol=5e-3, atol=5e-3 * float(y64.abs().max()) / 4)
+    assert C1[:, N:].abs().sum() == 0
+    own = C1[:, :N].double().view(B, rps, N)
+    l1 = own.abs().sum(1)
+    assert ((st1[..., 0].double() - own.sum(1)).abs() <= 1e-5 * l1 + 1e-2).all()
+    _, _, C2, _ = run()
+    assert torch.equal(C1, C2)
