@@ -39,6 +39,11 @@ extern "C" {
 int pdr_version(void);                      /* e.g. 100 = 0.1.0 */
 const char *pdr_last_error_string(void);    /* thread-local, never NULL */
 int pdr_built_for_sm(void);                 /* 100 */
+/* Diagnostic (no reference counterpart): HBM ceilings the store-dominated kernels are held against, measured with
+ * incompressible data.  mode 0: write-only, 16-byte stores; mode 1: the same plus one 512-byte segment in three read
+ * from src (1 read : 3 writes); mode 2: write-only through 4 KiB TMA bulk stores from shared memory.  n_floats a
+ * multiple of 1024, dst (and src) 16-byte aligned with n_floats elements.  bench.py / scripts/bw_probe.py time it. */
+int pdr_probe_hbm(int mode, float *dst, const float *src, size_t n_floats, void *stream);
 
 /* ---- pointnet2_ops._ext forward ops ----------------------------------------------------------- */
 

@@ -23,6 +23,7 @@ SIGNATURES = {
     "pdr_version": [],
     "pdr_last_error_string": [],
     "pdr_built_for_sm": [],
+    "pdr_probe_hbm": [_c_int, _ptr, _ptr, _c_size_t, _ptr],
     "pdr_fps_max_onchip_points": [],
     "pdr_furthest_point_sampling": [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],
     "pdr_gather_points": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr],

@@ -23,7 +23,9 @@
 //                           tmem_empty[a].
 //   When the whole weight matrix fits in 64 KiB of shared memory it is staged once per CTA (W-resident mode)
 //   and the ring carries A only.
+#include <cuda.h>      // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -62,6 +64,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
+}
+// same, for waits that are expected to be long (a producer that is ahead of the ring): sleep between polls so that the
+// retry loop does not take issue slots from the warps that are the bottleneck
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
+  if (ns == 0) { mbar_wait(bar, parity); return; }
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+  }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
@@ -128,12 +149,17 @@ struct TcPlan {
   int r_off;            // offset of the residual tile inside a stage (transform mode with R)
   int epi_alt;          // 1: the two groups of 4 epilogue warps take alternate TILES (one accumulator each);
                         // 0: both groups share every tile and alternate its column blocks
+  int prod_sleep_ns;    // > 0: producers / loaders sleep this long between polls of an EMPTY-stage barrier
 };
 
-// EPI: 0 = scalar epilogue, 1 = float4 epilogue, 2 = attention pooling over the K neighbour rows (no C store)
+// bytes of the TMA-store staging tiles (EPI 3): two 32 x 32 fp32 boxes per epilogue warp
+constexpr int kTmaStageBytes = kEpiWarps * 2 * 4096;
+
+// EPI: 0 = scalar epilogue, 1 = float4 epilogue, 2 = attention pooling over the K neighbour rows (no C store),
+//      3 = TMA-store epilogue (32 x 32 boxes through a 128B-swizzled staging tile, statistics read back column-wise)
 template <int BN, bool WRES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
+gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kWLoads = BN * 8 / kProdThreads;        // float4 of W per producer thread per chunk
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -145,7 +171,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
   // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
-  __shared__ __align__(16) float s_epi[kEpiWarps][32 * 36];
+  __shared__ __align__(16) float s_epi[kEpiWarps][EPI == 3 ? 192 : 32 * 36];   // EPI 3: per-column addends, <= 5 row groups
   // the column partials (4 lane quarters x BN x 4 sums) live in the dynamic region and are touched only through
   // explicit ld/st.shared (a handful of accesses per block), which keeps static shared memory under 48 KB
 
@@ -155,6 +181,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
   uint8_t *s_stages = smem + (WRES ? (size_t)plan.nk * kBTileBytes : 0);
   const uint32_t kStageBytes = (uint32_t)plan.stage_bytes;
   const uint32_t s_part = smem_u32(s_stages + (size_t)plan.stages * kStageBytes);   // [4][BN] float4
+  // EPI 3: staging tiles of the TMA stores, after the column partials (every region before is a multiple of 1 KiB)
+  constexpr uint32_t kPartRegion = (uint32_t)(BN <= 128 ? 4 : 2) * 4u * BN * 16u;
+  const uint32_t s_tma = s_part + kPartRegion;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = plan.stages, nk = plan.nk;
@@ -229,7 +258,14 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     // gathered A (PdrGemmArgs.a_rows): the neighbour rows of the CURRENT item sit in cidx, those of the NEXT item of
     // this CTA are already in flight in nidx, so the index loads never stall the copy loop
     const bool gath = a.a_rows != nullptr;
-    int cidx[4] = {-1, -1, -1, -1}, nidx[4] = {-1, -1, -1, -1};
+    // (kIdxAhead items ahead; 3 measured neutral-to-slower than 1 on B200, gpurun call r01s3b: the producers are not
+    // waiting for these loads)
+    constexpr int kIdxAhead = 1;
+    int cidx[4] = {-1, -1, -1, -1}, nidx[kIdxAhead][4];
+#pragma unroll
+    for (int d = 0; d < kIdxAhead; ++d)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nidx[d][i] = -1;
     auto fetch_idx = [&](int item, int (&out)[4]) {
       if (item >= plan.total_items) return;
       const int tile = item / plan.n_tiles_n;
@@ -258,8 +294,12 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       else locate(c);
       if (gath) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cidx[i] = nidx[i];
-        fetch_idx(c.item + G, nidx);
+        for (int i = 0; i < 4; ++i) cidx[i] = nidx[0][i];
+#pragma unroll
+        for (int d = 0; d + 1 < kIdxAhead; ++d)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) nidx[d][i] = nidx[d + 1][i];
+        fetch_idx(c.item + kIdxAhead * G, nidx[kIdxAhead - 1]);
       }
       derive(c);
     };
@@ -269,7 +309,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     const size_t w_step = (size_t)32 * a.ldw;
     Cur ci;
     ci.item = (int)blockIdx.x; ci.kc = 0;
-    if (gath && !is_loader) { fetch_idx(ci.item, cidx); fetch_idx(ci.item + G, nidx); }
+    if (gath && !is_loader) {
+      fetch_idx(ci.item, cidx);
+#pragma unroll
+      for (int d = 0; d < kIdxAhead; ++d) fetch_idx(ci.item + (d + 1) * G, nidx[d]);
+    }
     locate(ci); derive(ci);
 
     if (plan.direct) {
@@ -332,7 +376,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       };
       int stage = 0, phase = 0;
       for (int j = 0; j < (is_loader ? 0 : my_chunks); ++j) {
-        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));
+        mbar_wait_sleep(&bar_empty[stage], (uint32_t)(phase ^ 1), (uint32_t)plan.prod_sleep_ns);
         issue(ci, stage);
         cp_async_arrive_noinc(&bar_full[stage]);
         advance(ci);
@@ -359,6 +403,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       // raw gathered K tail (PdrGemmArgs.tail_rows): the table rows of this thread's 16 tile rows are fetched when the
       // item starts, i.e. k_pro / 32 chunks before they are needed
       const bool has_tail = a.tail_rows != nullptr;
+      // (requesting them one item ahead was measured 10-17 % SLOWER on the folded-residual GEMMs, gpurun call r01s3b)
       int tidx[16];
       int stage = 0, phase = 0;
       for (int j = 0; j < my_chunks; ++j) {
@@ -370,7 +415,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) tidx[i] = (lrow + 8 * i < cl.rows_valid) ? __ldg(p + 8 * i) : -1;
         }
-        mbar_wait(&bar_empty[stage], (uint32_t)(phase ^ 1));      // the MMAs that read this stage have retired
+        mbar_wait_sleep(&bar_empty[stage], (uint32_t)(phase ^ 1), (uint32_t)plan.prod_sleep_ns);   // the MMAs that read this stage have retired
         const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes) + l_sw;
         // interior chunks take a predicate-free path (see the direct producer)
         const int ksz = kin ? 16 : 0;
@@ -557,10 +602,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
     // =============================== EPILOGUE ================================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
     const int half = warp >> 2;                   // which of the two warps sharing this lane quarter
-    constexpr bool VEC = EPI == 1, POOL = EPI == 2;
+    constexpr bool VEC = EPI == 1, POOL = EPI == 2, TMA = EPI == 3;
     // epilogue block width: 32 columns; 16 for the narrowest tile so that all 8 warps have work there (the pooling
     // epilogue keeps whole 32-row groups in one warp instead: lane = column, rows = the K neighbours of 32 / K points)
-    constexpr int CW = (BN == 32 && !POOL) ? 16 : 32;
+    constexpr int CW = (BN == 32 && !POOL && !TMA) ? 16 : 32;
+    uint32_t tma_buf = 0;                         // EPI 3: which of this warp's two staging tiles is next
     // transpose tile row stride (floats).  CW + 4 keeps rows 16-byte aligned, so a lane parks its row with CW / 4
     // STS.128 (conflict-free per quarter warp: lane * 36 floats = lane * 4 banks) and the column-wise read-back
     // (bank = 4 r + lane) is conflict-free as well.  The 16-column blocks keep the odd stride: with 20 the two lane
@@ -604,6 +650,15 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
           radd_g0 = (size_t)b * groups_per_sample + g;
         } else {
           radd_g0 = wrow0 / (size_t)a.rowadd_div; radd_rem0 = (int)(wrow0 % (size_t)a.rowadd_div);
+        }
+      }
+      // EPI 3 with the broadcast row-add: the row groups this warp's valid rows span (at most 5: launch_tc keeps
+      // rowadd_div >= 8 here) and the group of my row (lane = row)
+      int tma_ng = 0, tma_gi = 0;
+      if constexpr (TMA) {
+        if (a.rowadd && wrows > 0) {
+          tma_ng = (radd_rem0 + wrows - 1) / a.rowadd_div + 1;
+          tma_gi = min((radd_rem0 + lane) / a.rowadd_div, tma_ng - 1);
         }
       }
       mbar_wait(&bar_tfull[acc], (uint32_t)acc_phase);
@@ -859,6 +914,90 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
             }
             __syncwarp();                                       // before the next block overwrites the tile
           }
+        } else if constexpr (TMA) {
+          // ---- TMA-store epilogue: lane = row parks its 32 columns (+ bias) in a 32 x 32 staging tile laid out as the
+          //      tensor map expects (128-byte rows, 16-byte chunk j of row r at j ^ (r & 7)), one lane issues the bulk
+          //      store (rows beyond the sample and columns beyond max(N, ldc_zero_to) are clipped by the TMA unit), and the
+          //      column statistics are read back from the same tile, lane = column, while the store drains.  No
+          //      per-element STG, no 64-bit address arithmetic: ~3 (store only) to ~9 instructions per element-row. ----
+          const int n = n0 + cb + lane;
+          const bool nin = n < a.N;
+          const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
+          if (a.rowadd) {
+            // bias + the broadcast row of every group, lane = column; same association as the scalar flavour:
+            // y = acc + (bias + rowadd)
+            const float *rp = a.rowadd + radd_g0 * a.ld_rowadd + (nin ? n : 0);
+            for (int g = 0; g < tma_ng; ++g) {
+              s_t[g * 36 + lane] = bias_n + (nin ? __ldg(rp) : 0.f);
+              rp += a.ld_rowadd;
+            }
+          } else {
+            s_t[lane] = bias_n;
+          }
+          __syncwarp();
+          float4 b4[8];                                       // the 32 addends of my row, fetched under the TMEM load
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) b4[j] = *reinterpret_cast<const float4 *>(s_t + tma_gi * 36 + 4 * j);   // broadcast
+          // the store that last read the tile about to be overwritten (two blocks ago) must have finished reading
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __syncwarp();
+          // (explicit shared-space accesses: through a generic pointer into the dynamic region these would be LD.E/ST.E)
+          const uint32_t tile = s_tma + ((uint32_t)warp * 2u + tma_buf) * 4096u;
+          tma_buf ^= 1u;
+          {
+            const uint32_t trow = tile + (uint32_t)lane * 128u;
+            const uint32_t sw = (uint32_t)lane & 7u;
+  #pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (((uint32_t)j ^ sw) << 4)),
+                           "f"(__uint_as_float(v[4 * j]) + b4[j].x), "f"(__uint_as_float(v[4 * j + 1]) + b4[j].y),
+                           "f"(__uint_as_float(v[4 * j + 2]) + b4[j].z), "f"(__uint_as_float(v[4 * j + 3]) + b4[j].w)
+                           : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (wrows > 0)
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmap_c)),
+                  "r"(n0 + cb), "r"(r0 + quarter * 32), "r"(b), "r"(tile)
+                  : "memory");
+            // always a group (possibly empty): wait_group.read 1 above counts groups, one per block
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (a.stats) {
+            const bool needP = !(a.stats_skip & 1), needR = !(a.stats_skip & 2);
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            // element (r, c) sits at r * 128 + (((c >> 2) ^ (r & 7)) << 4) + (c & 3) * 4 bytes: 8 per-lane offsets, one
+            // per value of r & 7, then immediates
+            uint32_t toff[8];
+  #pragma unroll
+            for (int k = 0; k < 8; ++k) toff[k] = tile + ((((uint32_t)lane >> 2) ^ (uint32_t)k) << 4) + ((uint32_t)lane & 3u) * 4u;
+            auto rows_loop = [&](auto p_c, auto r_c, auto full_c) {
+              constexpr bool P = decltype(p_c)::value, R = decltype(r_c)::value, FULL = decltype(full_c)::value;
+  #pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                if (!FULL && r >= wrows) break;
+                float t;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(toff[r & 7] + (uint32_t)r * 128u) : "memory");
+                if constexpr (P) { q0 += t; q1 = fmaf(t, t, q1); }
+                if constexpr (R) { const float p = fmaxf(t, 0.f); q2 += p; q3 = fmaf(p, p, q3); }
+              }
+            };
+            using T = std::true_type; using F = std::false_type;
+            if (wrows == 32) {
+              if (needP && needR) rows_loop(T{}, T{}, T{});
+              else if (needP) rows_loop(T{}, F{}, T{});
+              else if (needR) rows_loop(F{}, T{}, T{});
+            } else {
+              rows_loop(T{}, T{}, F{});
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part_g + (uint32_t)((quarter * BN + cb + lane) * 16)),
+                         "f"(q0), "f"(q1), "f"(q2), "f"(q3) : "memory");
+          }
+          __syncwarp();                                         // s_t (the addends) is rewritten by the next block
         } else {
           // per-column constants are fetched while the TMEM load is in flight
           const int hi = lane / CW, cl = lane % CW;
@@ -970,6 +1109,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
       if (alt) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    // the staging tiles must outlive the bulk stores that read them
+    if (TMA && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -982,17 +1123,68 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan) {
 
 constexpr int kPlanDoesNotFit = 12345;
 
-// Epilogue flavour.  Measured on B200 (profiles/r01_epilogue_ab_v7.txt): the float4 / packed-f32x2 epilogue wins
-// where the broadcast row-add is used on 32-column blocks (one float4 of the query term per lane and block instead of a
-// dependent scalar load per row group: 0.240 -> 0.177 ms on the 524288 x 172 x 128 score GEMM), the scalar one wins
-// everywhere else (lower per-block fixed cost; 15-20 % faster on the 16-column blocks of the narrowest tile).  auto = pick per call; PDR_GEMM_EPILOGUE=scalar|vec4 forces one (tests, A/B).
+// Epilogue flavour.  Measured on B200:
+//  * profiles/r01_epilogue_ab_v7.txt: float4 / packed-f32x2 beats scalar only where the broadcast row-add is used on
+//    32-column blocks (0.240 -> 0.177 ms on the 524288 x 172 x 128 score GEMM); scalar wins elsewhere.
+//  * profiles/r01_tma_epilogue_ab_v10.txt: the TMA-store flavour takes the dense 2 M x 32 x 32 GEMMs from 3.9 to
+//    4.9-5.9 TB/s and is neutral to +3 % elsewhere.
+// Default = tma (row groups of at least 8 rows; shorter ones fall back to the old choice).
+// PDR_GEMM_EPILOGUE=auto|scalar|vec4|tma forces one (tests, A/B); auto = the pre-TMA hybrid.
 int epilogue_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char *e = getenv("PDR_GEMM_EPILOGUE");
-    mode = !e ? 2 : (e[0] == 's' ? 0 : (e[0] == 'v' ? 1 : 2));
+    mode = !e ? 3 : (e[0] == 's' ? 0 : (e[0] == 'v' ? 1 : (e[0] == 't' ? 3 : 2)));
   }
   return mode;
+}
+
+// cuTensorMapEncodeTiled without linking libcuda: the entry point comes from the runtime
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// C seen by the TMA unit: (columns written, rows of one sample, samples), 32 x 32 x 1 boxes, 128-byte swizzle.
+// Clipping at dims 0 and 1 is what keeps a partial tile from touching the pad columns / the next sample.
+int make_c_tensor_map(const PdrGemmArgs &a, CUtensorMap *tm) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("gemm_tf32: cuTensorMapEncodeTiled is not available"); return PDR_ERR_UNSUPPORTED; }
+  const int cols = a.N > a.ldc_zero_to ? a.N : a.ldc_zero_to;
+  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)a.rows_per_sample, (cuuint64_t)a.batch};
+  const cuuint64_t gstr[2] = {(cuuint64_t)a.ldc * 4u, (cuuint64_t)a.rows_per_sample * (cuuint64_t)a.ldc * 4u};
+  const cuuint32_t box[3] = {32u, 32u, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)a.C, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tf32: cuTensorMapEncodeTiled failed (%d)", (int)r); return PDR_ERR_CUDA; }
+  return 0;
+}
+
+// PDR_GEMM_PROD_SLEEP=<ns>: back-off of the producers' empty-stage polls (0 = spin on try_wait)
+int producer_sleep_ns() {
+  static int ns = -1;
+  if (ns < 0) {
+    const char *e = getenv("PDR_GEMM_PROD_SLEEP");
+    ns = e ? atoi(e) : 0;
+    if (ns < 0) ns = 0;
+  }
+  return ns;
 }
 
 bool epilogue_alternates_tiles() {
@@ -1014,8 +1206,17 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   plan.total_items = (int)items;
   plan.nk = ceil_div(a.K, kTcBK);
   plan.epi_alt = epilogue_alternates_tiles() ? 1 : 0;
-  const size_t epi = (size_t)(BN <= 128 ? 4 : 2) * 4 * BN * 16;   // column partials: 2 epilogue groups (x 2 tile parities)
-  const size_t static_smem = (size_t)(kEpiWarps * 32 * 36) * sizeof(float) + 512;
+  plan.prod_sleep_ns = producer_sleep_ns();
+  // epilogue flavour: pooling when asked for; float4 for the broadcast row-add on 32-column blocks; otherwise scalar, or
+  // (PDR_GEMM_EPILOGUE=tma) the TMA-store flavour (row groups of at least 8 rows)
+  const int mode = epilogue_mode();
+  int vec;
+  if (a.pool_K > 0) vec = 2;
+  else if (mode == 3) vec = (a.rowadd && a.rowadd_div < 8) ? (BN > 32 ? 1 : 0) : 3;
+  else vec = (mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1) ? 1 : 0;
+  const size_t epi = (size_t)(BN <= 128 ? 4 : 2) * 4 * BN * 16 +   // column partials: 2 epilogue groups (x 2 tile parities)
+                     (vec == 3 ? (size_t)kTmaStageBytes : 0);       // + the staging tiles of the TMA stores
+  const size_t static_smem = (size_t)(kEpiWarps * (vec == 3 ? 192 : 32 * 36)) * sizeof(float) + 512;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;
   bool planned = false;
@@ -1042,18 +1243,23 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     set_error("gemm_tf32: shared memory budget exceeded (K=%d N=%d)", a.K, a.N);
     return PDR_ERR_UNSUPPORTED;
   }
-  const int mode = epilogue_mode();
-  const int vec = a.pool_K > 0 ? 2 : ((mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1) ? 1 : 0);
-  auto kern = vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
-                       : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
-  static bool configured[3] = {false, false, false};
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (vec == 3) {
+    const int rc = make_c_tensor_map(a, &tmap);
+    if (rc != 0) return rc;
+  }
+  auto kern = vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
+              : vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
+                         : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
+  static bool configured[4] = {false, false, false, false};
   if (!configured[vec]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
     configured[vec] = true;
   }
   const int grid = plan.total_items < kNumSMs ? plan.total_items : kNumSMs;
-  kern<<<grid, kTcThreads, smem, stream>>>(a, plan);
+  kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap);
   return check_launch("gemm_tf32_persistent");
 }
 

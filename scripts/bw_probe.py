@@ -34,4 +34,22 @@ out = {
     "read1_write3_GBps": best(lambda: b[:3 * q].view(3, q).copy_(a[:q].unsqueeze(0).expand(3, q)), 4 * 4 * q),
     "read2_write1_GBps": best(lambda: torch.add(a[:q], a[q:2 * q], out=b[:q]), 4 * 3 * q),
 }
+# incompressible data through our own store paths (pdr_probe_hbm): fill_/zero_ write a constant
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from point_diffusion_refinement_b200 import _lib
+L = _lib.lib()
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def probe(mode):
+    rc = L.pdr_probe_hbm(mode, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_size_t(n), st)
+    assert rc == 0, L.pdr_last_error_string()
+
+
+out["write_only_hash_stg128_GBps"] = best(lambda: probe(0), 4 * n)
+out["read1_write3_hash_stg128_GBps"] = best(lambda: probe(1), 4 * n * 4 // 3)
+out["write_only_hash_tma_bulk_GBps"] = best(lambda: probe(2), 4 * n)
+chk = a[:4096].clone()
+assert torch.isfinite(chk).all() and chk.min() >= 1 and chk.max() < 2 and chk.unique().numel() > 4000
 print(json.dumps(out))
