@@ -129,6 +129,16 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool p
 __device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void *src, int bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
+// ignore-src form: one LDGSTS.ZFILL with a predicate, no src-size arithmetic; with `ignore` the source is not read
+__device__ __forceinline__ void cp_async16_ignore(uint32_t dst, const void *src, bool ignore) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+      "}\n" ::"r"(dst), "l"(src), "r"((int)ignore)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -421,22 +431,23 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         const int ksz = kin ? 16 : 0;
         const bool afull = cl.rows_valid == kTcTileM;
         if (has_tail && kofs >= a.k_pro) {
+          // One address form for both halves of the tail, so that the warp does not split into a gathered, a geometric
+          // and a zero-fill path (three serial passes of ~20 instructions per row in the first version, which made the two
+          // loader warps the bottleneck of every folded-residual GEMM: profiles/r01_ncu_gemm16_v10_notes.txt):
+          //   src = base + sel * mul,  sel = table row (gathered part) | i (geometric part, rows lrow + 8 i),  sel < 0 -> zeros
           const int t0 = kofs - a.k_pro + lchunk * 4;             // column inside the tail
-          if (t0 < a.t_split) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const bool ok = tidx[i] >= 0;
-              cp_async16_sz(sa + i * 1024, ok ? a.T + (size_t)tidx[i] * a.ldt + t0 : a.A, ok ? 16 : 0);
-            }
-          } else {
+          const bool is_g = t0 < a.t_split;
+          const int nval = kin ? (cl.rows_valid - lrow + 7) >> 3 : 0;          // valid rows of this thread
+          const float *base = a.T + t0;
+          if (!is_g) {
             const size_t row = (size_t)cl.b * a.rows_per_sample + cl.tis * kTcTileM + lrow;
-            const float *src = a.T2 + row * a.ldt2 + (t0 - a.t_split);
-            const size_t st2 = (size_t)8 * a.ldt2;
+            base = nval > 0 ? a.T2 + row * a.ldt2 + (t0 - a.t_split) : a.T2;
+          }
+          const int mul = is_g ? a.ldt : 8 * a.ldt2;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const bool ok = kin && lrow + 8 * i < cl.rows_valid;
-              cp_async16_sz(sa + i * 1024, ok ? src + i * st2 : a.A, ok ? 16 : 0);
-            }
+          for (int i = 0; i < 16; ++i) {
+            const int sel = is_g ? tidx[i] : (i < nval ? i : -1);
+            cp_async16_ignore(sa + i * 1024, base + (long long)max(sel, 0) * mul, sel < 0);
           }
         } else if (afull) {
           const float *src = kin ? cl.pa + kofs : a.A;
@@ -661,6 +672,24 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
           tma_gi = min((radd_rem0 + lane) / a.rowadd_div, tma_ng - 1);
         }
       }
+      // EPI 3: the per-column addends (bias + the broadcast row of each group; lane = column) of the tile's first block
+      // are requested before the accumulator is waited for, so that single-block tiles (N <= 32) have no global latency
+      // between the TMEM load and the bulk store
+      float addn[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      auto load_addends = [&](int cb_) {
+        const int n = n0 + cb_ + lane;
+        const bool nin = n < a.N;
+        const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
+        addn[0] = bias_n;
+        if (a.rowadd) {
+          // same association as the scalar flavour: y = acc + (bias + rowadd)
+          const float *rp = a.rowadd + radd_g0 * a.ld_rowadd + (nin ? n : 0);
+#pragma unroll
+          for (int g = 0; g < 5; ++g)
+            if (g < tma_ng) addn[g] = bias_n + (nin ? __ldg(rp + (size_t)g * a.ld_rowadd) : 0.f);
+        }
+      };
+      if constexpr (TMA) load_addends(cb0);
       mbar_wait(&bar_tfull[acc], (uint32_t)acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -920,24 +949,19 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
           //      store (rows beyond the sample and columns beyond max(N, ldc_zero_to) are clipped by the TMA unit), and the
           //      column statistics are read back from the same tile, lane = column, while the store drains.  No
           //      per-element STG, no 64-bit address arithmetic: ~3 (store only) to ~9 instructions per element-row. ----
-          const int n = n0 + cb + lane;
-          const bool nin = n < a.N;
-          const float bias_n = (nin && a.bias) ? __ldg(a.bias + n) : 0.f;
-          if (a.rowadd) {
-            // bias + the broadcast row of every group, lane = column; same association as the scalar flavour:
-            // y = acc + (bias + rowadd)
-            const float *rp = a.rowadd + radd_g0 * a.ld_rowadd + (nin ? n : 0);
-            for (int g = 0; g < tma_ng; ++g) {
-              s_t[g * 36 + lane] = bias_n + (nin ? __ldg(rp) : 0.f);
-              rp += a.ld_rowadd;
-            }
-          } else {
-            s_t[lane] = bias_n;
-          }
+          // (later blocks fetch theirs here: requesting them during the previous block was measured ~10 % slower on every
+          //  multi-block tile, gpurun call r01s3d -- the loads in flight share a scoreboard with the TMEM load)
+          if (cb != cb0) load_addends(cb);
+#pragma unroll
+          for (int g = 0; g < 5; ++g)
+            if (g == 0 || g < tma_ng) s_t[g * 36 + lane] = addn[g];
           __syncwarp();
-          float4 b4[8];                                       // the 32 addends of my row, fetched under the TMEM load
+          // the 32 addends of my row (broadcast reads): the first half is fetched under the TMEM load, the second under
+          // the first four stores -- all eight at once cost 16 more live registers than the 96 this kernel can have
+          const float *sadd = s_t + tma_gi * 36;
+          float4 b4[4];
   #pragma unroll
-          for (int j = 0; j < 8; ++j) b4[j] = *reinterpret_cast<const float4 *>(s_t + tma_gi * 36 + 4 * j);   // broadcast
+          for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4 *>(sadd + 4 * j);
           // the store that last read the tile about to be overwritten (two blocks ago) must have finished reading
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -948,12 +972,17 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
           {
             const uint32_t trow = tile + (uint32_t)lane * 128u;
             const uint32_t sw = (uint32_t)lane & 7u;
+            float4 c4[4];
   #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j) c4[j] = *reinterpret_cast<const float4 *>(sadd + 16 + 4 * j);
+  #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = j < 4 ? b4[j] : c4[j - 4];
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (((uint32_t)j ^ sw) << 4)),
-                           "f"(__uint_as_float(v[4 * j]) + b4[j].x), "f"(__uint_as_float(v[4 * j + 1]) + b4[j].y),
-                           "f"(__uint_as_float(v[4 * j + 2]) + b4[j].z), "f"(__uint_as_float(v[4 * j + 3]) + b4[j].w)
+                           "f"(__uint_as_float(v[4 * j]) + b.x), "f"(__uint_as_float(v[4 * j + 1]) + b.y),
+                           "f"(__uint_as_float(v[4 * j + 2]) + b.z), "f"(__uint_as_float(v[4 * j + 3]) + b.w)
                            : "memory");
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
