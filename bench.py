@@ -25,6 +25,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+JSON_OUT = [sys.stdout]      # where the single JSON line goes; main() points sys.stdout at stderr for everything else
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -239,7 +240,7 @@ def run_reference_arm(args, rank):
             "cpu_baseline": {"value": value, "unit": "shapes/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), flush=True, file=JSON_OUT[0])
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -363,6 +364,18 @@ def fast_ddpm_lines(net, dev, B, dh, cond, label, rank):
 # ------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # contract: stdout carries exactly ONE JSON line.  Everything the library prints on the way (the reference's
+    # "begin sampling ..." banners, kept for drop-in fidelity) goes to stderr.
+    json_out = sys.stdout
+    sys.stdout = sys.stderr
+    try:
+        _main(args, json_out)
+    finally:
+        sys.stdout = json_out
+
+
+def _main(args, json_out):
+    JSON_OUT[0] = json_out
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -561,7 +574,7 @@ def main():
         "gpu_launches": launches, "eval_kernels": eval_kernels, "geometry_kernels": geometry_kernels,
         "fast_ddpm": fast_ddpm,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), flush=True, file=JSON_OUT[0])
     if world > 1:
         dist.destroy_process_group()
 
