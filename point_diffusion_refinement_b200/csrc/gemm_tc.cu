@@ -167,7 +167,14 @@ constexpr int kTmaStageBytes = kEpiWarps * 2 * 4096;
 
 // EPI: 0 = scalar epilogue, 1 = float4 epilogue, 2 = attention pooling over the K neighbour rows (no C store),
 //      3 = TMA-store epilogue (32 x 32 boxes through a 128B-swizzled staging tile, statistics read back column-wise)
-template <int BN, bool WRES, int EPI>
+//
+// GRING (experiment, opt-in through PDR_GEMM_IDX_RING=1; gathered A in the direct producers only): the neighbour-row indices
+// travel through a per-warp shared-memory ring filled by 4-byte cp.async kRingD items ahead and signalled by
+// cp.async.mbarrier.arrive, instead of register look-ahead -- a register that receives a look-ahead load shares its scoreboard
+// with the loads issued after it, so consuming the oldest one waits for the youngest (profiles/r01_ncu_gemm16_v10_notes.txt:
+// 38 % of the producers' time on the first GEMM of every stage).  NOT yet run on a GPU.
+constexpr int kRingD = 4;
+template <int BN, bool WRES, int EPI, bool GRING = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c) {
   constexpr int kBTileBytes = BN * 128;
@@ -178,6 +185,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2], bar_wready;
   __shared__ uint64_t bar_rfull[kMaxStages];   // transform mode: raw A (+R) of the stage has landed
   __shared__ uint32_t s_tmem_base;
+  __shared__ int s_iring[GRING ? kProdWarps : 1][kRingD][16];            // GRING: 16 indices per producer warp and item
+  __shared__ uint64_t bar_iring[GRING ? kProdWarps : 1][kRingD];
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
   // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
@@ -206,6 +215,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     mbar_init(&bar_tempty[0], tempty_count); mbar_init(&bar_tempty[1], tempty_count);
     mbar_init(&bar_wready, kProdThreads);
     for (int r = 0; r < S; ++r) mbar_init(&bar_rfull[r], kLoadThreads);
+    if constexpr (GRING)
+      for (int w = 0; w < kProdWarps; ++w)
+        for (int d = 0; d < kRingD; ++d) mbar_init(&bar_iring[w][d], 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -268,8 +280,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     // gathered A (PdrGemmArgs.a_rows): the neighbour rows of the CURRENT item sit in cidx, those of the NEXT item of
     // this CTA are already in flight in nidx, so the index loads never stall the copy loop
     const bool gath = a.a_rows != nullptr;
-    // (kIdxAhead items ahead; 3 measured neutral-to-slower than 1 on B200, gpurun call r01s3b: the producers are not
-    // waiting for these loads)
+    // (kIdxAhead items ahead; 3 measured neutral-to-slower than 1 on B200, gpurun call r01s3b: the registers of all
+    // look-ahead loads share one scoreboard, so the consumer of the oldest waits for the youngest -- see GRING)
     constexpr int kIdxAhead = 1;
     int cidx[4] = {-1, -1, -1, -1}, nidx[kIdxAhead][4];
 #pragma unroll
@@ -284,6 +296,37 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 4; ++i) out[i] = (r0 + arow + 32 * i < a.rows_per_sample) ? __ldg(p + 32 * i) : -1;
     };
+    // GRING: lanes 0..15 of a producer warp copy the 16 indices the warp needs for `item` (rows 4 pw + a + 32 i at slot
+    // entry a + 4 i) and arrive on the slot's barrier; every lane of the warp later waits on it and reads its 4 entries
+    const int pw = warp - kEpiWarps;
+    int ring_slot = 0, ring_phase = 0;
+    auto ring_issue = [&](int item, int slot) {
+      if constexpr (GRING) {
+        if (lane < 16) {
+          if (item < plan.total_items) {
+            const int tile = item / plan.n_tiles_n;
+            const int b = tile / plan.tiles_per_sample, r0 = (tile - b * plan.tiles_per_sample) * kTcTileM;
+            const int row = r0 + 4 * pw + (lane & 3) + 32 * (lane >> 2);
+            const bool ok = row < a.rows_per_sample;
+            const int *src = ok ? a.a_rows + (size_t)b * a.rows_per_sample + row : a.a_rows;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(&s_iring[pw][slot][lane])), "l"(src),
+                         "r"(ok ? 4 : 0)
+                         : "memory");
+          }
+          cp_async_arrive_noinc(&bar_iring[pw][slot]);
+        }
+      }
+    };
+    auto ring_take = [&](int next_item) {        // indices of the item at the head of the ring -> cidx; refill the slot
+      if constexpr (GRING) {
+        mbar_wait(&bar_iring[pw][ring_slot], (uint32_t)ring_phase);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cidx[i] = s_iring[pw][ring_slot][(lane >> 3) + 4 * i];
+        __syncwarp();                              // every lane has read the slot before it is refilled
+        ring_issue(next_item, ring_slot);
+        if (++ring_slot == kRingD) { ring_slot = 0; ring_phase ^= 1; }
+      }
+    };
     auto derive = [&](Cur &c) {  // pointers and row count from (b, tis)
       const int r0 = c.tis * kTcTileM;
       c.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
@@ -292,7 +335,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       c.pr = a.R ? a.R + row * a.ldr + chunk * 4 : nullptr;
       if (gath) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c.pg[i] = cidx[i] >= 0 ? a.A + (size_t)cidx[i] * a.lda + chunk * 4 : nullptr;
+        for (int i = 0; i < 4; ++i)
+          c.pg[i] = (cidx[i] >= 0 && (!GRING || arow + 32 * i < c.rows_valid)) ? a.A + (size_t)cidx[i] * a.lda + chunk * 4
+                                                                               : nullptr;
         c.p2 = a.A2 + row * a.lda2 + chunk * 4;
       }
     };
@@ -302,7 +347,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       c.item += G;
       if (fast_adv) { c.tis += G; if (c.tis >= plan.tiles_per_sample) { c.tis -= plan.tiles_per_sample; ++c.b; } }
       else locate(c);
-      if (gath) {
+      if (GRING && gath) {
+        ring_take(c.item + kRingD * G);
+      } else if (gath) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) cidx[i] = nidx[0][i];
 #pragma unroll
@@ -319,7 +366,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     const size_t w_step = (size_t)32 * a.ldw;
     Cur ci;
     ci.item = (int)blockIdx.x; ci.kc = 0;
-    if (gath && !is_loader) {
+    if (GRING && gath && !is_loader) {
+#pragma unroll
+      for (int d = 0; d < kRingD; ++d) ring_issue(ci.item + d * G, d);
+      ring_take(ci.item + kRingD * G);
+    } else if (gath && !is_loader) {
       fetch_idx(ci.item, cidx);
 #pragma unroll
       for (int d = 0; d < kIdxAhead; ++d) fetch_idx(ci.item + (d + 1) * G, nidx[d]);
@@ -1216,6 +1267,16 @@ int producer_sleep_ns() {
   return ns;
 }
 
+// PDR_GEMM_IDX_RING=1: gathered-A indices through the shared-memory ring (GRING instantiations; experiment)
+bool index_ring_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("PDR_GEMM_IDX_RING");
+    mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  return mode == 1;
+}
+
 bool epilogue_alternates_tiles() {
   static int mode = -1;
   if (mode < 0) {
@@ -1245,7 +1306,9 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   else vec = (mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1) ? 1 : 0;
   const size_t epi = (size_t)(BN <= 128 ? 4 : 2) * 4 * BN * 16 +   // column partials: 2 epilogue groups (x 2 tile parities)
                      (vec == 3 ? (size_t)kTmaStageBytes : 0);       // + the staging tiles of the TMA stores
-  const size_t static_smem = (size_t)(kEpiWarps * (vec == 3 ? 192 : 32 * 36)) * sizeof(float) + 512;
+  const bool gring = vec == 3 && a.a_rows != nullptr && index_ring_enabled();
+  const size_t static_smem = (size_t)(kEpiWarps * (vec == 3 ? 192 : 32 * 36)) * sizeof(float) + 512 +
+                             (gring ? (size_t)kProdWarps * kRingD * (16 * sizeof(int) + sizeof(uint64_t)) : 0);
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;
   bool planned = false;
@@ -1278,14 +1341,16 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     const int rc = make_c_tensor_map(a, &tmap);
     if (rc != 0) return rc;
   }
-  auto kern = vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
+  auto kern = gring      ? gemm_tf32_persistent<BN, WRES, 3, true>
+              : vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
               : vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
                          : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
-  static bool configured[4] = {false, false, false, false};
-  if (!configured[vec]) {
+  static bool configured[5] = {false, false, false, false, false};
+  const int cfg_slot = gring ? 4 : vec;
+  if (!configured[cfg_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
-    configured[vec] = true;
+    configured[cfg_slot] = true;
   }
   const int grid = plan.total_items < kNumSMs ? plan.total_items : kNumSMs;
   kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap);
