@@ -213,6 +213,10 @@ typedef struct PdrGemmArgs {
   const int *tail_rows; const float *T; int ldt; const float *T2; int ldt2; int t_split; int k_pro;
   int pool_K; const float *pool_V; int pool_ldv; const float *pool_sc; const float *pool_sh; int pool_ld_scsh;
   const int *pool_counts; float *pool_out; int pool_ldo;
+  /* tensor-core path: upper bound on the CTAs of the persistent grid (0 = one per SM).  A caller that runs another
+   * kernel next to this GEMM on a second stream (the engine's geometry chain, PDR_GEOM_OVERLAP) leaves it some SMs:
+   * CTAs of this kernel take a whole SM each and never share it. */
+  int max_ctas;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);

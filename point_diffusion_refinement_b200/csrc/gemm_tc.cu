@@ -1352,7 +1352,8 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
     configured[cfg_slot] = true;
   }
-  const int grid = plan.total_items < kNumSMs ? plan.total_items : kNumSMs;
+  const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
+  const int grid = plan.total_items < sm_cap ? plan.total_items : sm_cap;
   kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap);
   return check_launch("gemm_tf32_persistent");
 }

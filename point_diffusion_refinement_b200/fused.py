@@ -56,7 +56,8 @@ class GemmArgs(ctypes.Structure):
                 ("t_split", ctypes.c_int), ("k_pro", ctypes.c_int),
                 ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
                 ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
-                ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int)]
+                ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int),
+                ("max_ctas", ctypes.c_int)]
 
 
 class GnSource(ctypes.Structure):
@@ -75,6 +76,13 @@ class GnArgs(ctypes.Structure):
 PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
 # A/B switch for profiling only: PDR_STATS_SKIP=0 makes every GEMM epilogue accumulate both statistics pairs
 _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
+# PDR_GEOM_OVERLAP=1 (experiment, not yet run on a GPU): the per-step geometry chain (FPS x4 -> centre gathers -> 8 of the 9
+# ball queries -> kNN x4; ~1.0 ms of small grids, profiles/r01_ncu_launch_list_v10.csv) runs on a second stream next to the
+# first encoder feature-mapper block, which only needs the level-0 ball query.  The GEMMs of that block leave
+# 148 - PDR_GEOM_OVERLAP_CTAS SMs free (PdrGemmArgs.max_ctas): their CTAs own a whole SM and would otherwise serialise
+# against the 32-CTA FPS kernel.
+_GEOM_OVERLAP = os.environ.get("PDR_GEOM_OVERLAP", "0") == "1"
+_GEOM_OVERLAP_CTAS = int(os.environ.get("PDR_GEOM_OVERLAP_CTAS", "116"))
 # PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
 _FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
 # PDR_FUSE_POOL=1 pools inside the score GEMM's epilogue (PdrGemmArgs.pool_*; bit-identical, scores never stored).
@@ -204,6 +212,13 @@ class FusedDenoiser:
         self.cond_key = None
         self.n_kernel_calls = 0
         self._built = False
+        # geometry overlap (PDR_GEOM_OVERLAP): which ops of the main program go to the side stream, the CTA cap of the
+        # GEMMs emitted while it is set, and the op index at which the main stream waits for the side stream
+        self.side_ops = set()
+        self._emit_side = False
+        self._cta_limit = 0
+        self._join_at = None
+        self._side_stream = None
 
     # ------------------------------------------------------------------------------------------------
     # small helpers that append to the program
@@ -230,6 +245,8 @@ class FusedDenoiser:
             if rc != 0:
                 raise PdrError("%s failed (%d): %s" % (fn_name, rc, lib.pdr_last_error_string().decode()))
         self._ops.append(op)
+        if self._emit_side and self._ops is self.ops:
+            self.side_ops.add(len(self.ops) - 1)
         if self._ops is self.ops:
             self.n_kernel_calls += 1
         else:
@@ -238,6 +255,8 @@ class FusedDenoiser:
     def _torch(self, fn):
         self._meta.append(("torch", {}))
         self._ops.append(fn)
+        if self._emit_side and self._ops is self.ops:
+            self.side_ops.add(len(self.ops) - 1)
 
     def gemm(self, A, W, bias, out, rows_per_sample, batch=None, pro=PRO_NONE, scsh=None, add=None, R=None,
              rowadd=None, rowadd_div=1, want_stats=False, K=None, zero_to=None, pool=None, tail=None):
@@ -284,6 +303,7 @@ class FusedDenoiser:
             g.pool_out, g.pool_ldo = pout.ptr, pout.ld
             self.keep.append(pool)
         g.batch, g.rows_per_sample = batch, rows_per_sample
+        g.max_ctas = self._cta_limit if self._ops is self.ops else 0
         g.pro_mode = pro
         if pro != PRO_NONE:
             sc, sh = scsh
@@ -683,6 +703,20 @@ class FusedDenoiser:
         # ---- geometry ----------------------------------------------------------------------------------
         xyz = [self.x_in]
         fps_idx, ball, knn = [], {}, []
+        # PDR_GEOM_OVERLAP: the level-0 mapper query (x_t against the condition cloud, no FPS needed) is emitted first on
+        # the main stream; everything else of this section is tagged for the side stream
+        overlap = _GEOM_OVERLAP and L >= 1 and self.use_tf32
+
+        def ball_query(tag, centres, P, pts, n, radius, ns):
+            idx = self._zeros(B, P, ns, dtype=torch.int32)
+            cnt = self._zeros(B, P, dtype=torch.int32)
+            self._emit("pdr_ball_query", B, n, P, ctypes.c_float(radius), ns, ctypes.c_void_p(centres.data_ptr()),
+                       ctypes.c_void_p(pts.data_ptr()), ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(cnt.data_ptr()))
+            ball[tag] = (idx, cnt)
+
+        if overlap:
+            ball_query(("map", 0), xyz[0], n_lvl[0], uvw[0], m_lvl[0], marc["encoder_radius"][0], marc["encoder_nsample"][0])
+            self._emit_side = True
         for i in range(L):
             idx = self._zeros(B, n_lvl[i + 1], dtype=torch.int32)
             self._emit("pdr_furthest_point_sampling", B, n_lvl[i], n_lvl[i + 1], ctypes.c_void_p(xyz[i].data_ptr()), None,
@@ -692,15 +726,9 @@ class FusedDenoiser:
                        ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(nx.data_ptr()), 3)
             fps_idx.append(idx); xyz.append(nx)
 
-        def ball_query(tag, centres, P, pts, n, radius, ns):
-            idx = self._zeros(B, P, ns, dtype=torch.int32)
-            cnt = self._zeros(B, P, dtype=torch.int32)
-            self._emit("pdr_ball_query", B, n, P, ctypes.c_float(radius), ns, ctypes.c_void_p(centres.data_ptr()),
-                       ctypes.c_void_p(pts.data_ptr()), ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(cnt.data_ptr()))
-            ball[tag] = (idx, cnt)
-
         for i in range(L):
-            ball_query(("map", i), xyz[i], n_lvl[i], uvw[i], m_lvl[i], marc["encoder_radius"][i], marc["encoder_nsample"][i])
+            if not (overlap and i == 0):
+                ball_query(("map", i), xyz[i], n_lvl[i], uvw[i], m_lvl[i], marc["encoder_radius"][i], marc["encoder_nsample"][i])
             assert marc["decoder_radius"][i] == marc["encoder_radius"][i] and marc["decoder_nsample"][i] == marc["encoder_nsample"][i]
             ball_query(("sa", i), xyz[i + 1], n_lvl[i + 1], xyz[i], n_lvl[i], arch["radius"][i], K_ball[i])
         ball_query(("map", L), xyz[L], n_lvl[L], uvw[L], m_lvl[L], marc["decoder_radius"][L], marc["decoder_nsample"][L])
@@ -711,6 +739,7 @@ class FusedDenoiser:
                        ctypes.c_void_p(xyz[lvl].data_ptr()), ctypes.c_void_p(kd.data_ptr()), ctypes.c_void_p(kidx.data_ptr()))
             knn.append((lvl, kidx, kd))
         knn = {lvl: (a, b) for lvl, a, b in knn}
+        self._emit_side = False
 
         group_ball = self.group_ball
 
@@ -726,9 +755,14 @@ class FusedDenoiser:
             fm = net.encoder_feature_map[i]
             idx, cnt = ball[("map", i)]
             Cc = enc_cl[i].C
+            if overlap and i == 0:
+                self._cta_limit = _GEOM_OVERLAP_CTAS          # this block runs next to the geometry chain
             X0 = group_ball(enc_cl[i], Cc, uvw[i], m_lvl[i], xyz[i], n_lvl[i], idx.shape[2], idx, cnt, True)
             self.grouped_block("enc_map%d" % i, X0, Cc + 9, idx.shape[2], n_lvl[i] * idx.shape[2], fm.mlp, fm.attention_module,
                                Fl[i].cols(cm, own_dim[i]), cnt, Fl[i].cols(0, cm), no_emb2)
+            if overlap and i == 0:
+                self._cta_limit = 0
+                self._join_at = len(self.ops)                 # the SA block below is the first consumer of the side stream
             sa = net.SA_modules[i]
             idx, cnt = ball[("sa", i)]
             Cin = cm + own_dim[i]
@@ -929,7 +963,25 @@ class FusedDenoiser:
                 col += acc.shape[1]
 
     def run_program(self):
-        for op in self.ops:
+        if self._join_at is None or not self.side_ops:
+            for op in self.ops:
+                op()
+            return
+        # geometry overlap: fork the tagged ops onto the side stream, join before their first consumer.  Works the same
+        # eagerly and under CUDA-graph capture (the side stream joins the capture through wait_stream and rejoins).
+        main = torch.cuda.current_stream(self.dev)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.dev)
+        side = self._side_stream
+        side.wait_stream(main)                                # x_in / ts_in are written on the main stream
+        with torch.cuda.stream(side):
+            for k in sorted(self.side_ops):
+                self.ops[k]()
+        for k, op in enumerate(self.ops):
+            if k in self.side_ops:
+                continue
+            if k == self._join_at:
+                main.wait_stream(side)
             op()
 
     def profile(self):

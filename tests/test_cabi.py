@@ -63,3 +63,39 @@ def test_package_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src and "cpu_oracle" not in src, fn
+
+
+def test_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """PdrGemmArgs / PdrGnArgs are passed by address: the ctypes mirrors in fused.py must have the header's layout
+    field for field (gcc's offsetof/sizeof against ctypes')."""
+    import ctypes
+    from point_diffusion_refinement_b200.fused import GemmArgs, GnArgs, GnSource
+    header = os.path.join(ROOT, "include", "pdr_b200.h")
+    text = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names.append(re.sub(r"\[.*\]", "", decl.split()[-1].lstrip("*")))
+        return names
+
+    src = ['#include <stddef.h>', '#include <stdio.h>', '#include "pdr_b200.h"', 'int main(void) {']
+    want = {}
+    for cname, mirror in (("PdrGemmArgs", GemmArgs), ("PdrGnSource", GnSource), ("PdrGnArgs", GnArgs)):
+        fields = c_fields(cname)
+        assert fields == [f[0] for f in mirror._fields_], (cname, fields, [f[0] for f in mirror._fields_])
+        src.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        want[cname] = ctypes.sizeof(mirror)
+        for f in fields:
+            src.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+            want["%s.%s" % (cname, f)] = getattr(mirror, f).offset
+    src += ["  return 0;", "}"]
+    cfile = tmp_path / "layout.c"
+    cfile.write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(cfile)])
+    got = dict((k, int(v)) for k, v in (l.split() for l in subprocess.check_output([exe], text=True).splitlines()))
+    assert got == want, sorted(k for k in want if got.get(k) != want[k])

@@ -171,3 +171,31 @@ def test_compiled_programs_construct_without_a_gpu(cuda_lib):
         assert cond["pdr_gemm_fused"] == 68 and cond["pdr_attention_pool"] == 8 and cond["pdr_group_knn"] == 4
         assert eng.condition_shapes(384) == ([384, 128, 64, 32, 16], [4, 32, 64, 64, 128], [32, 32, 64, 64, 128])
         assert [v.C for v in eng._enc_cl] == [4, 32, 64, 64, 128] and eng.eps_out.shape == (2, 256, 3)
+
+
+def test_geometry_overlap_program_layout(cuda_lib, monkeypatch):
+    """PDR_GEOM_OVERLAP (opt-in): same multiset of calls; FPS chain, centre gathers, 8 ball queries and the kNN calls are
+    tagged for the side stream; the level-0 mapper query stays first on the main stream; the main stream joins right
+    before the first set-abstraction block; only the GEMMs of the first mapper block carry the CTA cap."""
+    import collections
+    from point_diffusion_refinement_b200 import configs, fused
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    layouts = {}
+    for on in (False, True):
+        monkeypatch.setattr(fused, "_GEOM_OVERLAP", on)
+        eng = fused.FusedDenoiser(PointNet2CloudCondition(configs.tiny_pointnet_config()).eval(), 2, 256, use_tf32=True,
+                                  use_graph=False)
+        eng.build(384)
+        layouts[on] = eng
+    off, on = layouts[False], layouts[True]
+    assert collections.Counter(n for n, _ in off.meta) == collections.Counter(n for n, _ in on.meta)
+    assert not off.side_ops and off._join_at is None
+    names = [n for n, _ in on.meta]
+    side = collections.Counter(names[k] for k in on.side_ops)
+    assert side == {"pdr_furthest_point_sampling": 4, "pdr_gather_rows": 4, "pdr_ball_query": 8, "pdr_knn_points": 4}
+    first_side = min(on.side_ops)
+    assert names[first_side - 1] == "pdr_ball_query" and max(on.side_ops) < on._join_at
+    assert names[on._join_at] == "pdr_group_geo_ball" and names[on._join_at - 1] == "pdr_attention_pool"
+    caps = [g.max_ctas for g in on.keep if isinstance(g, fused.GemmArgs)]
+    assert sum(1 for c in caps if c) == 7 and set(caps) == {0, fused._GEOM_OVERLAP_CTAS}
+    assert all(g.max_ctas == 0 for g in off.keep if isinstance(g, fused.GemmArgs))
