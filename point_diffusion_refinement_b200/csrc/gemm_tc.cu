@@ -174,7 +174,11 @@ constexpr int kTmaStageBytes = kEpiWarps * 2 * 4096;
 // with the loads issued after it, so consuming the oldest one waits for the youngest (profiles/r01_ncu_gemm16_v10_notes.txt:
 // 38 % of the producers' time on the first GEMM of every stage).  NOT yet run on a GPU.
 constexpr int kRingD = 4;
-template <int BN, bool WRES, int EPI, bool GRING = false>
+//
+// TAILX (experiment, opt-in through PDR_GEMM_TAIL_X=1; raw gathered K tail only): the tail chunks are copied by the 8 transform
+// warps, which have nothing to transform there (4 rows per thread, same address form), instead of by the 2 loader warps
+// (16 rows per thread), which the role analysis shows saturated on the folded-residual GEMMs.  NOT yet run on a GPU.
+template <int BN, bool WRES, int EPI, bool GRING = false, bool TAILX = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c) {
   constexpr int kBTileBytes = BN * 128;
@@ -470,7 +474,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       for (int j = 0; j < my_chunks; ++j) {
         const int kofs = cl.kc * kTcBK;
         const bool kin = kofs + lchunk * 4 < a.K;
-        if (has_tail && cl.kc == 0) {
+        if (!TAILX && has_tail && cl.kc == 0) {
           const int r0 = cl.tis * kTcTileM;
           const int *p = a.tail_rows + (size_t)cl.b * a.rows_per_sample + r0 + lrow;
 #pragma unroll
@@ -481,7 +485,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         // interior chunks take a predicate-free path (see the direct producer)
         const int ksz = kin ? 16 : 0;
         const bool afull = cl.rows_valid == kTcTileM;
-        if (has_tail && kofs >= a.k_pro) {
+        if (TAILX && has_tail && kofs >= a.k_pro) {
+          // the transform warps copy this chunk; the loaders only keep the raw-data barrier's phases in step (below)
+        } else if (has_tail && kofs >= a.k_pro) {
           // One address form for both halves of the tail, so that the warp does not split into a gathered, a geometric
           // and a zero-fill path (three serial passes of ~20 instructions per row in the first version, which made the two
           // loader warps the bottleneck of every folded-residual GEMM: profiles/r01_ncu_gemm16_v10_notes.txt):
@@ -582,8 +588,16 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       float4 s4, h4, e4;
       if (my_chunks > 0) fetch(ct, s4, h4, e4);
       int stage = 0, phase = 0;
+      int tidx4[4] = {-1, -1, -1, -1};                          // TAILX: table rows of my 4 tile rows (arow + 32 i)
       for (int j = 0; j < my_chunks; ++j) {
         const bool raw_chunk = ct.kc * kTcBK >= k_pro;          // gathered tail: lands ready for the tensor core
+        const int kc_cur = ct.kc, b_cur = ct.b, tis_cur = ct.tis;
+        if (TAILX && a.tail_rows && kc_cur == 0) {              // requested k_pro / 32 chunks before their first use
+          const int r0 = tis_cur * kTcTileM;
+          const int *p = a.tail_rows + (size_t)b_cur * a.rows_per_sample + r0 + arow;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tidx4[i] = (r0 + arow + 32 * i < a.rows_per_sample) ? __ldg(p + 32 * i) : -1;
+        }
         if (++ct.kc == nk) {                                    // cursor of chunk j + 1
           ct.kc = 0; ct.item += G;
           if (fast_adv) { ct.tis += G; if (ct.tis >= plan.tiles_per_sample) { ct.tis -= plan.tiles_per_sample; ++ct.b; } }
@@ -595,7 +609,31 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
           // nothing to transform.  The wait keeps this warp from running ahead of the ring (an arrival for the NEXT use
           // of a stage must not land in the phase of the current one); the data needs no fence, cp.async wrote it.
           mbar_wait(&bar_rfull[stage], (uint32_t)phase);
-          mbar_arrive(&bar_full[stage]);
+          if constexpr (TAILX) {
+            // the loaders passed this stage's empty barrier before arriving on rfull, so the stage is free: copy my four
+            // 16-byte pieces of the tail (one address form: base + sel * mul, sel < 0 -> zeros) and let the copies arrive
+            const int kofs = kc_cur * kTcBK;
+            const int t0 = kofs - a.k_pro + chunk * 4;
+            const bool is_g = t0 < a.t_split;
+            const int r0 = tis_cur * kTcTileM;
+            const int rows_valid = min(kTcTileM, a.rows_per_sample - r0);
+            const int nval = (kofs + chunk * 4 < a.K) ? (rows_valid - arow + 31) >> 5 : 0;
+            const float *base = a.T + t0;
+            if (!is_g) {
+              const size_t row = (size_t)b_cur * a.rows_per_sample + r0 + arow;
+              base = nval > 0 ? a.T2 + row * a.ldt2 + (t0 - a.t_split) : a.T2;
+            }
+            const int mul = is_g ? a.ldt : 32 * a.ldt2;
+            const uint32_t dst = smem_u32(s_stages + (size_t)stage * kStageBytes) + t_sw;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int sel = is_g ? tidx4[i] : (i < nval ? i : -1);
+              cp_async16_ignore(dst + i * 4096, base + (long long)max(sel, 0) * mul, sel < 0);
+            }
+            cp_async_arrive_noinc(&bar_full[stage]);
+          } else {
+            mbar_arrive(&bar_full[stage]);
+          }
           s4 = ns4; h4 = nh4; e4 = ne4;
           if (++stage == S) { stage = 0; phase ^= 1; }
           continue;
@@ -1277,6 +1315,16 @@ bool index_ring_enabled() {
   return mode == 1;
 }
 
+// PDR_GEMM_TAIL_X=1: raw K-tail chunks copied by the transform warps (TAILX instantiations; experiment)
+bool tail_by_transformers_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("PDR_GEMM_TAIL_X");
+    mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  return mode == 1;
+}
+
 bool epilogue_alternates_tiles() {
   static int mode = -1;
   if (mode < 0) {
@@ -1341,12 +1389,14 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     const int rc = make_c_tensor_map(a, &tmap);
     if (rc != 0) return rc;
   }
+  const bool tailx = vec == 3 && a.tail_rows != nullptr && tail_by_transformers_enabled();
   auto kern = gring      ? gemm_tf32_persistent<BN, WRES, 3, true>
+              : tailx    ? gemm_tf32_persistent<BN, WRES, 3, false, true>
               : vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
               : vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
                          : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
-  static bool configured[5] = {false, false, false, false, false};
-  const int cfg_slot = gring ? 4 : vec;
+  static bool configured[6] = {false, false, false, false, false, false};
+  const int cfg_slot = gring ? 4 : (tailx ? 5 : vec);
   if (!configured[cfg_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
