@@ -273,6 +273,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       const float *pa;           // &A[row_base + arow][chunk*4]
       const float *pr;           // same for the residual
       const float *pg[4];        // gathered A: &A[a_rows[row_base + arow + 32 i]][chunk*4], nullptr = zero row
+      int gs[4];                 // GRING: the table row itself (-1 = zero row), one address form in issue()
       const float *p2;           // gathered A: &A2[row_base + arow][chunk*4]
     };
     auto locate = [&](Cur &c) {  // full (division) geometry of c.item
@@ -339,9 +340,13 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       c.pr = a.R ? a.R + row * a.ldr + chunk * 4 : nullptr;
       if (gath) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          c.pg[i] = (cidx[i] >= 0 && (!GRING || arow + 32 * i < c.rows_valid)) ? a.A + (size_t)cidx[i] * a.lda + chunk * 4
-                                                                               : nullptr;
+        for (int i = 0; i < 4; ++i) {
+          if constexpr (GRING) {          // (the ring zero-fills the indices of rows beyond the sample: mask them here)
+            c.gs[i] = (cidx[i] >= 0 && arow + 32 * i < c.rows_valid) ? cidx[i] : -1;
+          } else {
+            c.pg[i] = cidx[i] >= 0 ? a.A + (size_t)cidx[i] * a.lda + chunk * 4 : nullptr;
+          }
+        }
         c.p2 = a.A2 + row * a.lda2 + chunk * 4;
       }
     };
@@ -395,7 +400,19 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         // are what the producer warps spend their issue slots on
         // (K tail: this thread's 16-byte piece is either wholly inside K or wholly zero-filled)
         const int ksz = kin ? 16 : 0;
-        if (gath) {
+        if (GRING && gath) {
+          // one address form for the gathered and the geometric part (src = base + sel * mul, sel < 0 -> zeros), so that a
+          // warp whose lanes straddle k_split does not run the two branches below one after the other
+          const bool is_g = kofs + chunk * 4 < a.k_split;
+          const int nval = kin ? (c.rows_valid - arow + 31) >> 5 : 0;
+          const float *base = is_g ? a.A + chunk * 4 + kofs : (nval > 0 ? c.p2 + (kofs - a.k_split) : a.A2);
+          const int mul = is_g ? a.lda : 32 * a.lda2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int sel = is_g ? c.gs[i] : (i < nval ? i : -1);
+            cp_async16_ignore(sa + i * 4096, base + (long long)max(sel, 0) * mul, sel < 0);
+          }
+        } else if (gath) {
           if (kofs + chunk * 4 < a.k_split) {          // feature part: one table row per grouped row
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
