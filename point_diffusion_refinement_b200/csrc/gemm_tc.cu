@@ -162,6 +162,88 @@ struct TcPlan {
   int prod_sleep_ns;    // > 0: producers / loaders sleep this long between polls of an EMPTY-stage barrier
 };
 
+// GNF (experiment, opt-in through PdrGemmArgs.gn_fused; TMA-store epilogue only): the GroupNorm finalisation that would
+// follow this GEMM as its own launch (pdr_gn_finalize, 98 per step, 6-8 us each of launch + latency) is done by the epilogue
+// group that completes the last tile of a sample.  NOT yet run on a GPU.
+struct GnFused {
+  PdrGnArgs gn;
+  int *counters;            // (batch) completed items per sample; zero outside a launch
+  int items_per_sample;     // tiles_per_sample * n_tiles_n
+};
+
+// One sample's finalisation by the T threads (T = 128 or 256, a power of two) that share named barrier `bar_id`:
+// the same reduction as gn_finalize_kernel (net.cu) for all groups at once -- per-tile partials added in a fixed order,
+// in double -- with L2 loads (the partials were written by other CTAs of this launch).
+// s_red: T x 2 doubles, s_tot: channels x 3 doubles.
+__device__ void gn_finalize_sample(const PdrGnArgs &g, int b, double *s_red, double *s_tot, int tid, int T, int bar_id) {
+  const int cpg = g.gn_channels / g.groups;
+  int src_off = 0;
+  for (int s = 0; s < g.nsrc; ++s) {
+    const PdrGnSource &src = g.src[s];
+    const int v_lo = src_off, v_hi = min(g.gn_channels, src_off + src.ncols);
+    for (int v0 = v_lo; v0 < v_hi; v0 += T) {
+      const int ncs = min(T, v_hi - v0);
+      int cw = 1;
+      while (cw < ncs) cw <<= 1;
+      const int nsl = T / cw;
+      const int cl = tid & (cw - 1), slice = tid / cw;
+      double sum = 0.0, sq = 0.0;
+      if (cl < ncs) {
+        const float *p = src.stats + ((size_t)b * src.tiles_per_sample * src.ld_stats + src.col0 + (v0 + cl - src_off)) * 4 +
+                         (src.use_relu ? 2 : 0);
+        const size_t tstride = (size_t)src.ld_stats * 4;
+        int t = slice;
+        for (; t + 7 * nsl < src.tiles_per_sample; t += 8 * nsl) {
+          float2 q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) q[u] = __ldcg(reinterpret_cast<const float2 *>(p + (size_t)(t + u * nsl) * tstride));
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { sum += (double)q[u].x; sq += (double)q[u].y; }
+        }
+        for (; t < src.tiles_per_sample; t += nsl) {
+          const float2 q = __ldcg(reinterpret_cast<const float2 *>(p + (size_t)t * tstride));
+          sum += (double)q.x;
+          sq += (double)q.y;
+        }
+      }
+      s_red[tid * 2 + 0] = sum;
+      s_red[tid * 2 + 1] = sq;
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
+      if (tid < ncs) {
+        double ts = 0.0, tq = 0.0;
+        for (int w = 0; w < nsl; ++w) { ts += s_red[(w * cw + tid) * 2 + 0]; tq += s_red[(w * cw + tid) * 2 + 1]; }
+        s_tot[(v0 + tid) * 3 + 0] = (double)src.mult * ts;
+        s_tot[(v0 + tid) * 3 + 1] = (double)src.mult * tq;
+        s_tot[(v0 + tid) * 3 + 2] = (double)src.mult * (double)src.rows;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
+    }
+    src_off += src.ncols;
+  }
+  for (int c = tid; c < g.channels; c += T) {
+    float sc = 1.f, sh = 0.f;      // MyGroupNorm passes the trailing C % G channels through (attention.py:17-23)
+    if (c < g.gn_channels) {
+      const int grp = c / cpg;
+      double sum = 0.0, sq = 0.0, n = 0.0;
+      for (int cc = grp * cpg; cc < (grp + 1) * cpg; ++cc) {
+        sum += s_tot[cc * 3 + 0]; sq += s_tot[cc * 3 + 1]; n += s_tot[cc * 3 + 2];
+      }
+      const double mean = sum / n;
+      double var = sq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double rstd = 1.0 / sqrt(var + (double)g.eps);
+      const double gsc = (double)__ldg(g.gamma + c) * rstd;
+      sc = (float)gsc;
+      sh = (float)((double)__ldg(g.beta + c) - mean * gsc);
+    }
+    int s = 0, off = 0;
+    while (s + 1 < g.nsrc && c >= off + g.src[s].ncols) { off += g.src[s].ncols; ++s; }
+    const int o = g.src[s].out_col0 + (c - off);
+    g.sc[(size_t)b * g.ld_out + o] = sc;
+    g.sh[(size_t)b * g.ld_out + o] = sh;
+  }
+}
+
 // bytes of the TMA-store staging tiles (EPI 3): two 32 x 32 fp32 boxes per epilogue warp
 constexpr int kTmaStageBytes = kEpiWarps * 2 * 4096;
 
@@ -178,9 +260,10 @@ constexpr int kRingD = 4;
 // TAILX (experiment, opt-in through PDR_GEMM_TAIL_X=1; raw gathered K tail only): the tail chunks are copied by the 8 transform
 // warps, which have nothing to transform there (4 rows per thread, same address form), instead of by the 2 loader warps
 // (16 rows per thread), which the role analysis shows saturated on the folded-residual GEMMs.  NOT yet run on a GPU.
-template <int BN, bool WRES, int EPI, bool GRING = false, bool TAILX = false>
+template <int BN, bool WRES, int EPI, bool GRING = false, bool TAILX = false, bool GNF = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c) {
+gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c,
+                     const __grid_constant__ GnFused gnf) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kWLoads = BN * 8 / kProdThreads;        // float4 of W per producer thread per chunk
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -191,6 +274,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   __shared__ uint32_t s_tmem_base;
   __shared__ int s_iring[GRING ? kProdWarps : 1][kRingD][16];            // GRING: 16 indices per producer warp and item
   __shared__ uint64_t bar_iring[GRING ? kProdWarps : 1][kRingD];
+  __shared__ int s_gn_last[2];                                           // GNF: this group completed a sample
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
   // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
@@ -1240,6 +1324,26 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         }
         if constexpr (kPartDB) part_parity ^= 1u;
         else asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
+        if constexpr (GNF) {
+          // fused GroupNorm finalisation: publish this item's partials, count it, and if it was the sample's last one
+          // let this group (128 threads, or all 256 when the groups share tiles) finalise the sample
+          __threadfence();
+          asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
+          const int gslot = alt ? half : 0;
+          if (stat_tid == 0) s_gn_last[gslot] = atomicAdd(gnf.counters + b, 1) == gnf.items_per_sample - 1;
+          asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
+          if (s_gn_last[gslot]) {
+            // scratch = this group's TMA staging tiles (32 KiB per group): their bulk stores must have read them
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __threadfence();
+            asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
+            double *scr = reinterpret_cast<double *>(s_stages + (size_t)plan.stages * kStageBytes + kPartRegion +
+                                                     (size_t)gslot * (kTmaStageBytes / 2));
+            gn_finalize_sample(gnf.gn, b, scr, scr + 2 * stat_threads, stat_tid, stat_threads, stat_bar);
+            if (stat_tid == 0) gnf.counters[b] = 0;              // ready for the next launch / graph replay
+            asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
+          }
+        }
       }
       if (alt) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1407,13 +1511,33 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     if (rc != 0) return rc;
   }
   const bool tailx = vec == 3 && a.tail_rows != nullptr && tail_by_transformers_enabled();
+  // fused GroupNorm finalisation (GNF): its own instantiation, and only where none of the other experiments applies
+  GnFused gnf;
+  memset(&gnf, 0, sizeof(gnf));
+  const bool use_gnf = a.gn_fused != nullptr;
+  if (use_gnf) {
+    const PdrGnArgs &g = *a.gn_fused;
+    const bool ok = vec == 3 && !gring && !tailx && a.stats && a.gn_counters && g.nsrc >= 1 && g.nsrc <= 2 &&
+                    g.src[g.nsrc - 1].stats == a.stats && g.src[g.nsrc - 1].tiles_per_sample == plan.tiles_per_sample &&
+                    g.src[g.nsrc - 1].ld_stats == a.N && g.batch == a.batch && g.groups > 0 &&
+                    g.gn_channels % g.groups == 0 && g.gn_channels <= g.channels && g.gamma && g.beta && g.sc && g.sh &&
+                    (size_t)g.channels * 24 + 4096 <= (size_t)kTmaStageBytes / 2;
+    if (!ok) {
+      set_error("gemm_tf32: gn_fused cannot be honoured for this call (flavour %d, channels %d)", vec, g.channels);
+      return PDR_ERR_UNSUPPORTED;
+    }
+    gnf.gn = g;
+    gnf.counters = a.gn_counters;
+    gnf.items_per_sample = plan.tiles_per_sample * plan.n_tiles_n;
+  }
   auto kern = gring      ? gemm_tf32_persistent<BN, WRES, 3, true>
               : tailx    ? gemm_tf32_persistent<BN, WRES, 3, false, true>
+              : use_gnf  ? gemm_tf32_persistent<BN, WRES, 3, false, false, true>
               : vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
               : vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
                          : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
-  static bool configured[6] = {false, false, false, false, false, false};
-  const int cfg_slot = gring ? 4 : (tailx ? 5 : vec);
+  static bool configured[7] = {false, false, false, false, false, false, false};
+  const int cfg_slot = gring ? 4 : (tailx ? 5 : (use_gnf ? 6 : vec));
   if (!configured[cfg_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
@@ -1421,7 +1545,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   }
   const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
   const int grid = plan.total_items < sm_cap ? plan.total_items : sm_cap;
-  kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap);
+  kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap, gnf);
   return check_launch("gemm_tf32_persistent");
 }
 

@@ -57,7 +57,8 @@ class GemmArgs(ctypes.Structure):
                 ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
                 ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
                 ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int),
-                ("max_ctas", ctypes.c_int)]
+                ("max_ctas", ctypes.c_int),
+                ("gn_fused", c_float_p), ("gn_counters", c_float_p)]
 
 
 class GnSource(ctypes.Structure):
@@ -81,6 +82,10 @@ _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
 # first encoder feature-mapper block, which only needs the level-0 ball query.  The GEMMs of that block leave
 # 148 - PDR_GEOM_OVERLAP_CTAS SMs free (PdrGemmArgs.max_ctas): their CTAs own a whole SM and would otherwise serialise
 # against the 32-CTA FPS kernel.
+# PDR_GEMM_GN_FUSED=1 (experiment, not yet run on a GPU): a pdr_gn_finalize call that directly follows the GEMM producing its
+# last source is folded into that GEMM (PdrGemmArgs.gn_fused: the epilogue group that completes a sample finalises it)
+# instead of being its own launch -- 6-8 us of launch + latency each, up to 98 times per step.
+_GN_FUSED = os.environ.get("PDR_GEMM_GN_FUSED", "0") == "1"
 _GEOM_OVERLAP = os.environ.get("PDR_GEOM_OVERLAP", "0") == "1"
 _GEOM_OVERLAP_CTAS = int(os.environ.get("PDR_GEOM_OVERLAP_CTAS", "116"))
 # PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
@@ -219,6 +224,8 @@ class FusedDenoiser:
         self._cta_limit = 0
         self._join_at = None
         self._side_stream = None
+        self._last_gemm = None      # GemmArgs of the op emitted last, if it was a GEMM (PDR_GEMM_GN_FUSED)
+        self._gn_counters = None
 
     # ------------------------------------------------------------------------------------------------
     # small helpers that append to the program
@@ -235,6 +242,7 @@ class FusedDenoiser:
         return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _emit(self, fn_name, *args, info=None):
+        self._last_gemm = None
         self._meta.append((fn_name, info or {}))
         fn = getattr(self.lib, fn_name)
         stream_of = self._stream
@@ -253,6 +261,7 @@ class FusedDenoiser:
             self.n_cond_kernel_calls += 1
 
     def _torch(self, fn):
+        self._last_gemm = None
         self._meta.append(("torch", {}))
         self._ops.append(fn)
         if self._emit_side and self._ops is self.ops:
@@ -340,6 +349,7 @@ class FusedDenoiser:
                       (M // rowadd_div * N if rowadd is not None else 0))
         self._emit("pdr_gemm_fused", ctypes.c_void_p(ctypes.addressof(g)),
                    info={"bytes": nbytes, "flops": 2 * M * N * K, "M": M, "N": N, "K": K})
+        self._last_gemm = g
         return st
 
     def gn(self, sources, gn_module, batch=None):
@@ -369,6 +379,17 @@ class FusedDenoiser:
         a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(gnm.eps)
         a.sc, a.sh, a.ld_out = sc.data_ptr(), sh.data_ptr(), ld_out
         self.keep += [a, gamma, beta]
+        host = sources[-1][0].g
+        if (_GN_FUSED and host is not None and host is self._last_gemm and host.use_tf32 and not host.pool_K
+                and not host.gn_fused and not (host.rowadd and host.rowadd_div < 8)
+                and channels * 24 + 4096 <= 32768):
+            # the GEMM that was just emitted produces the last source: it finalises (no launch of its own)
+            if self._gn_counters is None:
+                self._gn_counters = self._zeros(max(self.B, batch), dtype=torch.int32)
+            assert batch <= self._gn_counters.numel()
+            host.gn_fused = ctypes.addressof(a)
+            host.gn_counters = self._gn_counters.data_ptr()
+            return View(sc), View(sh)
         self._emit("pdr_gn_finalize", ctypes.c_void_p(ctypes.addressof(a)))
         return View(sc), View(sh)
 
