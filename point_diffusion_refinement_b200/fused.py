@@ -382,6 +382,8 @@ class FusedDenoiser:
         host = sources[-1][0].g
         if (_GN_FUSED and host is not None and host is self._last_gemm and host.use_tf32 and not host.pool_K
                 and not host.gn_fused and not (host.rowadd and host.rowadd_div < 8)
+                and not (host.a_rows and os.environ.get("PDR_GEMM_IDX_RING") == "1")      # those experiments have their
+                and not (host.tail_rows and os.environ.get("PDR_GEMM_TAIL_X") == "1")     # own kernel instantiations
                 and channels * 24 + 4096 <= 32768):
             # the GEMM that was just emitted produces the last source: it finalises (no launch of its own)
             if self._gn_counters is None:
