@@ -2,10 +2,10 @@
 # First GPU visit of the next round: A/B of the four opt-in experiments prepared at the end of round 1 (none of them has
 # run on a GPU yet -- each gets the GEMM / model parity tests under its switch first, under a hard timeout, and its
 # bench arm only if they pass).  ~5 minutes of box time.
-#   PDR_GEMM_IDX_RING=1   gathered-A indices through a per-warp shared-memory ring (gemm_tc.cu, GRING)
-#   PDR_GEMM_TAIL_X=1     raw K-tail chunks copied by the transform warps (gemm_tc.cu, TAILX)
+#   PDR_GEMM_IDX_RING=1   gathered-A indices through a per-warp shared-memory ring (gemm_tc.cuh, GRING)
+#   PDR_GEMM_TAIL_X=1     raw K-tail chunks copied by the transform warps (gemm_tc.cuh, TAILX)
 #   PDR_GEOM_OVERLAP=1    geometry chain on a side stream next to the first mapper block (fused.py, PdrGemmArgs.max_ctas)
-#   PDR_GEMM_GN_FUSED=1   pdr_gn_finalize folded into the GEMM that produces its last source (gemm_tc.cu GNF, PdrGemmArgs.gn_fused)
+#   PDR_GEMM_GN_FUSED=1   pdr_gn_finalize folded into the GEMM that produces its last source (gemm_tc.cuh GNF, PdrGemmArgs.gn_fused)
 tag=${1:-r02ab}
 out=gpurun_out/$tag
 mkdir -p $out
