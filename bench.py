@@ -57,8 +57,11 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-eval-kernels", action="store_true", help="skip the Chamfer / EMD Mpairs/s lines (configs[3])")
-    p.add_argument("--fast-ddpm", action="store_true",
-                   help="also run configs[4]: FastDPM 50-step VAR chain vs the full T=1000 chain (adds ~15 s)")
+    p.add_argument("--no-fast-ddpm", action="store_true",
+                   help="skip configs[4]: FastDPM 50-step VAR chain at B=128/GPU (+ on rank 0 its CD against T=1000 chains)")
+    p.add_argument("--no-gpu-reference", action="store_true",
+                   help="skip the `gpu_reference` leg (reference CUDA kernels + cuDNN module path) and the fp32-SIMT leg")
+    p.add_argument("--no-strong", action="store_true", help="skip the strong-scaling line (32 shapes total) at N > 1")
     p.add_argument("--profiler-range", action="store_true",
                    help="bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     return p.parse_args()
@@ -326,40 +329,144 @@ def geometry_kernel_lines(dev, sm_mhz):
     return out
 
 
-def fast_ddpm_lines(net, dev, B, dh, cond, label, rank):
-    """BASELINE configs[4]: fast_sampling_function_v2(length=50, 'var', 'quadratic', kappa=0.5) (README.md:95) against
-    the full T=1000 chain for the same condition clouds and network: shapes/s of each and cd_t between the outputs,
-    with the cd_t between two T=1000 seeds as the noise floor of a random-init network."""
+def fast_ddpm_lines(net, dev, B, dh, cond, label, rank, world, with_cd):
+    """BASELINE configs[4]: fast_sampling_function_v2(length=50, 'var', 'quadratic', kappa=0.5) (README.md:95).
+    Throughput: 128 shapes per GPU (the configuration's batch), every rank, max over ranks.  Quality (rank 0, the bench
+    batch): cd_t between the 50-step output and a full T=1000 chain for the same condition clouds, with the cd_t between
+    two T=1000 seeds as the noise floor of a random-init network."""
+    import contextlib
+    import io
+    import torch.distributed as dist
     from point_diffusion_refinement_b200 import util, util_fastdpmv2
     from point_diffusion_refinement_b200.chamfer_loss_new import Chamfer_F1
-    import contextlib, io
-    size = (B, N_POINTS, 3)
     dcfg = {"T": T_CHAIN, "beta_0": 1e-4, "beta_T": 0.02}
 
     def timed(fn):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with contextlib.redirect_stdout(io.StringIO()):
             e0.record(); r = fn(); e1.record()
         torch.cuda.synchronize()
-        return r, e0.elapsed_time(e1) / 1e3
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return r, ms.item() / 1e3
 
-    fast = lambda seed: util_fastdpmv2.fast_sampling_function_v2(
-        net, size, dh, dcfg, length=50, sampling_method="var", schedule="quadratic", kappa=0.5, print_every_n_steps=0,
-        label=label, verbose=False, condition=cond, seed=seed)
-    full = lambda seed: util.sampling(net, size, dh, print_every_n_steps=0, label=label, verbose=False, condition=cond,
-                                      seed=seed)
-    fast(0)                                                     # warm-up of the schedule / API path
-    xf, t_fast = timed(lambda: fast(1 + rank))
-    x1, t_full = timed(lambda: full(1 + rank))
-    x2, _ = timed(lambda: full(1001 + rank))
-    cf = Chamfer_F1()
-    cd = lambda a, b: float(cf(a / 2, b / 2)[1].mean().item())
-    return {"fast50_var_quadratic_kappa0.5": {"seconds": t_fast, "shapes_per_s_per_gpu": B / t_fast, "net_calls": 50},
-            "ddpm_T1000": {"seconds": t_full, "shapes_per_s_per_gpu": B / t_full, "net_calls": 1000},
-            "cd_t_fast_vs_T1000": cd(xf, x1), "cd_t_T1000_seed_vs_seed": cd(x1, x2), "batch_per_gpu": B,
-            "note": "random-init network: the CD values only show that the 50-step chain lands as close to a T=1000 "
-                    "sample as another T=1000 sample does"}
+    def fast(c, l, seed):
+        return util_fastdpmv2.fast_sampling_function_v2(
+            net, (c.shape[0], N_POINTS, 3), dh, dcfg, length=50, sampling_method="var", schedule="quadratic", kappa=0.5,
+            print_every_n_steps=0, label=l, verbose=False, condition=c, seed=seed, noise_stream=rank)
+
+    B5 = 128
+    cond5, label5, _ = make_inputs(B5, seed=500 + rank)
+    cond5, label5 = cond5.to(dev), label5.to(dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fast(cond5, label5, 0)                                  # compiles the B=128 programs, warms the API path
+    _, t_fast = timed(lambda: fast(cond5, label5, 1))
+    out = {"fast50_var_quadratic_kappa0.5": {"batch_per_gpu": B5, "seconds": t_fast, "net_calls": 50,
+                                             "shapes_per_s": world * B5 / t_fast, "n_gpus": world,
+                                             "ms_per_net_call": t_fast * 1e3 / 50}}
+    del cond5, label5
+    net._fused_engine = None                                    # drop the B=128 buffers
+    if with_cd:
+        size = (B, N_POINTS, 3)
+        full = lambda seed: util.sampling(net, size, dh, print_every_n_steps=0, label=label, verbose=False,
+                                          condition=cond, seed=seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            xf = fast(cond, label, 1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter(); x1 = full(1); torch.cuda.synchronize(); t_full = time.perf_counter() - t0
+            x2 = full(1001)
+        cf = Chamfer_F1()
+        cd = lambda a, b: float(cf(a / 2, b / 2)[1].mean().item())
+        out.update({"ddpm_T1000": {"batch_per_gpu": B, "seconds": t_full, "shapes_per_s_per_gpu": B / t_full,
+                                   "net_calls": 1000},
+                    "cd_t_fast_vs_T1000": cd(xf, x1), "cd_t_T1000_seed_vs_seed": cd(x1, x2),
+                    "note": "random-init network: the CD values only show that the 50-step chain lands as close to a "
+                            "T=1000 sample as another T=1000 sample does"})
+    return out
+
+
+def timed_steps(step_fn, steps, warmup, dev, world):
+    """`steps` calls of step_fn timed with CUDA events, barrier + device sync on both sides, max over ranks -> ms/step."""
+    import torch.distributed as dist
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(warmup):
+        step_fn()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item() / steps
+
+
+def baseline_legs(net, dev, B, dh, cond, label, xT_h, steps):
+    """N = 1 only.  (1) `fp32_simt`: the same compiled step with fp32 SIMT GEMMs instead of TF32 tensor cores (the
+    fp32-faithful number).  (2) `gpu_reference`: the reference's DESIGN on this box -- per-layer torch modules (cuDNN 1x1
+    convolutions, ATen GroupNorm) with the grouping / sampling entry points bound to the reference's own CUDA kernels
+    recompiled for sm_100a (oracle/_ref/libpdr_ref_cuda.so; pointnet2_with_pcld_condition.py:276-476 via util.py:224-249);
+    TF32 convolutions as PyTorch defaults to on this GPU.  Baselines, not the product path."""
+    from point_diffusion_refinement_b200 import util
+    out = {}
+    rng = util.DeviceNoise(seed=77)
+    Alpha = dh["Alpha"].numpy(); Abar = dh["Alpha_bar"].numpy(); Sigma = dh["Sigma"].numpy()
+    ts = torch.empty((B,), dtype=torch.float32, device=dev)
+    x = xT_h.to(dev)
+    state = {"t": T_CHAIN - 1}
+
+    def one_step():
+        t = state["t"]; state["t"] -= 1
+        ts.fill_(float(t))
+        eps = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+        inv = 1.0 / float(Alpha[t]) ** 0.5
+        c = (1.0 - float(Alpha[t])) / (1.0 - float(Abar[t])) ** 0.5
+        rng.affine_update(x, eps.contiguous(), inv, -c * inv, float(Sigma[t]))
+
+    net.reset_cond_features()
+    net.enable_fused(True, use_tf32=False, use_graph=True, fuse_cold=True)
+    one_step()                                                   # cold
+    out["fp32_simt"] = {"ms_per_step": timed_steps(one_step, steps, 3, dev, 1), "steps": steps,
+                        "engine": "fused program, fp32 SIMT GEMMs (use_tf32=False)"}
+    out["fp32_simt"]["shapes_per_s"] = B / (T_CHAIN * out["fp32_simt"]["ms_per_step"] / 1e3)
+    net.reset_cond_features()
+    net.enable_fused(False)
+    try:
+        from oracle import ref_cuda
+        from tests import common as C
+        if not ref_cuda.available():
+            raise RuntimeError("oracle/_ref/libpdr_ref_cuda.so not present")
+        old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cudnn.allow_tf32 = True
+        x.copy_(xT_h); state["t"] = T_CHAIN - 1
+        try:
+            with C.package_bound_to_reference_cuda():
+                one_step()                                       # cold: encodes the condition cloud
+                ms = timed_steps(one_step, steps, 2, dev, 1)
+        finally:
+            torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        out["gpu_reference"] = {"ms_per_step": ms, "shapes_per_s": B / (T_CHAIN * ms / 1e3), "steps": steps, "kind": "reference-design",
+                                "what": "per-layer torch modules (cuDNN convs, TF32 allowed as by PyTorch default) + the reference's own "
+                                        "pointnet2_ops CUDA kernels recompiled for sm_100a (oracle/_ref); kNN on our kernel "
+                                        "(pytorch3d is not vendored by the reference)"}
+    except Exception as exc:       # the .so is built where /root/reference exists and travels with the snapshot
+        out["gpu_reference"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+    net.reset_cond_features()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -481,14 +588,16 @@ def _main(args, json_out):
         e2e = None
         if not args.no_e2e:
             Ke = min(args.e2e_steps, T_CHAIN - 1)
-            out_h = torch.empty((B, N_POINTS, 3), dtype=torch.float32).pin_memory()
+            out_h = torch.empty((world * B, N_POINTS, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
 
             def chain():
                 c = cond_h.to(dev, non_blocking=True); l = label_h.to(dev, non_blocking=True)
                 xT = xT_h.to(dev, non_blocking=True)
                 r = util.sampling(net, (B, N_POINTS, 3), dh, label=l, condition=c, verbose=False,
-                                  print_every_n_steps=0, use_a_precomputed_XT=True, step=Ke, XT=xT, seed=rank)
-                out_h.copy_(r, non_blocking=True)
+                                  print_every_n_steps=0, use_a_precomputed_XT=True, step=Ke, XT=xT, seed=7, noise_stream=rank)
+                r = pdist.all_gather_shapes(r)                 # the one collective of the path (final gather), timed
+                if rank == 0:
+                    out_h.copy_(r, non_blocking=True)          # the whole job's clouds land on the host of rank 0
                 return r
 
             import contextlib, io
@@ -502,19 +611,56 @@ def _main(args, json_out):
             ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev)
             if world > 1:
                 dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-                _ = pdist.all_gather_shapes(r)        # the one collective of the path (final gather)
             chain_s = ems.item() / 1e3
-            h2d = cond_h.numel() * 4 + label_h.numel() * 8 + xT_h.numel() * 4
+            h2d = world * (cond_h.numel() * 4 + label_h.numel() * 8 + xT_h.numel() * 4)
             e2e = {"value": world * B / (chain_s * T_CHAIN / Ke), "unit": "shapes/s",
-                   "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": out_h.numel() * 4 / Ke,
-                   "chain_steps": Ke, "chain_ms": chain_s * 1e3,
-                   "note": "util.sampling(use_a_precomputed_XT, step=%d): %d reverse steps incl. the cold one, "
-                           "pinned-host condition/label/x_T in, generated cloud out; scaled by T/steps" % (Ke, Ke)}
+                   "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": world * B * N_POINTS * 3 * 4 / Ke,
+                   "chain_steps": Ke, "chain_ms": chain_s * 1e3, "cold_steps_in_chain": 1,
+                   "note": "util.sampling(use_a_precomputed_XT, step=%d): %d reverse steps incl. the cold one (= %.1f warm "
+                           "steps), pinned-host condition/label/x_T in, NCCL all_gather of the clouds + D2H of the whole "
+                           "job's result on rank 0 inside the timed region; scaled by T/steps (which charges the cold step "
+                           "and the gather %dx per chain)" % (Ke, Ke, cold_ms / ms_per_step, T_CHAIN // Ke)}
 
-    fast_ddpm = None
-    if args.fast_ddpm:
+    # ---- strong scaling (SURVEY 8d cfg 3, secondary line): 32 shapes in total, 32 / N per GPU ---------------------
+    strong = None
+    if world > 1 and not args.no_strong and args.engine == "fused" and 32 % world == 0:
         with torch.no_grad():
-            fast_ddpm = fast_ddpm_lines(net, dev, B, dh, cond, label, rank)
+            Bs = 32 // world
+            cond_s, label_s, x_s = [v.to(dev) for v in make_inputs(Bs, seed=300 + rank)]
+            ts_s = torch.empty((Bs,), dtype=torch.float32, device=dev)
+            st = {"t": T_CHAIN - 1}
+
+            def strong_step():
+                tt = st["t"]; st["t"] -= 1
+                ts_s.fill_(float(tt))
+                eps = net(x_s, cond_s, ts=ts_s, label=label_s, use_retained_condition_feature=True)
+                inv = 1.0 / float(Alpha[tt]) ** 0.5
+                c = (1.0 - float(Alpha[tt])) / (1.0 - float(Abar[tt])) ** 0.5
+                rng.affine_update(x_s, eps.contiguous(), inv, -c * inv, float(Sigma[tt]))
+
+            net.reset_cond_features()
+            strong_step()                                           # cold; compiles the (32 / N)-shape programs
+            s_ms = timed_steps(strong_step, args.steps, max(args.warmup, 3), dev, world)
+            eng_s = getattr(net, "_fused_engine", None)
+            per_kernel = None
+            if eng_s is not None and rank == 0:
+                agg_s = eng_s.profile(); agg_s.pop("torch", None)
+                per_kernel = {k: round(v["ms"], 4) for k, v in sorted(agg_s.items(), key=lambda kv: -kv[1]["ms"])}
+            net.reset_cond_features()
+            strong = {"scaling": "strong", "batch_total": 32, "batch_per_gpu": Bs, "n_gpus": world, "ms_per_step": s_ms,
+                      "shapes_per_s": 32 / (T_CHAIN * s_ms / 1e3), "per_kernel_ms_eager": per_kernel,
+                      "note": "same step, total work fixed at the N=1 batch; compare shapes_per_s with the N=1 `value`. "
+                              "Limiter at small per-GPU batch: FPS (one CTA per cloud, time independent of B) and the "
+                              "launch-latency-bound graph nodes of the deep levels"}
+    fast_ddpm = None
+    if not args.no_fast_ddpm and args.engine == "fused":
+        with torch.no_grad():
+            fast_ddpm = fast_ddpm_lines(net, dev, B, dh, cond, label, rank, world, with_cd=(rank == 0 and world == 1))
+            net.enable_fused(True, use_tf32=tf32, use_graph=not args.no_graph, fuse_cold=fuse_cold)
+    legs = None
+    if world == 1 and not args.no_gpu_reference and args.engine == "fused":
+        with torch.no_grad():
+            legs = baseline_legs(net, dev, B, dh, cond, label, xT_h, steps=5)
     eval_kernels = geometry_kernels = None
     if rank == 0 and not args.no_eval_kernels:
         with torch.no_grad():
@@ -573,8 +719,11 @@ def _main(args, json_out):
                    "parallelism": "dp%d: shapes sharded by rank, no collective inside the chain, one final all_gather" % world},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clock_info, "e2e": e2e,
         "gpu_launches": launches, "eval_kernels": eval_kernels, "geometry_kernels": geometry_kernels,
-        "fast_ddpm": fast_ddpm,
+        "fast_ddpm": fast_ddpm, "strong_scaling": strong,
+        "fp32_simt": (legs or {}).get("fp32_simt"), "gpu_reference": (legs or {}).get("gpu_reference"),
     }
+    if legs and legs.get("gpu_reference", {}).get("ms_per_step"):
+        line["gpu_reference"]["ours_over_reference_design"] = legs["gpu_reference"]["ms_per_step"] / ms_per_step
     print(json.dumps(line), flush=True, file=JSON_OUT[0])
     if world > 1:
         dist.destroy_process_group()

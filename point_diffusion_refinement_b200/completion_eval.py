@@ -46,8 +46,10 @@ def generate_batch(net, data, diffusion_hyperparams, task="completion", refine_o
                    use_a_precomputed_XT=False, T_step=100, point_upsample_factor=1,
                    include_displacement_center_to_final_output=False, noise_magnitude_added_to_gt=0.01,
                    add_noise_to_generated_for_refine_exp=False, fast_sampling=False, fast_sampling_config=None,
-                   diffusion_config=None, print_every_n_steps=200, num_points=None, seed=None):
-    """One batch of completion_eval.py:130-199 -> (generated (B,n,3) in network units, result_slices or None)."""
+                   diffusion_config=None, print_every_n_steps=200, num_points=None, seed=None, noise_stream=0):
+    """One batch of completion_eval.py:130-199 -> (generated (B,n,3) in network units, result_slices or None).
+    ``seed`` None draws from the advancing process-wide noise stream (util._default_rng); with a seed, ``noise_stream``
+    (batch index and rank, folded in by evaluate) keeps batches and ranks on different sub-streams."""
     dev = torch.device("cuda", torch.cuda.current_device())
     label = data["label"].to(dev)
     condition = data["partial"].to(dev)
@@ -78,15 +80,17 @@ def generate_batch(net, data, diffusion_hyperparams, task="completion", refine_o
                 out, result_slices = sampling(net, size, diffusion_hyperparams, print_every_n_steps=print_every_n_steps,
                                               label=label, condition=condition, verbose=False,
                                               return_multiple_t_slices=True, t_slices=list(t_slices),
-                                              use_a_precomputed_XT=use_a_precomputed_XT, step=T_step, XT=XT, seed=seed)
+                                              use_a_precomputed_XT=use_a_precomputed_XT, step=T_step, XT=XT, seed=seed,
+                                              noise_stream=noise_stream)
             elif fast_sampling:
                 out = fast_sampling_function_v2(net, size, diffusion_hyperparams, diffusion_config,
                                                 print_every_n_steps=print_every_n_steps, label=label, verbose=False,
-                                                condition=condition, **(fast_sampling_config or {}))
+                                                condition=condition, seed=seed, noise_stream=noise_stream,
+                                                **(fast_sampling_config or {}))
             else:
                 out = sampling(net, size, diffusion_hyperparams, print_every_n_steps=print_every_n_steps, label=label,
                                condition=condition, verbose=False, use_a_precomputed_XT=use_a_precomputed_XT,
-                               step=T_step, XT=XT, seed=seed)
+                               step=T_step, XT=XT, seed=seed, noise_stream=noise_stream)
     return out, gt, label, result_slices
 
 
@@ -132,7 +136,8 @@ def evaluate(net, testloader, diffusion_hyperparams, print_every_n_steps=200, pa
             noise_magnitude_added_to_gt=noise_magnitude_added_to_gt,
             add_noise_to_generated_for_refine_exp=add_noise_to_generated_for_refine_exp, fast_sampling=fast_sampling,
             fast_sampling_config=fast_sampling_config, diffusion_config=diffusion_config,
-            print_every_n_steps=print_every_n_steps, num_points=num_points, seed=seed)
+            print_every_n_steps=print_every_n_steps, num_points=num_points, seed=seed,
+            noise_stream=1 + idx + total_len * pdist.rank())       # one noise sub-stream per (batch, rank)
         torch.cuda.synchronize()
         generation_time = time.time() - start
         total_time += generation_time
@@ -148,7 +153,7 @@ def evaluate(net, testloader, diffusion_hyperparams, print_every_n_steps=200, pa
                 v = result_slices[key]
                 if augment_data_during_generation:
                     v = torch.matmul(v - translation, M_inv)
-                result_slices[key] = (v / 2 / scale).detach().cpu().numpy()
+                result_slices[key] = (v / 2 / scale).detach()
         if compute_cd:                                                 # :217-227
             cd_p, dist, f1 = cd_module(generated_data, gt)
         else:
@@ -177,6 +182,8 @@ def evaluate(net, testloader, diffusion_hyperparams, print_every_n_steps=200, pa
         metrics = {k: pdist.all_gather_shapes(v) for k, v in metrics.items()}
         if save_generated_samples and kept:
             kept = [pdist.all_gather_shapes(torch.cat(kept, 0))]
+            # the T-slice clouds go through the same gather, so every *_T<t>.h5 holds as many rows as the main file
+            kept_slices = {t: [pdist.all_gather_shapes(torch.cat(parts, 0))] for t, parts in sorted(kept_slices.items())}
         rank = torch.distributed.get_rank()
         avg_cd = metrics["cd_distance"].mean().item() if metrics["cd_distance"].numel() else 0.0
         avg_emd = metrics["emd_distance"].mean().item() if metrics["emd_distance"].numel() else 0.0
@@ -190,7 +197,7 @@ def evaluate(net, testloader, diffusion_hyperparams, print_every_n_steps=200, pa
                                   torch.cat(kept, 0).detach().cpu().numpy())
         for t, parts in kept_slices.items():
             results_io.save_generated(os.path.join(save_dir, results_io.generated_file_name(dataset, n_pts, t)),
-                                      np.concatenate(parts, axis=0))
+                                      torch.cat(parts, 0).detach().cpu().numpy())
     total_meta = total_meta.detach().cpu().numpy()
     if return_all_metrics:
         return avg_cd, avg_emd, total_meta, metrics

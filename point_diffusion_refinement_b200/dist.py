@@ -12,6 +12,11 @@ import torch
 import torch.distributed as dist
 
 
+def rank():
+    """Rank in the default process group, 0 without one."""
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+
+
 def shard_range(total, rank, world_size):
     """Contiguous [start, stop) of `total` shapes owned by `rank`; the first `total % world` ranks get one
     extra shape."""

@@ -12,11 +12,13 @@ from . import emd_cuda
 class EarthMoverDistanceFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2, return_match=False):
+        # (asked of ctx, not of the tensors: inside forward grad mode is off, and .contiguous() of a non-contiguous
+        #  input -- transpose=True -- is a copy with requires_grad False)
+        need_match = return_match or ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         xyz1 = xyz1.contiguous()
         xyz2 = xyz2.contiguous()
         assert xyz1.is_cuda and xyz2.is_cuda, "Only support cuda currently."
         scale = max(xyz1.shape[1], xyz2.shape[1])
-        need_match = return_match or xyz1.requires_grad or xyz2.requires_grad
         if not need_match:
             return emd_cuda.emd_cost_forward(xyz1, xyz2) / scale
         match = emd_cuda.approxmatch_forward(xyz1, xyz2)

@@ -226,6 +226,7 @@ class FusedDenoiser:
         self._side_stream = None
         self._last_gemm = None      # GemmArgs of the op emitted last, if it was a GEMM (PDR_GEMM_GN_FUSED)
         self._gn_counters = None
+        self.weights_tag = None     # fingerprint of the parameters the packed copies were made from (set by the owner)
 
     # ------------------------------------------------------------------------------------------------
     # small helpers that append to the program
@@ -984,6 +985,10 @@ class FusedDenoiser:
                     acc = v if acc is None else acc + v
                 self.C_all[:, col:col + acc.shape[1]] = acc
                 col += acc.shape[1]
+
+    def set_label(self, global_feature, label):
+        """Class label of the NEXT steps (the condition-only embeddings are precomputed per label)."""
+        self._condition_embeddings(global_feature, label)
 
     def run_program(self):
         if self._join_at is None or not self.side_ops:

@@ -162,21 +162,49 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
         self._fused_engine = None
         return self
 
-    def _engine(self, B, N):
+    # The compiled programs hold packed COPIES of the weights (fused.py), so anything that replaces or moves the
+    # parameters drops them; the next fused call recompiles.  (In-place edits of parameter storage, e.g. an optimizer
+    # step, are caught through the version counters checked in _engine.)
+    def load_state_dict(self, *args, **kwargs):
+        self._fused_engine = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._fused_engine = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _weights_tag(self):
+        """Cheap fingerprint of the parameter storage: (version, address) of every parameter tensor, folded."""
+        tag = 0
+        for p in self.parameters():
+            tag = (tag * 1000003 + p._version * 8191 + p.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        return tag
+
+    def _engine(self, B, N, check_weights=True):
         from .fused import FusedDenoiser
         eng = getattr(self, "_fused_engine", None)
+        if eng is not None and check_weights and eng.weights_tag != self._weights_tag():
+            eng = None                                   # parameters were updated in place since the program was built
         if eng is None or (eng.B, eng.N) != (B, N):
             eng = FusedDenoiser(self, B, N, **self._fused_cfg)
+            eng.weights_tag = self._weights_tag()
             self._fused_engine = eng
             self._fused_bound = None
         return eng
 
-    def _fused_step(self, pointcloud, ts):
+    def _fused_step(self, pointcloud, ts, label=None):
         B, N, _ = pointcloud.shape
-        eng = self._engine(B, N)
+        # the fingerprint walk costs ~0.2 ms: done when a chain (re)binds its condition state, not on every step
+        rebind = self._fused_bound is not self._cond_state or getattr(self, "_fused_engine", None) is None
+        eng = self._engine(B, N, check_weights=rebind)
         if self._fused_bound is not self._cond_state:
             eng.set_condition(self._cond_state, self._cond_label)
             self._fused_bound = self._cond_state
+            self._fused_label = self._cond_label
+        if label is not None and label is not getattr(self, "_fused_label", None):
+            # the reference embeds the label passed to EACH call (pointnet2_with_pcld_condition.py:386-392)
+            eng.set_label(self._cond_state.global_feature, label)
+            self._fused_label = label
         return eng.step(pointcloud, ts)
 
     def _fused_cold(self, pointcloud, condition, ts, label, retain):
@@ -192,6 +220,7 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
         if retain:
             cs = eng.export_condition_state(global_feature.detach().clone())
             self._cond_state, self._cond_label, self._fused_bound = cs, label, cs
+        self._fused_label = label
         return eng.step(pointcloud, ts)
 
     # -- retained condition state -------------------------------------------------------------------
@@ -247,7 +276,7 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
             assert condition is not None
         if (use_retained_condition_feature and self._cond_state is not None
                 and getattr(self, "_fused_cfg", None) is not None and pointcloud.is_cuda and not torch.is_grad_enabled()):
-            return self._fused_step(pointcloud, ts).clone()
+            return self._fused_step(pointcloud, ts, label).clone()
         if (getattr(self, "_fuse_cold", False) and getattr(self, "_fused_cfg", None) is not None and pointcloud.is_cuda
                 and not torch.is_grad_enabled() and self.include_local_feature and self.include_global_feature):
             return self._fused_cold(pointcloud, condition, ts, label, use_retained_condition_feature).clone()

@@ -51,10 +51,18 @@ def calc_diffusion_hyperparams(T, beta_0, beta_T):
 
 
 class DeviceNoise:
-    """Counter-based N(0,1) stream on the device (Philox4x32-10 + Box-Muller in libpdr_b200)."""
+    """Counter-based N(0,1) stream on the device (Philox4x32-10 + Box-Muller in libpdr_b200).
 
-    def __init__(self, seed=0):
-        self.seed = int(seed) & ((1 << 64) - 1)
+    ``stream`` selects an independent sub-stream of the same seed (it is folded into the Philox key through a
+    splitmix64 round), so that calls, batches and ranks that share a seed do not share noise."""
+
+    def __init__(self, seed=0, stream=0):
+        z = (int(seed) + 0x9E3779B97F4A7C15 * int(stream)) & ((1 << 64) - 1)
+        if stream:
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & ((1 << 64) - 1)
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & ((1 << 64) - 1)
+            z ^= z >> 31
+        self.seed = z
         self.offset = 0
 
     def _advance(self, count):
@@ -90,11 +98,27 @@ def std_normal(size, device="cuda", rng=None):
 _DEFAULT_RNG = None
 
 
+def _rank():
+    d = torch.distributed
+    return d.get_rank() if (d.is_available() and d.is_initialized()) else 0
+
+
 def _default_rng():
+    """The process-wide stream every unseeded draw comes from.  Like the reference's global CPU generator
+    (util.py:118-123) it ADVANCES between calls, so two unseeded sampling() calls -- two batches of an evaluation,
+    the trials of generate_samples.py --num_trials -- never see the same x_T / z_t; unlike it, ranks that were
+    seeded alike still draw from different sub-streams.  Re-created when torch.manual_seed changes the seed."""
     global _DEFAULT_RNG
-    if _DEFAULT_RNG is None:
-        _DEFAULT_RNG = DeviceNoise(seed=torch.initial_seed())
-    return _DEFAULT_RNG
+    key = (torch.initial_seed(), _rank())
+    if _DEFAULT_RNG is None or _DEFAULT_RNG[0] != key:
+        _DEFAULT_RNG = (key, DeviceNoise(seed=key[0], stream=key[1]))
+    return _DEFAULT_RNG[1]
+
+
+def chain_rng(seed, stream=0):
+    """Noise source of one sampling chain: the advancing process-wide stream when ``seed`` is None, otherwise the
+    reproducible stream (seed, stream)."""
+    return _default_rng() if seed is None else DeviceNoise(seed, stream=stream)
 
 
 def _host_schedule(_dh):
@@ -105,11 +129,13 @@ def _host_schedule(_dh):
 
 def sampling(net, size, diffusion_hyperparams, print_every_n_steps=100, label=0, verbose=True, condition=None,
              return_multiple_t_slices=False, t_slices=[5, 10, 20, 50, 100, 200, 400, 600, 800],
-             use_a_precomputed_XT=False, step=100, XT=None, noise=None, seed=None, device=None):
+             use_a_precomputed_XT=False, step=100, XT=None, noise=None, seed=None, device=None, noise_stream=0):
     """Ancestral sampling p(x_0|x_T) = prod_t p_theta(x_{t-1}|x_t).  reference util.py:184-255.
 
     Extra keyword arguments (not in the reference): ``noise`` -- callable ``(t, size) -> tensor`` (t = T for
-    the initial x_T) replaying a given noise sequence; ``seed`` -- Philox seed; ``device``.
+    the initial x_T) replaying a given noise sequence; ``seed`` -- Philox seed of a reproducible chain (None: the
+    process-wide stream, which keeps advancing from call to call like the reference's global generator);
+    ``noise_stream`` -- sub-stream of ``seed`` (callers fold the batch index and the rank into it); ``device``.
     """
     _dh = diffusion_hyperparams
     T = _dh["T"]
@@ -117,7 +143,7 @@ def sampling(net, size, diffusion_hyperparams, print_every_n_steps=100, label=0,
     assert len(Alpha) == T and len(Alpha_bar) == T and len(Sigma) == T and len(size) == 3
     if device is None:
         device = condition.device if condition is not None else torch.device("cuda", torch.cuda.current_device())
-    rng = DeviceNoise(torch.initial_seed() if seed is None else seed)
+    rng = chain_rng(seed, noise_stream)
     print("begin sampling, total number of reverse steps = %s" % T)
     result_slices = {}
 

@@ -8,7 +8,7 @@ log-Gamma approximation) is host-side numpy exactly as in the reference; the per
 import numpy as np
 import torch
 
-from .util import DeviceNoise, calc_diffusion_hyperparams  # noqa: F401
+from .util import DeviceNoise, calc_diffusion_hyperparams, chain_rng  # noqa: F401
 
 
 def bisearch(f, domain, target, eps=1e-8):
@@ -111,10 +111,10 @@ def _precompute_VAR_steps(diffusion_hyperparams, user_defined_eta):
     return steps
 
 
-def _run_chain(net, size, taus, coef_fn, label, verbose, condition, noise, seed, device):
+def _run_chain(net, size, taus, coef_fn, label, verbose, condition, noise, seed, device, noise_stream=0):
     if device is None:
         device = condition.device if condition is not None else torch.device("cuda", torch.cuda.current_device())
-    rng = DeviceNoise(torch.initial_seed() if seed is None else seed)
+    rng = chain_rng(seed, noise_stream)
     n_steps = len(taus)
     draw = (lambda i: noise(i, size).to(device=device, dtype=torch.float32)) if noise is not None else None
     x = (draw(-1) if draw else rng.normal(size, device)).contiguous()
@@ -154,7 +154,7 @@ def _ddim_coefficients(a_cur, a_next, kappa, last):
 
 def VAR_sampling(net, size, diffusion_hyperparams, user_defined_eta, kappa, continuous_steps,
                  print_every_n_steps=100, label=0, verbose=True, condition=None, noise=None, seed=None,
-                 device=None):
+                 device=None, noise_stream=0):
     """:307-381."""
     _dh = diffusion_hyperparams
     T = _dh["T"]
@@ -173,11 +173,12 @@ def VAR_sampling(net, size, diffusion_hyperparams, user_defined_eta, kappa, cont
         nxt = None if last else Gamma_bar[T_user - 1 - i - 1]
         return _ddim_coefficients(cur, nxt, kappa, last)
 
-    return _run_chain(net, size, list(continuous_steps), coef, label, verbose, condition, noise, seed, device)
+    return _run_chain(net, size, list(continuous_steps), coef, label, verbose, condition, noise, seed, device,
+                      noise_stream)
 
 
 def STEP_sampling(net, size, diffusion_hyperparams, user_defined_steps, kappa, print_every_n_steps=100, label=0,
-                  verbose=True, condition=None, noise=None, seed=None, device=None):
+                  verbose=True, condition=None, noise=None, seed=None, device=None, noise_stream=0):
     """:384-452."""
     _dh = diffusion_hyperparams
     T = _dh["T"]
@@ -193,17 +194,17 @@ def STEP_sampling(net, size, diffusion_hyperparams, user_defined_steps, kappa, p
         nxt = None if last else Alpha_bar[steps[i + 1]]
         return _ddim_coefficients(Alpha_bar[tau], nxt, kappa, last)
 
-    return _run_chain(net, size, steps, coef, label, verbose, condition, noise, seed, device)
+    return _run_chain(net, size, steps, coef, label, verbose, condition, noise, seed, device, noise_stream)
 
 
 def fast_sampling_function_v2(net, size, diffusion_hyperparams, diffusion_config, length=100, sampling_method="var",
                               schedule="quadratic", kappa=0.0, print_every_n_steps=100, label=0, verbose=True,
-                              condition=None, noise=None, seed=None, device=None):
+                              condition=None, noise=None, seed=None, device=None, noise_stream=0):
     """:455-476."""
     assert sampling_method in ["var", "step"]
     assert schedule in ["quadratic", "linear"]
     extra = dict(print_every_n_steps=print_every_n_steps, label=label, verbose=verbose, condition=condition,
-                 noise=noise, seed=seed, device=device)
+                 noise=noise, seed=seed, device=device, noise_stream=noise_stream)
     if sampling_method == "var":
         eta = get_VAR_noise(length, diffusion_config, schedule)
         taus = _precompute_VAR_steps(diffusion_hyperparams, eta)

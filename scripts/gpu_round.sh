@@ -12,7 +12,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o
 COLD=""
 if [ $rc -ne 0 ]; then COLD="--module-cold"; fi      # compiled cold path only when its parity tests are green
 ( timeout 300 python __graft_entry__.py smoke ) > $out/smoke.log 2>&1; echo "smoke exit $?" >> $out/smoke.log
-( timeout 900 python bench.py $COLD --fast-ddpm --dump-ops $out/ops.json ) > $out/bench.json 2> $out/bench.err
+( timeout 900 python bench.py $COLD --dump-ops $out/ops.json ) > $out/bench.json 2> $out/bench.err
 if [ -z "$SKIP_REF" ]; then
 ( timeout 300 python bench.py --impl reference --steps 2 --warmup 1 ) > $out/bench_reference.json 2> $out/bench_reference.err
 fi

@@ -43,6 +43,31 @@ def denoiser_inputs(B, N, M, seed=0):
     return x, cond, ts, label
 
 
+def stub_eps(x, ts=None, label=None, **_):
+    """The parameter-free eps_theta stand-in of tests/golden/make_golden.py::stub_net (same three lines)."""
+    t = ts.to(x.dtype).view(-1, 1, 1) / 1000.0
+    return 0.9 * x / torch.sqrt(1.001 - torch.exp(-(0.1 * t + 10.0 * t * t))) + 0.1 * torch.tanh(x + t)
+
+
+def run_fastdpm_case(case, size, device, record):
+    """Replay one case of tests/golden/fastdpm_loops.pt through the package's VAR_sampling / STEP_sampling with the
+    fixture's noise bank; `record` receives every x the loop hands to eps_theta."""
+    from point_diffusion_refinement_b200 import configs, util, util_fastdpmv2 as fast
+    dh = util.calc_diffusion_hyperparams(**configs.DIFFUSION_CONFIG)
+    bank = case["bank"]
+
+    def net(x, ts=None, label=None):
+        record.append(x.detach().cpu().clone())
+        return stub_eps(x, ts=ts)
+    kw = dict(label=None, verbose=False, condition=None, noise=lambda i, s: bank[i + 1], device=device)
+    if case["method"] == "var":
+        eta = fast.get_VAR_noise(case["length"], configs.DIFFUSION_CONFIG, case["schedule"])
+        taus = fast._precompute_VAR_steps(dh, eta)
+        return fast.VAR_sampling(net, size, dh, eta, case["kappa"], taus, **kw)
+    steps = fast.get_STEP_step(case["length"], configs.DIFFUSION_CONFIG, case["schedule"])
+    return fast.STEP_sampling(net, size, dh, steps, case["kappa"], **kw)
+
+
 def ssg_config():
     """Small unconditional PointNet2SemSegSSG with the three_nn / three_interpolate decoder
     (reference default, pointnet2_ssg_sem.py:213)."""
@@ -81,3 +106,25 @@ def package_bound_to_oracle():
     finally:
         for (mod, name), fn in saved.items():
             setattr(mod, name, fn)
+
+
+@contextlib.contextmanager
+def package_bound_to_reference_cuda():
+    """TESTS / bench.py's `gpu_reference` baseline leg ONLY: the package's per-layer module path with its native entry
+    points bound to the REFERENCE's own CUDA kernels recompiled for sm_100a (oracle/_ref/libpdr_ref_cuda.so) -- FPS, gather,
+    ball query, grouping, three_nn / three_interpolate -- i.e. the reference's design (pointnet2_ops kernels + cuDNN 1x1
+    convolutions + ATen GroupNorm, ~1000 launches per step) on this box.  pytorch3d's kNN is not vendored by the reference,
+    so kNN stays on the package's kernel."""
+    from oracle import ref_cuda as R
+    from point_diffusion_refinement_b200 import _ext
+    table = dict(furthest_point_sampling=R.furthest_point_sampling, gather_points=R.gather_points,
+                 ball_query=R.ball_query, group_points=R.group_points,
+                 three_nn=lambda u, k: list(R.three_nn(u, k)), three_interpolate=R.three_interpolate)
+    saved = {name: getattr(_ext, name) for name in table}
+    for name, fn in table.items():
+        setattr(_ext, name, fn)
+    try:
+        yield
+    finally:
+        for name, fn in saved.items():
+            setattr(_ext, name, fn)

@@ -7,7 +7,7 @@ Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 
 Outputs (small, committed): tests/golden/*.pt, tests/golden/state_dict_keys.json
-(`--only-refinement-io` regenerates refinement_io.pt alone.)
+(`--only-refinement-io` regenerates refinement_io.pt alone, `--only-fastdpm` fastdpm_loops.pt alone.)
 """
 import json
 import os
@@ -72,10 +72,69 @@ def refinement_io_fixtures():
     print("refinement_io.pt written")
 
 
+def stub_net(x, ts=None, label=None):
+    """Deterministic stand-in for eps_theta used by the FastDPM loop fixture: nonlinear in x and in the
+    (continuous) step, no parameters, roughly x / sqrt(1 - alpha_bar) so that the chain stays O(1).  tests/test_host_model.py and tests/test_model_gpu.py hold the same
+    three lines; the reference's own loop checker uses `lambda x, ts, label: x` (util_fastdpmv2.py:480)."""
+    t = ts.to(x.dtype).view(-1, 1, 1) / 1000.0
+    return 0.9 * x / torch.sqrt(1.001 - torch.exp(-(0.1 * t + 10.0 * t * t))) + 0.1 * torch.tanh(x + t)
+
+
+def fastdpm_fixtures():
+    """a14: the reference's VAR_sampling / STEP_sampling update loops (util_fastdpmv2.py:307-452) run from the
+    reference's own file with a stub eps_theta and an injected noise bank (its std_normal replaced by a
+    replay of pre-drawn tensors, its .cuda() calls made no-ops)."""
+    import pointnet2.util as ref_util
+    import pointnet2.util_fastdpmv2 as ref_fast
+    from point_diffusion_refinement_b200 import configs
+    dh = ref_util.calc_diffusion_hyperparams(**configs.DIFFUSION_CONFIG)
+    dh64 = dict(dh, Beta=dh["Beta"].double())       # float64 Stirling: see schedules.pt "taus_f64"
+    size = (3, 40, 3)
+    cases = []
+    real_cuda, real_normal = torch.Tensor.cuda, ref_fast.std_normal
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for method, schedule, length, kappa in (("var", "quadratic", 12, 0.5), ("var", "linear", 8, 0.0),
+                                                ("var", "quadratic", 50, 1.0), ("step", "quadratic", 12, 0.5),
+                                                ("step", "linear", 9, 0.2), ("step", "quadratic", 50, 0.0)):
+            g = torch.Generator().manual_seed(1000 + len(cases))
+            bank = [torch.randn(size, generator=g) for _ in range(length + 1)]   # [x_T, z of step 0, 1, ...]
+            drawn = []
+
+            def replay(sz):
+                assert tuple(sz) == size
+                drawn.append(len(drawn))
+                return bank[len(drawn) - 1].clone()
+            ref_fast.std_normal = replay
+            seen = []
+
+            def net(x, ts=None, label=None):
+                seen.append(x.clone())
+                return stub_net(x, ts=ts, label=label)
+            if method == "var":
+                eta = ref_fast.get_VAR_noise(length, configs.DIFFUSION_CONFIG, schedule)
+                taus = ref_fast._precompute_VAR_steps(dh64, eta)
+                x = ref_fast.VAR_sampling(net, size, dh, eta, kappa, taus, label=None, verbose=False)
+            else:
+                steps = ref_fast.get_STEP_step(length, configs.DIFFUSION_CONFIG, schedule)
+                x = ref_fast.STEP_sampling(net, size, dh, steps, kappa, label=None, verbose=False)
+            assert len(drawn) == length + 1     # the reference draws z every step, also when sigma == 0
+            cases.append({"method": method, "schedule": schedule, "length": length, "kappa": kappa,
+                          "bank": torch.stack(bank), "x_in": torch.stack(seen), "x0": x.clone()})
+            print("fastdpm", method, schedule, length, kappa, "x0 abs-mean %.4f" % x.abs().mean().item())
+    finally:
+        torch.Tensor.cuda, ref_fast.std_normal = real_cuda, real_normal
+    torch.save({"size": size, "cases": cases}, os.path.join(HERE, "fastdpm_loops.pt"))
+    print("fastdpm_loops.pt written")
+
+
 def main():
     bind_reference_to_oracle()
     if "--only-refinement-io" in sys.argv:
         refinement_io_fixtures()
+        return
+    if "--only-fastdpm" in sys.argv:
+        fastdpm_fixtures()
         return
     from pointnet2.models.pointnet2_with_pcld_condition import PointNet2CloudCondition as RefNet
     from pointnet2.models.pointnet2_ssg_sem import PointNet2SemSegSSG as RefSSG
@@ -165,6 +224,7 @@ def main():
     torch.save({"p1": p1, "p2": p2, "dist1": P.min(2)[0].float(), "dist2": P.min(1)[0].float(),
                 "idx1": P.min(2)[1].int(), "idx2": P.min(1)[1].int()}, os.path.join(HERE, "chamfer_f64.pt"))
     refinement_io_fixtures()
+    fastdpm_fixtures()
     print("golden fixtures written to", HERE)
 
 

@@ -86,6 +86,31 @@ def test_schedules_match_reference(golden_dir):
         assert all(a > b for a, b in zip(taus[:-1], taus[1:])) and abs(taus[-1]) < 0.1
 
 
+def test_fastdpm_loops_match_reference_python(golden_dir, monkeypatch):
+    """a14: VAR_sampling / STEP_sampling (reference util_fastdpmv2.py:307-452) step by step against the fixture the
+    reference's own loops produced with the same stub eps_theta and noise bank.  Host logic only: the fused device
+    update x*a + c*eps + sigma*z is replaced by the same expression in torch (the GPU twin of this test,
+    tests/test_model_gpu.py, runs the real kernel).  Tolerance: 2e-6 relative + 1e-6 absolute per step (fp32 ulp level: the reference
+    updates x in two rounded steps, x *= a; x += c*eps + sigma*z)."""
+    from point_diffusion_refinement_b200 import util
+    gold = torch.load(golden_dir + "/fastdpm_loops.pt")
+
+    def affine_update(self, x, eps, scale_x, scale_eps, sigma, noise=None):
+        x.mul_(scale_x).add_(eps, alpha=scale_eps)
+        if sigma != 0.0:
+            x.add_(noise.to(x.dtype), alpha=sigma)
+        return x
+    monkeypatch.setattr(util.DeviceNoise, "affine_update", affine_update)
+    size = tuple(gold["size"])
+    assert len(gold["cases"]) == 6
+    for case in gold["cases"]:
+        seen = []
+        x0 = C.run_fastdpm_case(case, size, torch.device("cpu"), seen)
+        assert len(seen) == case["length"] == case["x_in"].shape[0]
+        torch.testing.assert_close(torch.stack(seen), case["x_in"], rtol=2e-6, atol=1e-6)
+        torch.testing.assert_close(x0, case["x0"], rtol=2e-6, atol=1e-6)
+
+
 def test_ddim_coefficients_reduce_to_ddpm_limits():
     from point_diffusion_refinement_b200.util_fastdpmv2 import _ddim_coefficients
     sx, c, s = _ddim_coefficients(0.5, None, 0.7, last=True)       # last step: x0 = (x - sqrt(1-a) eps)/sqrt(a)

@@ -2,8 +2,9 @@
 (tests/golden/make_golden.py) -- indices are bit-exact functions of the coordinates, so the only
 deviation is floating-point accumulation order in the 1x1 convolutions / GroupNorm.
 
-Tolerances: eps_theta rtol = atol = 1e-4 with fp32 GEMMs; 2e-2 with TF32 GEMMs (10-bit mantissa through
-~12 GroupNorm-ed layers of random-init weights; measured max error 7e-3 on |eps| ~ 0.9)."""
+Tolerances: eps_theta rtol = atol = 1e-4 with fp32 GEMMs.  TF32 GEMMs (10-bit mantissa through ~12 GroupNorm-ed layers of
+random-init weights, |eps| ~ 0.9) are judged by the error DISTRIBUTION -- median / 99.9th percentile / maximum, see
+TF32_MEDIAN / TF32_P999 / TF32_MAX below and profiles/r02_tf32_error_report.txt -- plus a chain-level point-set check."""
 import pytest
 import torch
 
@@ -121,6 +122,18 @@ def test_fast_sampling_runs_var_and_step():
     assert torch.equal(a, b)
 
 
+def test_fastdpm_loops_match_reference_fixture(golden_dir):
+    """a14 on the device: the same replay as tests/test_host_model.py::test_fastdpm_loops_match_reference_python with the
+    real fused update kernel (pdr_affine_noise_update, injected z).  Same ulp-level tolerance (2e-6 relative + 1e-6 absolute)."""
+    gold = torch.load(golden_dir + "/fastdpm_loops.pt")
+    size = tuple(gold["size"])
+    for case in gold["cases"]:
+        seen = []
+        x0 = C.run_fastdpm_case(case, size, torch.device(DEV), seen)
+        torch.testing.assert_close(torch.stack(seen), case["x_in"], rtol=2e-6, atol=1e-6)
+        torch.testing.assert_close(x0.cpu(), case["x0"], rtol=2e-6, atol=1e-6)
+
+
 def test_refiner_and_ssg_fixture(golden_dir):
     from point_diffusion_refinement_b200 import configs
     from point_diffusion_refinement_b200.pointnet2_ssg_sem import PointNet2SemSegSSG
@@ -192,3 +205,139 @@ def test_fused_engine_tf32_within_tolerance(golden_dir):
         net.reset_cond_features()
     assert torch.equal(warm, again)
     torch.testing.assert_close(warm.cpu(), gold["eps_warm"], rtol=2e-2, atol=2e-2)
+
+
+# TF32 bar of the compiled step ("state the tolerance used"): the error against the fp32 fixture is judged by
+# its DISTRIBUTION, not only its maximum -- a 10-bit mantissa through ~12 GroupNorm-ed layers gives a bell of a few 1e-4
+# with a thin tail.  Bounds = measured on B200 (profiles/r02_tf32_error_report.txt) with ~2x headroom.
+TF32_MEDIAN, TF32_P999, TF32_MAX = 1e-3, 8e-3, 2e-2
+
+
+def _tf32_error_profile(got, want):
+    err = (got.float().cpu() - want.float().cpu()).abs().flatten()
+    q = torch.quantile(err, torch.tensor([0.5, 0.999]))
+    return float(q[0]), float(q[1]), float(err.max())
+
+
+def test_benchmarked_shape_all_three_engines_agree():
+    """The shape bench.py times (B = 32 / GPU, shipped DDPM config): the per-layer module path (fp32 cuDNN), the compiled
+    program with fp32 SIMT GEMMs and the compiled program with tcgen05 TF32 GEMMs, cold and warm step.  Covers the
+    persistent GEMM scheduler's item order at 32 samples x tiles and gn_finalize at B = 32, which the B = 2 fixtures do not."""
+    from point_diffusion_refinement_b200 import configs
+    net = _net(configs.ddpm_pointnet_config(), 1)
+    x, cond, ts, label = [t.to(DEV) for t in C.denoiser_inputs(32, 2048, 3072, seed=5)]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    res = {}
+    try:
+        with torch.no_grad():
+            cold = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+            x2 = x + 0.05 * cold
+            res["modules"] = (cold, net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True))
+            for name, tf32 in (("simt", False), ("tf32", True)):
+                net.reset_cond_features()
+                net.enable_fused(True, use_tf32=tf32, use_graph=True, fuse_cold=True)
+                c = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+                w = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+                assert torch.equal(w, net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True))
+                res[name] = (c, w)
+            net.reset_cond_features()
+            net.enable_fused(False)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    for i in range(2):
+        torch.testing.assert_close(res["simt"][i], res["modules"][i], rtol=1e-4, atol=1e-4)
+        med, p999, mx = _tf32_error_profile(res["tf32"][i], res["simt"][i])
+        print("B=32 %s step: TF32 vs fp32-SIMT |err| median %.2e p99.9 %.2e max %.2e" % (("cold", "warm")[i], med, p999, mx))
+        assert med <= TF32_MEDIAN and p999 <= TF32_P999 and mx <= TF32_MAX, (med, p999, mx)
+
+
+def test_tf32_error_distribution_against_reference_fixture(golden_dir):
+    """Compiled TF32 step against the reference-Python fixture (fp32, CPU): median / 99.9th percentile / maximum."""
+    from point_diffusion_refinement_b200 import configs
+    gold = torch.load(golden_dir + "/denoiser_full.pt")
+    net = _net(configs.ddpm_pointnet_config(), gold["param_seed"])
+    x, cond, ts, label = [t.to(DEV) for t in C.denoiser_inputs(gold["B"], gold["N"], gold["M"], seed=gold["input_seed"])]
+    with torch.no_grad():
+        net.enable_fused(True, use_tf32=True, use_graph=True, fuse_cold=True)
+        cold = net(x, cond, ts=ts, label=label, use_retained_condition_feature=True)
+        warm = net(x + 0.05 * gold["eps_cold"].to(DEV), cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
+        net.reset_cond_features()
+    for name, got, want in (("cold", cold, gold["eps_cold"]), ("warm", warm, gold["eps_warm"])):
+        med, p999, mx = _tf32_error_profile(got, want)
+        print("fixture %s step: TF32 |err| median %.2e p99.9 %.2e max %.2e (|eps| mean %.2f)" % (name, med, p999, mx,
+                                                                                                float(want.abs().mean())))
+        assert med <= TF32_MEDIAN and p999 <= TF32_P999 and mx <= TF32_MAX, (name, med, p999, mx)
+
+
+def test_tf32_chain_lands_where_the_fp32_chain_does():
+    """Distributional check (trajectories are chaotic, so whole chains are compared as point SETS): the cd_t
+    between a 60-step TF32 chain and the fp32-SIMT chain from the same x_T and the same Philox noise must sit well below
+    the seed-to-seed cd_t of two fp32 chains (the floor a different noise draw produces)."""
+    from point_diffusion_refinement_b200 import configs, util
+    from point_diffusion_refinement_b200.chamfer_loss_new import Chamfer_F1
+    net = _net(configs.ddpm_pointnet_config(), 1)
+    _, cond, _, label = [t.to(DEV) for t in C.denoiser_inputs(4, 2048, 3072, seed=9)]
+    dh = util.calc_diffusion_hyperparams(**configs.DIFFUSION_CONFIG)
+    size = (4, 2048, 3)
+    XT = torch.randn(size, generator=torch.Generator().manual_seed(2)).to(DEV) * 0.5
+    kw = dict(label=label, condition=cond, verbose=False, print_every_n_steps=0, use_a_precomputed_XT=True, step=60, XT=XT)
+    out = {}
+    for name, tf32, seed in (("f32", False, 3), ("tf32", True, 3), ("f32_other_seed", False, 4)):
+        net.enable_fused(True, use_tf32=tf32, use_graph=True, fuse_cold=True)
+        out[name] = util.sampling(net, size, dh, seed=seed, **kw)
+    net.enable_fused(False)
+    cf = Chamfer_F1()
+    cd = lambda a, b: float(cf(a, b)[1].mean())
+    same_noise, floor = cd(out["tf32"], out["f32"]), cd(out["f32_other_seed"], out["f32"])
+    print("cd_t(TF32 chain, fp32 chain; same noise) %.3e   cd_t(fp32 seed a, fp32 seed b) %.3e" % (same_noise, floor))
+    assert torch.isfinite(out["tf32"]).all() and same_noise < 0.25 * floor, (same_noise, floor)
+
+
+def test_fused_engine_follows_weight_and_label_changes():
+    """the compiled programs hold packed copies of the weights -- load_state_dict / in-place updates must not
+    leave them stale, and a warm call embeds the label it is GIVEN (reference :386-392), not the cold call's."""
+    from point_diffusion_refinement_b200 import configs
+    net = _net(configs.tiny_pointnet_config(), 1)
+    other = _net(configs.tiny_pointnet_config(), 2)
+    x, cond, ts, label = [t.to(DEV) for t in C.denoiser_inputs(2, 256, 384, seed=3)]
+    label2 = (label + 5) % 16
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            def run(n, lab_cold, lab_warm):
+                n.reset_cond_features()
+                n(x, cond, ts=ts, label=lab_cold, use_retained_condition_feature=True)
+                return n(x, cond, ts=ts - 1, label=lab_warm, use_retained_condition_feature=True)
+            want_other = run(other, label, label)
+            want_label2 = run(net, label, label2)
+            net.enable_fused(True, use_tf32=False, use_graph=True, fuse_cold=True)
+            a = run(net, label, label)
+            torch.testing.assert_close(run(net, label, label2), want_label2, rtol=1e-4, atol=1e-4)
+            net.load_state_dict(other.state_dict())
+            b = run(net, label, label)
+            torch.testing.assert_close(b, want_other, rtol=1e-4, atol=1e-4)
+            assert not torch.allclose(a, b, atol=1e-3)
+            for p_ in net.parameters():                      # in-place update (optimizer-style)
+                p_.mul_(1.01)
+            c = run(net, label, label)
+            net.enable_fused(False)
+            torch.testing.assert_close(c, run(net, label, label), rtol=1e-4, atol=1e-4)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_unseeded_sampling_calls_draw_different_noise():
+    """like the reference's global generator, the default noise stream advances between calls."""
+    from point_diffusion_refinement_b200 import configs, util
+    net = _net(configs.tiny_pointnet_config(), 1)
+    _, cond, _, label = [t.to(DEV) for t in C.denoiser_inputs(2, 256, 384, seed=3)]
+    dh = util.calc_diffusion_hyperparams(**configs.DIFFUSION_CONFIG)
+    XT = torch.zeros(2, 256, 3, device=DEV)
+    kw = dict(label=label, condition=cond, verbose=False, print_every_n_steps=0, use_a_precomputed_XT=True, step=3, XT=XT)
+    a, b = util.sampling(net, (2, 256, 3), dh, **kw), util.sampling(net, (2, 256, 3), dh, **kw)
+    assert not torch.equal(a, b)
+    c, d = util.sampling(net, (2, 256, 3), dh, seed=5, **kw), util.sampling(net, (2, 256, 3), dh, seed=5, **kw)
+    e = util.sampling(net, (2, 256, 3), dh, seed=5, noise_stream=1, **kw)
+    assert torch.equal(c, d) and not torch.equal(c, e)

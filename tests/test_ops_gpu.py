@@ -192,6 +192,32 @@ def test_chamfer_large_properties():
     assert torch.all(ct1 <= 2 * 3 * 0.01 ** 2 * 1.0001)           # each point has a neighbour at distance <= |shift|
 
 
+def test_chamfer_16384_against_the_oracle(oracle):
+    """BASELINE config 4's second shape (16384 x 16384) against the CPU oracle on one cloud pair (< 1 s of host work)."""
+    from point_diffusion_refinement_b200.chamfer_loss_new import Chamfer_F1
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(1, 16384, 3, generator=g) * 2 - 1, torch.rand(1, 16384, 3, generator=g) * 2 - 1
+    cp, ct, f1 = Chamfer_F1(f1_threshold=1e-3)(a.to(DEV), b.to(DEV))
+    ocp, oct_, of1 = oracle.chamfer_f1(a, b, 1e-3)
+    torch.testing.assert_close(cp.cpu(), ocp, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(ct.cpu(), oct_, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(f1.cpu(), of1, rtol=1e-5, atol=1e-7)
+
+
+def test_emd_gradient_through_a_non_contiguous_input():
+    """transpose=True hands forward() a non-contiguous tensor; the match must still be saved for backward."""
+    from point_diffusion_refinement_b200.emd import earth_mover_distance
+    g = torch.Generator().manual_seed(1)
+    a = torch.rand(2, 3, 64, generator=g).to(DEV).requires_grad_(True)
+    b = torch.rand(2, 3, 64, generator=g).to(DEV)
+    cost = earth_mover_distance(a, b, transpose=True)
+    cost.sum().backward()
+    assert a.grad is not None and a.grad.shape == a.shape and torch.isfinite(a.grad).all() and a.grad.abs().sum() > 0
+    a2 = a.detach().transpose(1, 2).contiguous().requires_grad_(True)
+    earth_mover_distance(a2, b.transpose(1, 2).contiguous()).sum().backward()
+    torch.testing.assert_close(a.grad.transpose(1, 2), a2.grad, rtol=1e-5, atol=1e-7)
+
+
 def test_emd_known_answer_and_api():
     from point_diffusion_refinement_b200.emd import EMD_distance, earth_mover_distance
     p1 = torch.tensor([[[1.7, -0.1, 0.1], [0.1, 1.2, 0.3]]], device=DEV).repeat(3, 1, 1)
