@@ -195,9 +195,10 @@ class PointNet2CloudCondition(PointNet2SemSegSSG):
     def _fused_step(self, pointcloud, ts, label=None):
         B, N, _ = pointcloud.shape
         # the fingerprint walk costs ~0.2 ms: done when a chain (re)binds its condition state, not on every step
-        rebind = self._fused_bound is not self._cond_state or getattr(self, "_fused_engine", None) is None
+        eng0 = getattr(self, "_fused_engine", None)
+        rebind = eng0 is None or getattr(self, "_fused_bound", None) is not self._cond_state
         eng = self._engine(B, N, check_weights=rebind)
-        if self._fused_bound is not self._cond_state:
+        if getattr(self, "_fused_bound", None) is not self._cond_state:
             eng.set_condition(self._cond_state, self._cond_label)
             self._fused_bound = self._cond_state
             self._fused_label = self._cond_label
