@@ -288,6 +288,77 @@ int pdr_group_src_rows(int batch, int n, int P, int K, const void *idx, int idx_
 int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, const int *idx, float *out,
                     int ldo, void *stream);
 
+/* ================================================================================================
+ * Fused stage: one grouped stage of the network -- the chain of 1x1 convolutions over the same grouped rows that
+ * Mlp_plus_t_emb + AttentionModule apply (pointnet2_ops/pointnet2_modules.py:57-65,129-174, attention.py:70-96) --
+ * evaluated in sweeps that keep every intermediate on chip (csrc/stage_chain.cu).  A sweep is a step program:
+ * per 128-row tile, step s issues its MMAs (accumulators in TMEM), then its epilogue operations run over blocks of 32
+ * accumulator columns:
+ *   XFORM  y = acc + bias (+ rowadd[row / group_k]);  t = pro(y; sc[b], sh[b]) + emb[b], rounded to TF32, written back
+ *          to TMEM as the A operand of a later MMA (never stored)
+ *   STATS  per-tile column statistics of y for the GroupNorm that follows, same layout as PdrGemmArgs.stats:
+ *          stats[(tile * stats_n + stat_col0 + c) * 4 + {sum, sum^2, relu-sum, relu-sum^2}]
+ *   POOL   out[point, c] = sum_k softmax_k(y[point*group_k + k, c] masked to k < max(counts[point], 1))
+ *                               * relu((acc_v + v_bias) * v_sc[b] + v_sh[b])         (pdr_attention_pool)
+ * All column numbers are relative to the 256 TMEM columns of the tile's group; widths are padded to multiples of 32
+ * (pad columns of an XFORM are written as zeros).  rows_per_sample % 128 == 0, group_k in {8, 16, 32}.
+ * ============================================================================================== */
+#define PDR_CHAIN_MAX_STEPS 4
+#define PDR_CHAIN_MAX_MMA 4
+#define PDR_CHAIN_MAX_EPI 3
+#define PDR_CHAIN_XFORM 1
+#define PDR_CHAIN_STATS 2
+#define PDR_CHAIN_POOL 3
+
+typedef struct PdrChainMma {
+  int d_col; int n;                  /* accumulator columns [d_col, d_col + n), n a multiple of 16, <= 256 */
+  int a_tmem; int a_col; int k;      /* A = TMEM columns [a_col, a_col + k) (a_tmem != 0) or columns [a_col, a_col + k) of the
+                                        gathered X0 tile in shared memory; k a multiple of 8 */
+  int w_off; int w_rows;             /* B: matrix at byte w_off of the weight image, w_rows rows (see w_image) */
+  int w_row0; int w_k0;              /* first row (multiple of 8) and first column (multiple of 8) used */
+  int accumulate;                    /* 0: the first K step overwrites the accumulator */
+} PdrChainMma;
+
+typedef struct PdrChainEpi {
+  int kind; int d_col; int ncols;                          /* ncols valid columns from d_col; every per-column array below is
+                                                              readable (zeros) up to the next multiple of 4 */
+  const float *bias;                                       /* (32-padded ncols) or NULL */
+  const float *rowadd; int ld_rowadd;                      /* (points, ld_rowadd) or NULL */
+  int pro_mode; const float *sc; const float *sh; int ld_scsh;   /* XFORM: PDR_PRO_*, (batch, ld_scsh) */
+  const float *emb; int ld_emb;                            /* XFORM: (batch, ld_emb) or NULL */
+  int a_col;                                               /* XFORM: destination TMEM columns */
+  int stat_col0; int stat_skip;                            /* STATS: column offset in `stats`; bit 0 / 1 as stats_skip */
+  int v_col; const float *v_bias; const float *v_sc; const float *v_sh; int v_ld_scsh;   /* POOL: the values */
+} PdrChainEpi;
+
+typedef struct PdrChainStep {
+  int n_mma; int n_epi;
+  int release_x0;                    /* the X0 tile is not read after this step's MMAs (exactly one step sets it) */
+  PdrChainMma mma[PDR_CHAIN_MAX_MMA];
+  PdrChainEpi epi[PDR_CHAIN_MAX_EPI];
+} PdrChainStep;
+
+typedef struct PdrChainArgs {
+  /* gathered operand X0[r] = [ table[src_rows[r], 0:k_split] | geo[r, 0:k0-k_split] ]  (src_rows[r] < 0: zeros), as
+   * PdrGemmArgs.a_rows: pdr_group_geo_ball / pdr_group_geo_knn produce src_rows and geo */
+  const float *table; int ld_table; int k_split;
+  const int *src_rows; const float *geo; int ld_geo; int k0;
+  /* every weight matrix of the stage, TF32-rounded, in the shared-memory image the tensor core reads: per matrix
+   * (rows R, a multiple of 32; K padded to a multiple of 32) chunk kc = columns [32 kc, 32 kc + 32) is R rows of 128
+   * bytes, the 16-byte piece p of row r stored at piece p ^ (r & 7) (K-major SWIZZLE_128B); chunks follow each other.
+   * w_bytes a multiple of 1024. */
+  const void *w_image; int w_bytes;
+  int batch; int rows_per_sample; int group_k;
+  float *stats; int stats_n;         /* STATS target: (batch * rows_per_sample / 128, stats_n, 4) */
+  unsigned int stats_relu_mask[4];   /* bit c: column c of `stats` carries the relu pair (slots 2, 3), else the plain pair
+                                        (slots 0, 1); the other pair is written as zeros */
+  const int *counts; float *out; int ld_out;      /* POOL: counts (points) or NULL, out (points, ld_out) */
+  int max_ctas;                      /* upper bound on the CTAs of the persistent grid (0 = one per SM), as PdrGemmArgs.max_ctas */
+  int n_steps; PdrChainStep steps[PDR_CHAIN_MAX_STEPS];
+} PdrChainArgs;
+int pdr_stage_chain_tile_rows(void);
+int pdr_stage_chain(const PdrChainArgs *args, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,8 @@ SIGNATURES = {
     "pdr_group_geo_knn": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "pdr_group_src_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _ptr],
     "pdr_gather_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr],
+    "pdr_stage_chain_tile_rows": [],
+    "pdr_stage_chain": [_ptr, _ptr],
 }
 _RESTYPES = {
     "pdr_last_error_string": ctypes.c_char_p,

@@ -1,0 +1,574 @@
+// Fused stage kernel for the denoiser -- sm_100a only.
+//
+// One grouped stage of the network (pointnet2_modules.py:57-65,129-174 + attention.py:70-96) is a chain of 1x1
+// convolutions over the SAME grouped rows, with a per-sample GroupNorm between any two of them:
+//
+//     X0 --W1--> [y1 | key]      y1 --GN,ReLU--> a1 --W2--> y2 ...  --Wv (+ folded residual of X0)--> V
+//                                key --ReLU,GN--> k1 --W1k (+ query row)--> s1 --ReLU,GN--> s1' --Ws--> S
+//     out[point] = sum_k softmax_k(S) * relu(GN(V))
+//
+// The per-layer engine (gemm_tc.cuh) writes every one of these tensors to HBM and reads it back: ~400 floats per grouped
+// row for a 32-channel stage.  A GroupNorm needs the statistics of the WHOLE sample before its output can be used, so the
+// chain cannot be evaluated in one sweep -- but it can be evaluated in L + 2 sweeps that each RECOMPUTE the chain from X0
+// up to the layer whose statistics are still missing, keeping every intermediate on chip:
+//
+//     sweep d:  for every 128-row tile:  X0 (gathered rows, 13-60 floats per row, shared memory)
+//               -> tcgen05.mma (A from shared memory) -> accumulator in TMEM
+//               -> epilogue warps: tcgen05.ld, + bias, GroupNorm scale/shift + ReLU + embedding, TF32 rounding,
+//                  tcgen05.st back into TMEM as the A OPERAND of the next layer's tcgen05.mma (A from TMEM)
+//               -> ... -> layer d: per-tile column statistics only (sweeps 1 .. L+1), or the soft-attention pooling
+//                  over the K neighbour rows straight from the two accumulators (last sweep).
+//
+// Nothing but X0 is read and nothing but statistics / the pooled rows is written: the tensor pipe (idle at 3-12 % in the
+// per-layer engine) pays for the recomputation, HBM traffic drops by ~8x for the stages this kernel takes.
+//
+// The layer chain is data: a small step program (PdrChainArgs) built by the host (fused.py) -- per step a list of MMAs
+// (A = X0 tile in shared memory | TMEM columns written by an earlier epilogue; B = a weight matrix resident in shared
+// memory in the canonical K-major SWIZZLE_128B layout; D = TMEM columns) followed by a list of epilogue operations
+// (XFORM / STATS / POOL over blocks of 32 accumulator columns).
+//
+// Persistent, warp-specialised, one CTA of 544 threads per SM, every CTA a contiguous range of row tiles:
+//   warps 0..7   epilogue: two GROUPS of four warps (one warp per TMEM lane quarter); group g owns the tiles g, g+2, ...
+//                of the CTA's range and TMEM columns [256 g, 256 g + 256), so two tiles are in flight and one group's
+//                epilogue overlaps the other group's MMAs.
+//   warps 8..15  producers: cp.async of the gathered X0 rows (table row + geometric channels) into a ring of
+//                SWIZZLE_128B tiles, completion by cp.async.mbarrier.arrive.
+//   warp 16      MMA issue (one lane): walks both groups' step programs in lock step.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pdr {
+namespace {
+
+constexpr int kEpiWarps = 8, kProdWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
+constexpr int kThreads = kEpiThreads + kProdThreads + 32;      // 544
+constexpr int kMmaWarp = kEpiWarps + kProdWarps;               // 16
+constexpr int kTileM = 128;
+constexpr int kChunkBytes = kTileM * 128;                      // one 32-float K chunk of a 128-row tile
+constexpr int kGroupCols = 256;                                // TMEM columns per tile group
+constexpr int kMaxSlots = 8;
+constexpr int kMaxStatCols = 128;                              // statistics columns per sweep
+constexpr int kScratchFloats = 32 * 36;                        // per-warp transposition tile (rows x 36 floats)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "CH_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra CH_WAIT_DONE;\n\t"
+      "bra CH_WAIT_LOOP;\n\t"
+      "CH_WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem: lane = row, one column per K element] . B[smem desc]
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, SWIZZLE_128B, 8-row groups 1024 B apart (same encoding as gemm_tc.cuh)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+__device__ __forceinline__ void cp_async16_ignore(uint32_t dst, const void *src, bool ignore) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t"
+      "}\n" ::"r"(dst), "l"(src), "r"((int)ignore)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+struct ChainPlan {
+  int tiles_per_sample, total_tiles;
+  int nk0;          // 32-float K chunks of the gathered X0 tile
+  int slots;        // ring depth
+  int w_region;     // bytes reserved for the weight image (multiple of 1024)
+  int any_stats;    // some step has a STATS operation
+};
+
+// y = accumulator + bias (+ the broadcast query row of the point this row belongs to), 32 columns of my row
+__device__ __forceinline__ void epi_prelude(const PdrChainEpi &op, int c0, size_t point, float (&y)[32],
+                                            const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const int c = c0 + 4 * j4;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < op.ncols) {
+      if (op.bias) b = __ldg(reinterpret_cast<const float4 *>(op.bias + c));
+      if (op.rowadd) {
+        const float4 r = __ldg(reinterpret_cast<const float4 *>(op.rowadd + point * (size_t)op.ld_rowadd + c));
+        b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
+      }
+    }
+    y[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b.x;
+    y[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+    y[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
+    y[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[kMaxSlots], bar_empty[kMaxSlots], bar_mma_done[2], bar_epi_done[2];
+  __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) float s_scratch[kEpiWarps][kScratchFloats];        // per-warp transposition tile (stats, pooling)
+  __shared__ __align__(16) float s_part[2][4][kMaxStatCols][2];              // per group / lane quarter column partials
+
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *s_w = smem;                                   // weight image
+  uint8_t *s_x0 = smem + plan.w_region;                  // ring of gathered X0 tiles
+  const uint32_t slot_bytes = (uint32_t)plan.nk0 * kChunkBytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < plan.slots; ++s) { mbar_init(&bar_full[s], kProdThreads); mbar_init(&bar_empty[s], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&bar_mma_done[g], 1); mbar_init(&bar_epi_done[g], kEpiThreads / 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weight image: a byte-exact copy (the host laid it out in the swizzled K-major form the tensor core reads)
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.w_image);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_w);
+    for (int i = tid; i < a.w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  // this CTA's contiguous range of row tiles
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int base_n = plan.total_tiles / G, rem = plan.total_tiles % G;
+  const int t_lo = cta * base_n + min(cta, rem);
+  const int n_my = base_n + (cta < rem ? 1 : 0);
+
+  if (warp >= kEpiWarps && warp < kMmaWarp) {
+    // =============================== PRODUCERS: gathered X0 tiles ================================
+    const int ptid = tid - kEpiThreads;
+    const int piece = ptid & 7;       // 16-byte piece of the 128-byte chunk row
+    const int arow = ptid >> 3;       // rows arow + 32 i
+    const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ (arow & 7)) << 4));
+    int slot = 0, phase = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = t_lo + i;
+      const size_t row0 = (size_t)tile * kTileM + arow;             // rows_per_sample % 128 == 0: tiles are dense
+      int idx[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) idx[r] = __ldg(a.src_rows + row0 + 32 * r);
+      mbar_wait(&bar_empty[slot], (uint32_t)(phase ^ 1));
+      const uint32_t sbase = smem_u32(s_x0 + (size_t)slot * slot_bytes) + sw_off;
+      for (int kc = 0; kc < plan.nk0; ++kc) {
+        const int k = kc * 32 + piece * 4;
+        const uint32_t dst = sbase + (uint32_t)kc * kChunkBytes;
+        if (k < a.k_split) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            cp_async16_ignore(dst + r * 4096, a.table + (size_t)max(idx[r], 0) * a.ld_table + k, idx[r] < 0);
+        } else {
+          const bool in = k < a.k0;
+          const float *p = a.geo + row0 * (size_t)a.ld_geo + (in ? k - a.k_split : 0);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) cp_async16_ignore(dst + r * 4096, in ? p + (size_t)32 * r * a.ld_geo : a.geo, !in);
+        }
+      }
+      cp_async_arrive_noinc(&bar_full[slot]);
+      if (++slot == plan.slots) { slot = 0; phase ^= 1; }
+    }
+  } else if (warp == kMmaWarp) {
+    // =============================== MMA ISSUER ==================================================
+    // both tile groups in lock step: step s of tile 2j (group 0), step s of tile 2j + 1 (group 1), step s + 1 ...
+    uint32_t ph_epi[2] = {0u, 0u};
+    bool first[2] = {true, true};
+    constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+    for (int pair = 0; pair * 2 < n_my; ++pair) {
+      for (int s = 0; s < a.n_steps; ++s) {
+        const PdrChainStep &st = a.steps[s];
+        for (int g = 0; g < 2; ++g) {
+          const int i = pair * 2 + g;
+          if (i >= n_my) continue;
+          const int slot = i % plan.slots;
+          const uint32_t slot_phase = (uint32_t)((i / plan.slots) & 1);
+          if (!first[g]) {
+            // the epilogue of this group's previous step (or of its previous tile's last step) has drained the
+            // accumulators and published the A operands
+            mbar_wait(&bar_epi_done[g], ph_epi[g]);
+            ph_epi[g] ^= 1u;
+          }
+          first[g] = false;
+          if (s == 0) mbar_wait(&bar_full[slot], slot_phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t tg = tmem_base + (uint32_t)(g * kGroupCols);
+            const uint32_t x0 = smem_u32(s_x0 + (size_t)slot * slot_bytes);
+            const uint32_t wb = smem_u32(s_w);
+            for (int m = 0; m < st.n_mma; ++m) {
+              const PdrChainMma &op = st.mma[m];
+              const uint32_t idesc = kIdescBase | ((uint32_t)(op.n >> 3) << 17);
+              const uint32_t d = tg + (uint32_t)op.d_col;
+              for (int kk = 0; kk < op.k; kk += 8) {
+                const int kw = op.w_k0 + kk;
+                const uint64_t bdesc =
+                    make_desc(wb + (uint32_t)op.w_off + (uint32_t)(kw >> 5) * (uint32_t)op.w_rows * 128u +
+                              (uint32_t)op.w_row0 * 128u) + (uint64_t)((kw & 31) >> 2);
+                const uint32_t acc = (kk > 0 || op.accumulate) ? 1u : 0u;
+                if (op.a_tmem) {
+                  umma_ts(d, tg + (uint32_t)(op.a_col + kk), bdesc, idesc, acc);
+                } else {
+                  const int ka = op.a_col + kk;
+                  const uint64_t adesc = make_desc(x0 + (uint32_t)(ka >> 5) * kChunkBytes) + (uint64_t)((ka & 31) >> 2);
+                  umma_ss(d, adesc, bdesc, idesc, acc);
+                }
+              }
+            }
+            umma_commit(&bar_mma_done[g]);
+            if (st.release_x0) umma_commit(&bar_empty[slot]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =============================== EPILOGUE ====================================================
+    const int g = warp >> 2, quarter = warp & 3;
+    const int gtid = tid & (kEpiThreads / 2 - 1);            // thread index inside the group
+    const int gbar = 1 + g;                                  // named barrier of the group
+    const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * kGroupCols);
+    float *scr = s_scratch[warp];
+    uint32_t ph = 0u;
+    const float ninf = __int_as_float(0xff800000);
+    for (int i = g; i < n_my; i += 2) {
+      const int tile = t_lo + i;
+      const int b = tile / plan.tiles_per_sample;
+      const size_t grow = (size_t)tile * kTileM + quarter * 32 + lane;     // my global grouped row
+      const size_t point = grow / (size_t)a.group_k;
+      for (int s = 0; s < a.n_steps; ++s) {
+        const PdrChainStep &st = a.steps[s];
+        mbar_wait(&bar_mma_done[g], ph);
+        ph ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        bool wrote_tmem = false, did_stats = false;
+        for (int e = 0; e < st.n_epi; ++e) {
+          const PdrChainEpi &op = st.epi[e];
+          const int nblk = (op.ncols + 31) >> 5;
+          for (int blk = 0; blk < nblk; ++blk) {
+            const int c0 = blk * 32;
+            uint32_t v[32];
+            float y[32];
+            tmem_ld32(tq + (uint32_t)(op.d_col + c0), v);
+            tmem_wait_ld();
+            epi_prelude(op, c0, point, y, v);
+            if (op.kind == PDR_CHAIN_XFORM) {
+              // t = pro(y) + emb -> TF32 -> the A operand of a later MMA (TMEM, lane = row, one column per channel)
+              const float lo1 = op.pro_mode == PDR_PRO_RELU_GN ? 0.f : ninf;
+              const float lo2 = op.pro_mode == PDR_PRO_GN_RELU ? 0.f : ninf;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const int c = c0 + 4 * j4;
+                float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4, e4 = sc4;
+                if (c < op.ncols) {
+                  sc4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                  if (op.pro_mode != PDR_PRO_NONE) {
+                    sc4 = __ldg(reinterpret_cast<const float4 *>(op.sc + (size_t)b * op.ld_scsh + c));
+                    sh4 = __ldg(reinterpret_cast<const float4 *>(op.sh + (size_t)b * op.ld_scsh + c));
+                  }
+                  if (op.emb) e4 = __ldg(reinterpret_cast<const float4 *>(op.emb + (size_t)b * op.ld_emb + c));
+                }
+                const float t0 = fmaxf(fmaf(fmaxf(y[4 * j4 + 0], lo1), sc4.x, sh4.x), lo2) + e4.x;
+                const float t1 = fmaxf(fmaf(fmaxf(y[4 * j4 + 1], lo1), sc4.y, sh4.y), lo2) + e4.y;
+                const float t2 = fmaxf(fmaf(fmaxf(y[4 * j4 + 2], lo1), sc4.z, sh4.z), lo2) + e4.z;
+                const float t3 = fmaxf(fmaf(fmaxf(y[4 * j4 + 3], lo1), sc4.w, sh4.w), lo2) + e4.w;
+                v[4 * j4 + 0] = __float_as_uint(to_tf32(t0));
+                v[4 * j4 + 1] = __float_as_uint(to_tf32(t1));
+                v[4 * j4 + 2] = __float_as_uint(to_tf32(t2));
+                v[4 * j4 + 3] = __float_as_uint(to_tf32(t3));
+              }
+              tmem_st32(tq + (uint32_t)(op.a_col + c0), v);
+              wrote_tmem = true;
+            } else if (op.kind == PDR_CHAIN_STATS) {
+              // per-tile column statistics of y: park my row, read the tile back column-wise (lane = column).  Every
+              // consumer reads ONE of the two pairs (plain or relu), stat_skip says which one is not needed.
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4 *>(scr + lane * 36 + 4 * j4) =
+                    make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
+              __syncwarp();
+              float q0 = 0.f, q1 = 0.f;
+              if (op.stat_skip & 1) {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) { const float p = fmaxf(scr[r * 36 + lane], 0.f); q0 += p; q1 = fmaf(p, p, q1); }
+              } else {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) { const float t = scr[r * 36 + lane]; q0 += t; q1 = fmaf(t, t, q1); }
+              }
+              *reinterpret_cast<float2 *>(&s_part[g][quarter][op.stat_col0 + c0 + lane][0]) = make_float2(q0, q1);
+              did_stats = true;
+              __syncwarp();
+            } else {
+              // soft-attention pooling over the group_k neighbour rows of each point (attention.py:85-96): scores = y,
+              // values = relu(GN(V accumulator + bias)).  One transposition tile, three phases:
+              //   (1) lane = row parks its scores; lane = column takes the masked maximum and the denominator of each
+              //       point and leaves exp(score - max) in place;
+              //   (2) lane = row multiplies its row of weights with its values (TMEM) in place;
+              //   (3) lane = column adds the group_k products of each point and divides.
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<float4 *>(scr + lane * 36 + 4 * j4) =
+                    make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
+              tmem_ld32(tq + (uint32_t)(op.v_col + c0), v);          // the values, in flight during phase 1
+              __syncwarp();
+              const int PK = a.group_k;
+              const size_t point0 = ((size_t)tile * kTileM + quarter * 32) / (size_t)PK;
+              float den[4] = {1.f, 1.f, 1.f, 1.f};                    // 32 / group_k <= 4 points per warp
+#pragma unroll
+              for (int pi = 0; pi < 4; ++pi) {
+                const int r0 = pi * PK;
+                if (r0 < 32) {
+                  int cnt = PK;
+                  if (a.counts) { cnt = __ldg(a.counts + point0 + pi); cnt = cnt < 1 ? 1 : cnt; }
+                  float mx = -3.0e38f;
+#pragma unroll 8
+                  for (int k = 0; k < PK; ++k) mx = fmaxf(mx, k < cnt ? scr[(r0 + k) * 36 + lane] : -1e9f);
+                  float dsum = 0.f;
+#pragma unroll 8
+                  for (int k = 0; k < PK; ++k) {
+                    const float sk = k < cnt ? scr[(r0 + k) * 36 + lane] : -1e9f;
+                    const float ex = expf(sk - mx);
+                    dsum += ex;
+                    scr[(r0 + k) * 36 + lane] = ex;
+                  }
+                  den[pi] = dsum;
+                }
+              }
+              tmem_wait_ld();
+              __syncwarp();
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const int c = c0 + 4 * j4;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = b4, sh4 = b4;
+                if (c < op.ncols) {
+                  if (op.v_bias) b4 = __ldg(reinterpret_cast<const float4 *>(op.v_bias + c));
+                  sc4 = __ldg(reinterpret_cast<const float4 *>(op.v_sc + (size_t)b * op.v_ld_scsh + c));
+                  sh4 = __ldg(reinterpret_cast<const float4 *>(op.v_sh + (size_t)b * op.v_ld_scsh + c));
+                }
+                float4 w = *reinterpret_cast<const float4 *>(scr + lane * 36 + 4 * j4);
+                w.x *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]) + b4.x, sc4.x, sh4.x), 0.f);
+                w.y *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]) + b4.y, sc4.y, sh4.y), 0.f);
+                w.z *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]) + b4.z, sc4.z, sh4.z), 0.f);
+                w.w *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]) + b4.w, sc4.w, sh4.w), 0.f);
+                *reinterpret_cast<float4 *>(scr + lane * 36 + 4 * j4) = w;
+              }
+              __syncwarp();
+              const int n = c0 + lane;                               // my output channel
+#pragma unroll
+              for (int pi = 0; pi < 4; ++pi) {
+                const int r0 = pi * PK;
+                if (r0 < 32) {
+                  float num = 0.f;
+#pragma unroll 8
+                  for (int k = 0; k < PK; ++k) num += scr[(r0 + k) * 36 + lane];
+                  if (n < op.ncols) a.out[(point0 + pi) * (size_t)a.ld_out + n] = num / den[pi];
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+        // the accumulators of this step are drained and (XFORM) the next A operands are in TMEM
+        if (wrote_tmem) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&bar_epi_done[g]);
+        if (did_stats) {
+          // fold the four lane quarters in a fixed order and publish this tile's column partials
+          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(kEpiThreads / 2) : "memory");
+          for (int col = gtid; col < a.stats_n; col += kEpiThreads / 2) {
+            const float s0 = s_part[g][0][col][0] + s_part[g][1][col][0] + s_part[g][2][col][0] + s_part[g][3][col][0];
+            const float s1 = s_part[g][0][col][1] + s_part[g][1][col][1] + s_part[g][2][col][1] + s_part[g][3][col][1];
+            const bool relu = (a.stats_relu_mask[col >> 5] >> (col & 31)) & 1u;
+            *reinterpret_cast<float4 *>(a.stats + ((size_t)tile * a.stats_n + col) * 4) =
+                relu ? make_float4(0.f, 0.f, s0, s1) : make_float4(s0, s1, 0.f, 0.f);
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(kEpiThreads / 2) : "memory");
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+}  // namespace pdr
+
+using namespace pdr;
+
+extern "C" int pdr_stage_chain_tile_rows(void) { return kTileM; }
+
+extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
+  PDR_REQUIRE(args, "stage_chain: null args");
+  const PdrChainArgs &a = *args;
+  PDR_REQUIRE(a.table && a.src_rows && a.geo && a.w_image, "stage_chain: null pointer");
+  PDR_REQUIRE(a.batch > 0 && a.rows_per_sample > 0 && a.rows_per_sample % kTileM == 0,
+              "stage_chain: rows_per_sample=%d must be a positive multiple of %d", a.rows_per_sample, kTileM);
+  PDR_REQUIRE(a.group_k == 8 || a.group_k == 16 || a.group_k == 32, "stage_chain: group_k=%d not in {8,16,32}", a.group_k);
+  PDR_REQUIRE(a.k_split > 0 && a.k_split % 4 == 0 && a.ld_table % 4 == 0 && a.ld_table >= a.k_split && a.ld_geo % 4 == 0 &&
+                  a.k0 > a.k_split && a.k0 - a.k_split <= a.ld_geo && ((uintptr_t)a.table % 16) == 0 &&
+                  ((uintptr_t)a.geo % 16) == 0,
+              "stage_chain: bad gathered-operand layout (k_split=%d ld_table=%d ld_geo=%d k0=%d)", a.k_split, a.ld_table,
+              a.ld_geo, a.k0);
+  PDR_REQUIRE(a.w_bytes > 0 && a.w_bytes % 1024 == 0 && ((uintptr_t)a.w_image % 16) == 0, "stage_chain: weight image");
+  PDR_REQUIRE(a.n_steps >= 1 && a.n_steps <= PDR_CHAIN_MAX_STEPS, "stage_chain: n_steps=%d", a.n_steps);
+  ChainPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  plan.nk0 = ceil_div(a.k0, 32);
+  plan.tiles_per_sample = a.rows_per_sample / kTileM;
+  const long long tiles = (long long)a.batch * plan.tiles_per_sample;
+  PDR_REQUIRE(tiles < (1ll << 24), "stage_chain: too many tiles");
+  plan.total_tiles = (int)tiles;
+  plan.w_region = a.w_bytes;
+  int releases = 0;
+  for (int s = 0; s < a.n_steps; ++s) {
+    const PdrChainStep &st = a.steps[s];
+    PDR_REQUIRE(st.n_mma >= 1 && st.n_mma <= PDR_CHAIN_MAX_MMA && st.n_epi >= 1 && st.n_epi <= PDR_CHAIN_MAX_EPI,
+                "stage_chain: step %d has %d MMAs / %d epilogue operations", s, st.n_mma, st.n_epi);
+    releases += st.release_x0 ? 1 : 0;
+    for (int m = 0; m < st.n_mma; ++m) {
+      const PdrChainMma &op = st.mma[m];
+      PDR_REQUIRE(op.n >= 16 && op.n <= 256 && op.n % 16 == 0 && op.k > 0 && op.k % 8 == 0 && op.d_col >= 0 &&
+                      op.d_col + op.n <= kGroupCols && op.w_off >= 0 && op.w_off % 1024 == 0 && op.w_rows % 8 == 0 &&
+                      op.w_row0 % 8 == 0 && op.w_row0 + op.n <= op.w_rows && op.w_k0 % 8 == 0 && op.a_col >= 0 &&
+                      op.a_col % 8 == 0,
+                  "stage_chain: step %d MMA %d is malformed", s, m);
+      const long long w_end = (long long)op.w_off + (long long)ceil_div(op.w_k0 + op.k, 32) * op.w_rows * 128;
+      PDR_REQUIRE(w_end <= a.w_bytes, "stage_chain: step %d MMA %d reads past the weight image", s, m);
+      if (op.a_tmem) PDR_REQUIRE(op.a_col + op.k <= kGroupCols, "stage_chain: step %d MMA %d: A operand past the group's TMEM", s, m);
+      else PDR_REQUIRE(op.a_col + op.k <= plan.nk0 * 32, "stage_chain: step %d MMA %d: A operand past the X0 tile", s, m);
+    }
+    for (int e = 0; e < st.n_epi; ++e) {
+      const PdrChainEpi &op = st.epi[e];
+      const int padded = ceil_div(op.ncols, 32) * 32;
+      // (ncols need not be a multiple of 4: bias / sc / sh / emb / rowadd rows are read in float4 groups up to the next
+      //  multiple of 4, their pad entries are zero by the engine's layout rule, and the pad columns come out as zeros)
+      PDR_REQUIRE(op.kind >= PDR_CHAIN_XFORM && op.kind <= PDR_CHAIN_POOL && op.ncols > 0 &&
+                      op.d_col >= 0 && op.d_col + padded <= kGroupCols,
+                  "stage_chain: step %d epilogue operation %d is malformed", s, e);
+      PDR_REQUIRE((!op.bias || ((uintptr_t)op.bias % 16) == 0) &&
+                      (!op.rowadd || (op.ld_rowadd % 4 == 0 && ((uintptr_t)op.rowadd % 16) == 0)),
+                  "stage_chain: bias / rowadd alignment");
+      if (op.kind == PDR_CHAIN_XFORM) {
+        PDR_REQUIRE(op.a_col >= 0 && op.a_col + padded <= kGroupCols, "stage_chain: XFORM destination");
+        PDR_REQUIRE(op.pro_mode == PDR_PRO_NONE || (op.sc && op.sh && op.ld_scsh % 4 == 0 && ((uintptr_t)op.sc % 16) == 0 &&
+                                                     ((uintptr_t)op.sh % 16) == 0),
+                    "stage_chain: XFORM needs aligned sc / sh");
+        PDR_REQUIRE(!op.emb || (op.ld_emb % 4 == 0 && ((uintptr_t)op.emb % 16) == 0), "stage_chain: emb alignment");
+      } else if (op.kind == PDR_CHAIN_STATS) {
+        PDR_REQUIRE(a.stats && op.stat_col0 >= 0 && op.stat_col0 + padded <= kMaxStatCols && op.stat_col0 + op.ncols <= a.stats_n,
+                    "stage_chain: STATS columns [%d, +%d) do not fit (stats_n=%d, cap %d)", op.stat_col0, op.ncols, a.stats_n,
+                    kMaxStatCols);
+        plan.any_stats = 1;
+      } else {
+        PDR_REQUIRE(a.out && a.ld_out >= op.ncols && op.v_sc && op.v_sh && op.v_ld_scsh % 4 == 0 && op.v_col >= 0 &&
+                        op.v_col + padded <= kGroupCols && ((uintptr_t)op.v_sc % 16) == 0 && ((uintptr_t)op.v_sh % 16) == 0 &&
+                        (!op.v_bias || ((uintptr_t)op.v_bias % 16) == 0),
+                    "stage_chain: POOL operands");
+      }
+    }
+  }
+  PDR_REQUIRE(releases == 1, "stage_chain: exactly one step must release the X0 tile (%d do)", releases);
+  PDR_REQUIRE(!plan.any_stats || (a.stats_n > 0 && a.stats_n <= kMaxStatCols), "stage_chain: stats_n=%d", a.stats_n);
+  // shared memory: weight image + ring of X0 tiles (static: barriers, transposition tiles, column partials)
+  const size_t static_smem = sizeof(float) * (size_t)(kEpiWarps * kScratchFloats + 2 * 4 * kMaxStatCols * 2) + 512;
+  const size_t budget = 226 * 1024 - static_smem;
+  const size_t slot_bytes = (size_t)plan.nk0 * kChunkBytes;
+  const size_t fixed = 1024 + (size_t)plan.w_region;
+  if (fixed + 2 * slot_bytes > budget) {
+    set_error("stage_chain: weights (%d B) + two X0 tiles (%zu B each) exceed shared memory", a.w_bytes, slot_bytes);
+    return PDR_ERR_UNSUPPORTED;
+  }
+  int slots = (int)((budget - fixed) / slot_bytes);
+  if (slots > kMaxSlots) slots = kMaxSlots;
+  plan.slots = slots;
+  const size_t smem = fixed + (size_t)slots * slot_bytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stage_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e != cudaSuccess) { set_error("stage_chain: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
+    configured = true;
+  }
+  const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
+  const int grid = plan.total_tiles < sm_cap ? plan.total_tiles : sm_cap;
+  stage_chain_kernel<<<grid, kThreads, smem, (cudaStream_t)stream_>>>(a, plan);
+  return check_launch("stage_chain_kernel");
+}

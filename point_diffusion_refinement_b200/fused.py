@@ -29,6 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from . import chain as CH
 from ._lib import PdrError
 from .attention import MyGroupNorm
 from .pointnet2_ssg_sem import calc_t_emb, swish
@@ -97,6 +98,13 @@ _FUSE_POOL = os.environ.get("PDR_FUSE_POOL", "0") == "1"
 # PDR_FOLD_RES=0 keeps the residual convolution of Mlp_plus_t_emb as a section of the stage's first GEMM (written, then
 # re-read by the values GEMM) instead of folding it into the values GEMM through the raw gathered K tail
 _FOLD_RES = os.environ.get("PDR_FOLD_RES", "1") != "0"
+
+
+# PDR_STAGE_CHAIN=0 keeps every stage on the per-layer GEMMs.  Default: stages whose weights fit in shared memory run as
+# fused sweeps (csrc/stage_chain.cu, chain.py): intermediates stay in tensor memory, only the gathered rows are read.
+_STAGE_CHAIN = os.environ.get("PDR_STAGE_CHAIN", "1") != "0"
+# PDR_STAGE_CHAIN_ONLY=name[,name...] restricts it to the named stages (enc_map0, dec_map1, sa0, ...): A/B and debugging
+_STAGE_CHAIN_ONLY = [n for n in os.environ.get("PDR_STAGE_CHAIN_ONLY", "").split(",") if n]
 
 
 def r4(c):
@@ -516,6 +524,10 @@ class FusedDenoiser:
         # K tail): its c_last output channels are then neither written by this stage's first GEMM nor re-read
         fold_res = (_FOLD_RES and gathered is not None and res_conv is not None and c_last % 32 == 0
                     and self.use_tf32 and B * rows_per_sample >= 512)
+        if (fold_res and _STAGE_CHAIN and (not _STAGE_CHAIN_ONLY or name in _STAGE_CHAIN_ONLY)
+                and self._stage_chain(name, gathered, K, rows_per_sample, layers, lay, res_conv, key_conv, att, query,
+                                      counts, out, emb_views)):
+            return
         # pad each section to a multiple of 4 output columns by inserting zero rows
         def pad_rows(w, b, n_to):
             if w.shape[0] < n_to:
@@ -614,6 +626,94 @@ class FusedDenoiser:
         self._emit("pdr_attention_pool", B, P, K, c_out, ctypes.c_void_p(S.ptr), S.ld, ctypes.c_void_p(V.ptr), V.ld,
                    ctypes.c_void_p(scv.ptr), ctypes.c_void_p(shv.ptr), scv.ld,
                    ctypes.c_void_p(counts.data_ptr()) if counts is not None else None, ctypes.c_void_p(out.ptr), out.ld)
+
+    def _stage_chain(self, name, gathered, K, rows_per_sample, layers, lay, res_conv, key_conv, att, query, counts, out,
+                     emb_views):
+        """The whole grouped stage as L + 2 sweeps of pdr_stage_chain (chain.py): every intermediate stays in tensor
+        memory, HBM sees the gathered rows once per sweep, the per-tile statistics and the pooled rows.  The small
+        per-POINT GEMMs of the attention query (feat_conv, the query half of weight_conv) and the GroupNorm finalisations
+        between the sweeps stay what they are.  Returns False (nothing emitted) when the stage does not qualify."""
+        B, dev = self.B, self.dev
+        P = rows_per_sample // K
+        L = len(layers)
+        c = [conv.out_channels for conv, _ in layers]
+        c_key = key_conv.out_channels
+        wc = list(att.weight_conv)            # [ReLU, GN, Conv, ReLU, GN, Conv]
+        gn_w1, conv_w1, gn_w2, conv_w2 = wc[1], wc[2], wc[4], wc[5]
+        inter, c_out = conv_w1.out_channels, conv_w2.out_channels
+        fo = list(att.feat_out_conv)          # [Conv, GN, ReLU]
+        conv_v, gn_v = fo[0], fo[1]
+        qconv = att.feat_conv
+        cq_in, cq = qconv.in_channels, qconv.out_channels
+        if (rows_per_sample % CH.TILE_ROWS != 0 or K not in (8, 16, 32) or L > 3
+                or conv_v.out_channels != c_out or conv_v.in_channels != c[-1]):
+            return False
+        w1 = _conv_w(conv_w1)
+        w_res = _pack([(_conv_w(res_conv), lay)], dev).double()                       # (c_last, k0)
+        wv64 = _conv_w(conv_v).double()
+        b_v = (_bias(conv_v, c_out, dev).double() + wv64 @ _bias(res_conv, c[-1], dev).double()).float()
+        mlp = [(_pack([(_conv_w(layers[0][0]), lay)], dev), _bias(layers[0][0], c[0], dev))]
+        mlp += [(_conv_w(conv), _bias(conv, conv.out_channels, dev)) for conv, _ in layers[1:]]
+        spec = CH.StageSpec(gathered.K, gathered.Cp, mlp,
+                            key=(_pack([(_conv_w(key_conv), lay)], dev), _bias(key_conv, c_key, dev)),
+                            w1k=(w1[:, cq:cq + c_key].contiguous(), _bias(conv_w1, inter, dev)),
+                            ws=(_conv_w(conv_w2), _bias(conv_w2, c_out, dev)),
+                            wv=(_conv_w(conv_v), (wv64 @ w_res).float(), b_v))
+        plan = CH.StagePlan(spec, dev)
+        if not plan.fits():
+            return False
+        M = B * rows_per_sample
+        tiles_ps = rows_per_sample // CH.TILE_ROWS
+        rt = dict(table=(gathered.table.ptr, gathered.table.ld), src_rows=gathered.src_row.data_ptr(),
+                  geo=(gathered.geo.ptr, gathered.geo.ld), batch=B, rows_per_sample=rows_per_sample, group_k=K, gn={}, emb={},
+                  counts=counts.data_ptr() if counts is not None else None, out=(out.ptr, out.ld),
+                  max_ctas=self._cta_limit if self._ops is self.ops else 0)
+        for l in range(L):
+            v = self._resolve_emb(emb_views[l])
+            rt["emb"][l + 1] = (v.ptr, v.ld) if v is not None else None
+        self.keep += [plan, gathered, rt]
+        x0_bytes = 4 * (min(M, gathered.table.rows) * gathered.Cp + M * (gathered.geo.ld + 1))
+        flops_layer = {"y1": 2 * M * gathered.K * (CH.p32(c[0]) + CH.p32(c_key))}
+
+        def sweep(d):
+            stats = None
+            n = plan.sweep_stats_n(d)
+            if n:
+                stats = Stats(self._zeros(B * tiles_ps, n, 4), tiles_ps, n, rows_per_sample)
+                rt["stats"] = stats.t.data_ptr()
+            args, steps = plan.build_sweep(d, rt)
+            self.keep.append(args)
+            flops = sum(2 * M * m["n"] * m["k"] for st in steps for m in st["mma"])
+            nbytes = x0_bytes + plan.image.bytes + (4 * B * tiles_ps * n * 4 if n else 4 * B * P * c_out)
+            self._emit("pdr_stage_chain", ctypes.c_void_p(ctypes.addressof(args)),
+                       info={"bytes": nbytes, "flops": flops, "M": M, "stage": name, "sweep": d})
+            return stats
+
+        bind = lambda nm, sc, sh: rt["gn"].__setitem__(nm, (sc.ptr, sh.ptr, sc.ld))
+        # sweep 1: statistics of y1 and relu(key); then the per-point query path of AttentionModule
+        st1 = sweep(1)
+        bind("y1", *self.gn([(st1, 0, c[0], False, 1.0)], layers[0][1]))
+        Wq = _pack([(_conv_w(qconv), [(0, cq_in, r4(cq_in))])], dev)
+        Q = self._mat(B * P, cq)
+        assert query.rows == B * P
+        stq = self.gemm(View(query.t, r4(cq_in), query.col0), Wq, _bias(qconv, cq, dev), Q, P, want_stats=True)
+        sc1, sh1 = self.gn([(stq, 0, cq, True, float(K)), (st1, CH.p32(c[0]), c_key, True, 1.0)], gn_w1)
+        bind("key", sc1.cols(r4(cq), r4(c_key)), sh1.cols(r4(cq), r4(c_key)))
+        YQ = self._mat(B * P, inter)
+        self.gemm(View(Q.t, r4(cq), 0), _pack([(w1, [(0, cq, r4(cq))])], dev), None, YQ, P, pro=PRO_RELU_GN,
+                  scsh=(sc1.cols(0, r4(cq)), sh1.cols(0, r4(cq))))
+        rt["rowadd"] = (YQ.ptr, YQ.ld)
+        # sweep 2: statistics of y2 and relu(s1)
+        st2 = sweep(2)
+        bind("y2", *self.gn([(st2, 0, c[1], False, 1.0)], layers[1][1]))
+        bind("s1", *self.gn([(st2, CH.p32(c[1]), inter, True, 1.0)], gn_w2))
+        for d in range(3, L + 1):
+            std = sweep(d)
+            bind("y%d" % d, *self.gn([(std, 0, c[d - 1], False, 1.0)], layers[d - 1][1]))
+        stv = sweep(L + 1)
+        bind("V", *self.gn([(stv, 0, c_out, False, 1.0)], gn_v))
+        sweep(L + 2)
+        return True
 
     def pointwise_mlp(self, name, Hin, C_in, rows_per_sample, mlp, out, emb_views):
         """Mlp_plus_t_emb over per-point rows (K = 1) with its residual; result materialised into `out`."""
@@ -798,8 +898,10 @@ class FusedDenoiser:
             self.grouped_block("sa%d" % i, X0, Cin + 9, idx.shape[2], n_lvl[i + 1] * idx.shape[2], sa.mlps[0],
                                sa.attention_modules[0], Qf, cnt, Fl[i + 1].cols(cm_next, own_dim[i + 1]), plans[("sa", i)])
 
+        self._Fl = Fl                                 # (kept for tests: per-level encoder features)
         # ---- decoder -----------------------------------------------------------------------------------
         Gl = [None] * (L + 1)                         # G[lvl]: [dec-mapped | level feature] (+ xyz for level 0)
+        self._Gl = Gl
         for lvl in range(L + 1):
             cd = dec_dim[lvl] if lvl < L else own_dim[L]
             Gl[lvl] = self._mat(B * n_lvl[lvl], dec_map_dim[lvl] + cd + (3 if lvl == 0 else 0))

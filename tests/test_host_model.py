@@ -206,6 +206,7 @@ def test_geometry_overlap_program_layout(cuda_lib, monkeypatch):
     from point_diffusion_refinement_b200 import configs, fused
     from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
     layouts = {}
+    monkeypatch.setattr(fused, "_STAGE_CHAIN", False)         # layout of the per-layer engine
     for on in (False, True):
         monkeypatch.setattr(fused, "_GEOM_OVERLAP", on)
         eng = fused.FusedDenoiser(PointNet2CloudCondition(configs.tiny_pointnet_config()).eval(), 2, 256, use_tf32=True,
@@ -220,7 +221,7 @@ def test_geometry_overlap_program_layout(cuda_lib, monkeypatch):
     assert side == {"pdr_furthest_point_sampling": 4, "pdr_gather_rows": 4, "pdr_ball_query": 8, "pdr_knn_points": 4}
     first_side = min(on.side_ops)
     assert names[first_side - 1] == "pdr_ball_query" and max(on.side_ops) < on._join_at
-    assert names[on._join_at] == "pdr_group_geo_ball" and names[on._join_at - 1] == "pdr_attention_pool"
+    assert names[on._join_at] == "pdr_group_geo_ball" and names[on._join_at - 1] in ("pdr_attention_pool", "pdr_stage_chain")
     caps = [g.max_ctas for g in on.keep if isinstance(g, fused.GemmArgs)]
     assert sum(1 for c in caps if c) == 7 and set(caps) == {0, fused._GEOM_OVERLAP_CTAS}
     assert all(g.max_ctas == 0 for g in off.keep if isinstance(g, fused.GemmArgs))
@@ -234,6 +235,7 @@ def test_fused_groupnorm_program_layout(cuda_lib, monkeypatch):
     from point_diffusion_refinement_b200 import configs, fused
     from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
     counts = {}
+    monkeypatch.setattr(fused, "_STAGE_CHAIN", False)         # layout of the per-layer engine
     for on in (False, True):
         monkeypatch.setattr(fused, "_GN_FUSED", on)
         eng = fused.FusedDenoiser(PointNet2CloudCondition(configs.tiny_pointnet_config()).eval(), 2, 256, use_tf32=True,
