@@ -294,7 +294,8 @@ int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, c
  *   POOL   out[point, c] = sum_k softmax_k(y[point*group_k + k, c] masked to k < max(counts[point], 1))
  *                               * relu((acc_v + v_bias) * v_sc[b] + v_sh[b])         (pdr_attention_pool)
  * All column numbers are relative to the 256 TMEM columns of the tile's group; widths are padded to multiples of 32
- * (pad columns of an XFORM are written as zeros).  rows_per_sample % 128 == 0, group_k in {8, 16, 32}.
+ * (pad columns of an XFORM come out as zeros because the per-column arrays are zero there).  rows_per_sample % 128 == 0,
+ * group_k in {8, 16, 32}.
  * ============================================================================================== */
 #define PDR_CHAIN_MAX_STEPS 4
 #define PDR_CHAIN_MAX_MMA 4
@@ -314,7 +315,8 @@ typedef struct PdrChainMma {
 
 typedef struct PdrChainEpi {
   int kind; int d_col; int ncols;                          /* ncols valid columns from d_col; every per-column array below is
-                                                              readable (zeros) up to the next multiple of 4 */
+                                                              read in whole 32-column blocks: readable, and zero, up to the
+                                                              next multiple of 32 */
   const float *bias;                                       /* (32-padded ncols) or NULL */
   const float *rowadd; int ld_rowadd;                      /* (points, ld_rowadd) or NULL */
   int pro_mode; const float *sc; const float *sh; int ld_scsh;   /* XFORM: PDR_PRO_*, (batch, ld_scsh) */

@@ -27,13 +27,13 @@
 // memory in the canonical K-major SWIZZLE_128B layout; D = TMEM columns) followed by a list of epilogue operations
 // (XFORM / STATS / POOL over blocks of 32 accumulator columns).
 //
-// Persistent, warp-specialised, one CTA of 544 threads per SM, every CTA a contiguous range of row tiles:
+// Persistent, warp-specialised, one CTA of 416 threads per SM, every CTA a contiguous range of row tiles:
 //   warps 0..7   epilogue: two GROUPS of four warps (one warp per TMEM lane quarter); group g owns the tiles g, g+2, ...
 //                of the CTA's range and TMEM columns [256 g, 256 g + 256), so two tiles are in flight and one group's
 //                epilogue overlaps the other group's MMAs.
-//   warps 8..15  producers: cp.async of the gathered X0 rows (table row + geometric channels) into a ring of
+//   warps 8..11  producers: cp.async of the gathered X0 rows (table row + geometric channels) into a ring of
 //                SWIZZLE_128B tiles, completion by cp.async.mbarrier.arrive.
-//   warp 16      MMA issue (one lane): walks both groups' step programs in lock step.
+//   warp 12      MMA issue (one lane): walks both groups' step programs in lock step.
 #include <stdlib.h>
 #include <string.h>
 
@@ -42,10 +42,10 @@
 namespace pdr {
 namespace {
 
-constexpr int kEpiWarps = 8, kProdWarps = 8;
+constexpr int kEpiWarps = 8, kProdWarps = 4;
 constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
-constexpr int kThreads = kEpiThreads + kProdThreads + 32;      // 544
-constexpr int kMmaWarp = kEpiWarps + kProdWarps;               // 16
+constexpr int kThreads = kEpiThreads + kProdThreads + 32;      // 416
+constexpr int kMmaWarp = kEpiWarps + kProdWarps;               // 12
 constexpr int kTileM = 128;
 constexpr int kChunkBytes = kTileM * 128;                      // one 32-float K chunk of a 128-row tile
 constexpr int kGroupCols = 256;                                // TMEM columns per tile group
@@ -68,6 +68,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "CH_WAIT_DONE:\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
+}
+// for waits that are expected to be long (a producer ahead of the ring): sleep between polls, the retry loop must not take
+// issue slots from the epilogue warps
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    asm volatile("nanosleep.u32 200;");
+  }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
@@ -145,24 +163,45 @@ struct ChainPlan {
   int any_stats;    // some step has a STATS operation
 };
 
-// y = accumulator + bias (+ the broadcast query row of the point this row belongs to), 32 columns of my row
-__device__ __forceinline__ void epi_prelude(const PdrChainEpi &op, int c0, size_t point, float (&y)[32],
-                                            const uint32_t (&v)[32]) {
+// One epilogue operation with everything a thread needs resolved ONCE per (tile, operation): the descriptor lives in the
+// kernel parameter block, and indexing it inside the unrolled column loops made ptxas reload every field per float4 group
+// (LDC + branch + 64-bit address arithmetic in front of every load; r02d: 870 SASS instructions per 32-column block).
+struct EpiOp {
+  int kind, d_col, ncols, a_col, stat_col0, stat_skip, v_col;
+  float lo1, lo2;                    // clamps of the prologue: (-inf, 0) GN->ReLU, (0, -inf) ReLU->GN
+  const float *bias, *rowadd, *sc, *sh, *emb, *v_bias, *v_sc, *v_sh;      // rows of THIS sample / point, or nullptr
+};
+__device__ __forceinline__ EpiOp resolve(const PdrChainEpi &op, int b, size_t point) {
+  EpiOp r;
+  r.kind = op.kind; r.d_col = op.d_col; r.ncols = op.ncols; r.a_col = op.a_col;
+  r.stat_col0 = op.stat_col0; r.stat_skip = op.stat_skip; r.v_col = op.v_col;
+  const float ninf = __int_as_float(0xff800000);
+  r.lo1 = op.pro_mode == PDR_PRO_RELU_GN ? 0.f : ninf;
+  r.lo2 = op.pro_mode == PDR_PRO_GN_RELU ? 0.f : ninf;
+  r.bias = op.bias;
+  r.rowadd = op.rowadd ? op.rowadd + point * (size_t)op.ld_rowadd : nullptr;
+  const bool pro = op.pro_mode != PDR_PRO_NONE && op.sc != nullptr;
+  r.sc = pro ? op.sc + (size_t)b * op.ld_scsh : nullptr;
+  r.sh = pro ? op.sh + (size_t)b * op.ld_scsh : nullptr;
+  r.emb = op.emb ? op.emb + (size_t)b * op.ld_emb : nullptr;
+  r.v_bias = op.v_bias;
+  r.v_sc = op.v_sc ? op.v_sc + (size_t)b * op.v_ld_scsh : nullptr;
+  r.v_sh = op.v_sh ? op.v_sh + (size_t)b * op.v_ld_scsh : nullptr;
+  return r;
+}
+// y = accumulator + bias (+ the broadcast query row of the point this row belongs to), 32 columns of my row, in place.
+// No column guards: every per-column array is readable, and zero, up to the end of its last 32-column block (header).
+__device__ __forceinline__ void epi_prelude(const EpiOp &op, int c0, float (&y)[32]) {
+  // (same association as the per-layer GEMM epilogue: y = acc + (bias + rowadd))
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    const int c = c0 + 4 * j4;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < op.ncols) {
-      if (op.bias) b = __ldg(reinterpret_cast<const float4 *>(op.bias + c));
-      if (op.rowadd) {
-        const float4 r = __ldg(reinterpret_cast<const float4 *>(op.rowadd + point * (size_t)op.ld_rowadd + c));
-        b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
-      }
+    if (op.bias) b = __ldg(reinterpret_cast<const float4 *>(op.bias + c0) + j4);
+    if (op.rowadd) {
+      const float4 r = __ldg(reinterpret_cast<const float4 *>(op.rowadd + c0) + j4);
+      b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
     }
-    y[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b.x;
-    y[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
-    y[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
-    y[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+    y[4 * j4 + 0] += b.x; y[4 * j4 + 1] += b.y; y[4 * j4 + 2] += b.z; y[4 * j4 + 3] += b.w;
   }
 }
 
@@ -215,29 +254,29 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     // =============================== PRODUCERS: gathered X0 tiles ================================
     const int ptid = tid - kEpiThreads;
     const int piece = ptid & 7;       // 16-byte piece of the 128-byte chunk row
-    const int arow = ptid >> 3;       // rows arow + 32 i
+    const int arow = ptid >> 3;       // rows arow + 16 i, i < 8 ((arow + 16 i) & 7 == arow & 7)
     const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ (arow & 7)) << 4));
     int slot = 0, phase = 0;
     for (int i = 0; i < n_my; ++i) {
       const int tile = t_lo + i;
       const size_t row0 = (size_t)tile * kTileM + arow;             // rows_per_sample % 128 == 0: tiles are dense
-      int idx[4];
+      int idx[8];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) idx[r] = __ldg(a.src_rows + row0 + 32 * r);
-      mbar_wait(&bar_empty[slot], (uint32_t)(phase ^ 1));
+      for (int r = 0; r < 8; ++r) idx[r] = __ldg(a.src_rows + row0 + 16 * r);
+      mbar_wait_sleep(&bar_empty[slot], (uint32_t)(phase ^ 1));
       const uint32_t sbase = smem_u32(s_x0 + (size_t)slot * slot_bytes) + sw_off;
       for (int kc = 0; kc < plan.nk0; ++kc) {
         const int k = kc * 32 + piece * 4;
         const uint32_t dst = sbase + (uint32_t)kc * kChunkBytes;
         if (k < a.k_split) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-            cp_async16_ignore(dst + r * 4096, a.table + (size_t)max(idx[r], 0) * a.ld_table + k, idx[r] < 0);
+          for (int r = 0; r < 8; ++r)
+            cp_async16_ignore(dst + r * 2048, a.table + (size_t)max(idx[r], 0) * a.ld_table + k, idx[r] < 0);
         } else {
           const bool in = k < a.k0;
           const float *p = a.geo + row0 * (size_t)a.ld_geo + (in ? k - a.k_split : 0);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) cp_async16_ignore(dst + r * 4096, in ? p + (size_t)32 * r * a.ld_geo : a.geo, !in);
+          for (int r = 0; r < 8; ++r) cp_async16_ignore(dst + r * 2048, in ? p + (size_t)16 * r * a.ld_geo : a.geo, !in);
         }
       }
       cp_async_arrive_noinc(&bar_full[slot]);
@@ -304,7 +343,6 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * kGroupCols);
     float *scr = s_scratch[warp];
     uint32_t ph = 0u;
-    const float ninf = __int_as_float(0xff800000);
     for (int i = g; i < n_my; i += 2) {
       const int tile = t_lo + i;
       const int b = tile / plan.tiles_per_sample;
@@ -312,12 +350,15 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
       const size_t point = grow / (size_t)a.group_k;
       for (int s = 0; s < a.n_steps; ++s) {
         const PdrChainStep &st = a.steps[s];
+        const int n_epi = st.n_epi;
+        // resolve the first operation's pointers while the MMAs run
+        EpiOp op = resolve(st.epi[0], b, point);
         mbar_wait(&bar_mma_done[g], ph);
         ph ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         bool wrote_tmem = false, did_stats = false;
-        for (int e = 0; e < st.n_epi; ++e) {
-          const PdrChainEpi &op = st.epi[e];
+        for (int e = 0; e < n_epi; ++e) {
+          if (e > 0) op = resolve(st.epi[e], b, point);
           const int nblk = (op.ncols + 31) >> 5;
           for (int blk = 0; blk < nblk; ++blk) {
             const int c0 = blk * 32;
@@ -325,27 +366,23 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
             float y[32];
             tmem_ld32(tq + (uint32_t)(op.d_col + c0), v);
             tmem_wait_ld();
-            epi_prelude(op, c0, point, y, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+            epi_prelude(op, c0, y);
             if (op.kind == PDR_CHAIN_XFORM) {
               // t = pro(y) + emb -> TF32 -> the A operand of a later MMA (TMEM, lane = row, one column per channel)
-              const float lo1 = op.pro_mode == PDR_PRO_RELU_GN ? 0.f : ninf;
-              const float lo2 = op.pro_mode == PDR_PRO_GN_RELU ? 0.f : ninf;
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const int c = c0 + 4 * j4;
-                float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4, e4 = sc4;
-                if (c < op.ncols) {
-                  sc4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                  if (op.pro_mode != PDR_PRO_NONE) {
-                    sc4 = __ldg(reinterpret_cast<const float4 *>(op.sc + (size_t)b * op.ld_scsh + c));
-                    sh4 = __ldg(reinterpret_cast<const float4 *>(op.sh + (size_t)b * op.ld_scsh + c));
-                  }
-                  if (op.emb) e4 = __ldg(reinterpret_cast<const float4 *>(op.emb + (size_t)b * op.ld_emb + c));
+                float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = sh4;
+                if (op.sc) {
+                  sc4 = __ldg(reinterpret_cast<const float4 *>(op.sc + c0) + j4);
+                  sh4 = __ldg(reinterpret_cast<const float4 *>(op.sh + c0) + j4);
                 }
-                const float t0 = fmaxf(fmaf(fmaxf(y[4 * j4 + 0], lo1), sc4.x, sh4.x), lo2) + e4.x;
-                const float t1 = fmaxf(fmaf(fmaxf(y[4 * j4 + 1], lo1), sc4.y, sh4.y), lo2) + e4.y;
-                const float t2 = fmaxf(fmaf(fmaxf(y[4 * j4 + 2], lo1), sc4.z, sh4.z), lo2) + e4.z;
-                const float t3 = fmaxf(fmaf(fmaxf(y[4 * j4 + 3], lo1), sc4.w, sh4.w), lo2) + e4.w;
+                if (op.emb) e4 = __ldg(reinterpret_cast<const float4 *>(op.emb + c0) + j4);
+                const float t0 = fmaxf(fmaf(fmaxf(y[4 * j4 + 0], op.lo1), sc4.x, sh4.x), op.lo2) + e4.x;
+                const float t1 = fmaxf(fmaf(fmaxf(y[4 * j4 + 1], op.lo1), sc4.y, sh4.y), op.lo2) + e4.y;
+                const float t2 = fmaxf(fmaf(fmaxf(y[4 * j4 + 2], op.lo1), sc4.z, sh4.z), op.lo2) + e4.z;
+                const float t3 = fmaxf(fmaf(fmaxf(y[4 * j4 + 3], op.lo1), sc4.w, sh4.w), op.lo2) + e4.w;
                 v[4 * j4 + 0] = __float_as_uint(to_tf32(t0));
                 v[4 * j4 + 1] = __float_as_uint(to_tf32(t1));
                 v[4 * j4 + 2] = __float_as_uint(to_tf32(t2));
@@ -363,10 +400,10 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
               __syncwarp();
               float q0 = 0.f, q1 = 0.f;
               if (op.stat_skip & 1) {
-#pragma unroll 8
+#pragma unroll
                 for (int r = 0; r < 32; ++r) { const float p = fmaxf(scr[r * 36 + lane], 0.f); q0 += p; q1 = fmaf(p, p, q1); }
               } else {
-#pragma unroll 8
+#pragma unroll
                 for (int r = 0; r < 32; ++r) { const float t = scr[r * 36 + lane]; q0 += t; q1 = fmaf(t, t, q1); }
               }
               *reinterpret_cast<float2 *>(&s_part[g][quarter][op.stat_col0 + c0 + lane][0]) = make_float2(q0, q1);
@@ -412,13 +449,10 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
               __syncwarp();
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const int c = c0 + 4 * j4;
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = b4, sh4 = b4;
-                if (c < op.ncols) {
-                  if (op.v_bias) b4 = __ldg(reinterpret_cast<const float4 *>(op.v_bias + c));
-                  sc4 = __ldg(reinterpret_cast<const float4 *>(op.v_sc + (size_t)b * op.v_ld_scsh + c));
-                  sh4 = __ldg(reinterpret_cast<const float4 *>(op.v_sh + (size_t)b * op.v_ld_scsh + c));
-                }
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (op.v_bias) b4 = __ldg(reinterpret_cast<const float4 *>(op.v_bias + c0) + j4);
+                const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(op.v_sc + c0) + j4);
+                const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(op.v_sh + c0) + j4);
                 float4 w = *reinterpret_cast<const float4 *>(scr + lane * 36 + 4 * j4);
                 w.x *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]) + b4.x, sc4.x, sh4.x), 0.f);
                 w.y *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]) + b4.y, sc4.y, sh4.y), 0.f);
@@ -519,8 +553,8 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
     for (int e = 0; e < st.n_epi; ++e) {
       const PdrChainEpi &op = st.epi[e];
       const int padded = ceil_div(op.ncols, 32) * 32;
-      // (ncols need not be a multiple of 4: bias / sc / sh / emb / rowadd rows are read in float4 groups up to the next
-      //  multiple of 4, their pad entries are zero by the engine's layout rule, and the pad columns come out as zeros)
+      // (ncols need not be a multiple of 32: bias / sc / sh / emb / rowadd rows are read, unguarded, up to the end of their last
+      //  32-column block; the caller keeps them readable and zero there, so the pad columns come out as zeros)
       PDR_REQUIRE(op.kind >= PDR_CHAIN_XFORM && op.kind <= PDR_CHAIN_POOL && op.ncols > 0 &&
                       op.d_col >= 0 && op.d_col + padded <= kGroupCols,
                   "stage_chain: step %d epilogue operation %d is malformed", s, e);

@@ -350,16 +350,18 @@ class FusedDenoiser:
                    info={"bytes": nbytes, "flops": 2 * M * N * K, "M": M, "N": N, "K": K})
         return st
 
-    def gn(self, sources, gn_module, batch=None):
+    def gn(self, sources, gn_module, batch=None, pad=4):
         """sources: list of (Stats, col0, ncols, use_relu, mult).  Returns (sc View, sh View) with each source
-        padded to a multiple of 4 columns."""
+        padded to a multiple of `pad` columns (4; 32 for the consumers of pdr_stage_chain, which reads whole 32-column
+        blocks unguarded -- the pad entries are never written and stay zero)."""
+        rp = lambda c: (c + pad - 1) // pad * pad
         batch = self.B if batch is None else batch
         if isinstance(gn_module, MyGroupNorm):
             gnm, groups, gn_channels = gn_module.group_norm, gn_module.num_groups, gn_module.num_channels
         else:
             gnm, groups, gn_channels = gn_module, gn_module.num_groups, gn_module.num_channels
         channels = sum(s[2] for s in sources)
-        ld_out = sum(r4(s[2]) for s in sources)
+        ld_out = sum(rp(s[2]) for s in sources)
         sc, sh = self._zeros(batch, ld_out), self._zeros(batch, ld_out)
         a = GnArgs()
         off = 0
@@ -370,7 +372,7 @@ class FusedDenoiser:
             s.use_relu, s.rows, s.mult = int(use_relu), st.rows, float(mult)
             if st.g is not None:
                 st.g.stats_skip &= ~(2 if use_relu else 1)
-            off += r4(ncols)
+            off += rp(ncols)
         a.nsrc, a.batch, a.channels, a.gn_channels, a.groups = len(sources), batch, channels, gn_channels, groups
         gamma = gnm.weight.detach().float().contiguous()
         beta = gnm.bias.detach().float().contiguous()
@@ -668,26 +670,26 @@ class FusedDenoiser:
         bind = lambda nm, sc, sh: rt["gn"].__setitem__(nm, (sc.ptr, sh.ptr, sc.ld))
         # sweep 1: statistics of y1 and relu(key); then the per-point query path of AttentionModule
         st1 = sweep(1)
-        bind("y1", *self.gn([(st1, 0, c[0], False, 1.0)], layers[0][1]))
+        bind("y1", *self.gn([(st1, 0, c[0], False, 1.0)], layers[0][1], pad=32))
         Wq = _pack([(_conv_w(qconv), [(0, cq_in, r4(cq_in))])], dev)
         Q = self._mat(B * P, cq)
         assert query.rows == B * P
         stq = self.gemm(View(query.t, r4(cq_in), query.col0), Wq, _bias(qconv, cq, dev), Q, P, want_stats=True)
-        sc1, sh1 = self.gn([(stq, 0, cq, True, float(K)), (st1, CH.p32(c[0]), c_key, True, 1.0)], gn_w1)
-        bind("key", sc1.cols(r4(cq), r4(c_key)), sh1.cols(r4(cq), r4(c_key)))
-        YQ = self._mat(B * P, inter)
+        sc1, sh1 = self.gn([(stq, 0, cq, True, float(K)), (st1, CH.p32(c[0]), c_key, True, 1.0)], gn_w1, pad=32)
+        bind("key", sc1.cols(CH.p32(cq), CH.p32(c_key)), sh1.cols(CH.p32(cq), CH.p32(c_key)))
+        YQ = View(self._zeros(B * P, CH.p32(inter)), inter)            # rows read in whole 32-column blocks
         self.gemm(View(Q.t, r4(cq), 0), _pack([(w1, [(0, cq, r4(cq))])], dev), None, YQ, P, pro=PRO_RELU_GN,
                   scsh=(sc1.cols(0, r4(cq)), sh1.cols(0, r4(cq))))
         rt["rowadd"] = (YQ.ptr, YQ.ld)
         # sweep 2: statistics of y2 and relu(s1)
         st2 = sweep(2)
-        bind("y2", *self.gn([(st2, 0, c[1], False, 1.0)], layers[1][1]))
-        bind("s1", *self.gn([(st2, CH.p32(c[1]), inter, True, 1.0)], gn_w2))
+        bind("y2", *self.gn([(st2, 0, c[1], False, 1.0)], layers[1][1], pad=32))
+        bind("s1", *self.gn([(st2, CH.p32(c[1]), inter, True, 1.0)], gn_w2, pad=32))
         for d in range(3, L + 1):
             std = sweep(d)
-            bind("y%d" % d, *self.gn([(std, 0, c[d - 1], False, 1.0)], layers[d - 1][1]))
+            bind("y%d" % d, *self.gn([(std, 0, c[d - 1], False, 1.0)], layers[d - 1][1], pad=32))
         stv = sweep(L + 1)
-        bind("V", *self.gn([(stv, 0, c_out, False, 1.0)], gn_v))
+        bind("V", *self.gn([(stv, 0, c_out, False, 1.0)], gn_v, pad=32))
         sweep(L + 2)
         return True
 
@@ -766,8 +768,9 @@ class FusedDenoiser:
         for i, fp in enumerate(net.FP_modules):
             for nm, m in (("fp1", fp.mlp1), ("fp2", fp.mlp2)):
                 plans[(nm, i)] = self._register_embeddings(self._embedding_plan(m, len(self._mlp_layers(m))))
-        self.T_all = self._zeros(B, max(r4(self.t_cols), 4))
-        self.C_all = self._zeros(B, max(r4(self.c_cols), 4))
+        # (+ 32 zero columns: pdr_stage_chain reads an embedding slice up to the end of its last 32-column block)
+        self.T_all = self._zeros(B, max(r4(self.t_cols), 4) + 32)
+        self.C_all = self._zeros(B, max(r4(self.c_cols), 4) + 32)
         no_emb2 = [None, None]
 
         # ---- static inputs / condition tensors (channels-last) -----------------------------------------

@@ -86,7 +86,7 @@ def test_every_sweep_against_the_emulator(case):
                 gam, bet, groups = gn[name]
                 sc, sh = _gn_affine(st[:, :, 2 if relu else 0], st[:, :, 3 if relu else 1], rps, gam, bet, groups)
                 host["gn"][name] = (sc, sh)
-                ld = CH.r4(nc) + 4
+                ld = CH.p32(nc) + 4              # read in whole 32-column blocks: zero padded
                 d_sc, d_sh = torch.zeros(B, ld, device=dev), torch.zeros(B, ld, device=dev)
                 d_sc[:, :nc], d_sh[:, :nc] = up(sc), up(sh)
                 keep += [d_sc, d_sh]
