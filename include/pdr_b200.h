@@ -110,6 +110,13 @@ int pdr_chamfer_f1(int b, int n, int m, const float *xyz1, const float *xyz2, fl
 int pdr_nm_distance(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
                     int *idx1, float *dist2, int *idx2, void *stream);
 
+/* Backward of NmDistance (chamfer_cuda_backward, chamfer3D.cu:155-196): grad_xyz1 (b,n,3), grad_xyz2 (b,m,3) from the
+ * gradients of dist1 (b,n) / dist2 (b,m) and the saved argmin indices.  Fully written (no memset needed); the scatter
+ * term is accumulated in index order instead of by atomicAdd, so the result is deterministic. */
+int pdr_nm_distance_grad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *grad_dist1,
+                         const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
+                         float *grad_xyz2, void *stream);
+
 /* ---- emd_cuda (PytorchEMD/cuda/emd_kernel.cu) -------------------------------------------------- */
 
 /* temp: pdr_emd_workspace_bytes(b,n,m) bytes of device scratch (the reference allocates

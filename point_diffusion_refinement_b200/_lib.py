@@ -39,6 +39,7 @@ SIGNATURES = {
     "pdr_chamfer_f1": [_c_int, _c_int, _c_int, _ptr, _ptr, _c_float, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                        _c_size_t, _ptr],
     "pdr_nm_distance": [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "pdr_nm_distance_grad": [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "pdr_emd_workspace_bytes": [_c_int, _c_int, _c_int],
     "pdr_emd_approxmatch": [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_size_t, _ptr],
     "pdr_emd_matchcost": [_c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_size_t, _ptr],

@@ -29,6 +29,7 @@ XFORM, STATS, POOL = 1, 2, 3
 PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
 GROUP_COLS = 256          # TMEM columns of one tile group (stage_chain.cu kGroupCols)
 MAX_STAT_COLS = 128
+MAX_CONST_COLS = 512       # 32-padded columns of all epilogue operations of one sweep (stage_chain.cu kConstCols)
 TILE_ROWS = 128
 
 
@@ -195,15 +196,19 @@ class StagePlan:
         for l in range(1, s.L):
             self.b["y%d" % (l + 1)] = _pad_bias(s.mlp[l][1], s.c[l], device)
 
-    def smem_bytes(self, slots=2):
-        """Dynamic shared memory of a launch with `slots` X0 tiles in the ring (+ alignment slack)."""
-        return 1024 + self.image.bytes + slots * (self.k0p // 32) * TILE_ROWS * 128
+    def smem_bytes(self, slots=2, wpg=4):
+        """Dynamic shared memory of a launch with `slots` X0 tiles in the ring and `wpg` epilogue warps per tile group
+        (stage_chain.cu: transposition tiles + weight image + ring, + alignment slack)."""
+        return 2048 + 2 * wpg * 32 * 36 * 4 + self.image.bytes + slots * (self.k0p // 32) * TILE_ROWS * 128
 
     def fits(self):
-        """Shared memory (weights + at least two X0 tiles), statistics columns per sweep and MMA widths within the kernel's limits."""
-        static = 4 * (8 * 32 * 36 + 2 * 4 * MAX_STAT_COLS * 2) + 512
+        """Shared memory (weights + at least two X0 tiles with 4 epilogue warps per group), statistics columns, folded-constant
+        columns and MMA widths within the kernel's limits."""
+        static = 4 * (2 * 4 * MAX_STAT_COLS * 2 + 2 * MAX_CONST_COLS * 3) + 1024
         s = self.spec
-        return (self.smem_bytes(2) <= 226 * 1024 - static and p32(s.c[0]) + p32(s.ck) <= 256
+        const_cols = 2 * p32(s.co) + sum(p32(c) for c in s.c) + p32(s.ck) + p32(s.ci)       # the last sweep holds them all
+        return (self.smem_bytes(2, 4) <= 226 * 1024 - static and p32(s.c[0]) + p32(s.ck) <= 256
+                and const_cols <= MAX_CONST_COLS
                 and all(self.sweep_stats_n(d) <= MAX_STAT_COLS for d in range(1, s.L + 2)))
 
     # ---- step programs --------------------------------------------------------------------------------

@@ -357,6 +357,71 @@ extern "C" int pdr_chamfer_f1(int b, int n, int m, const float *xyz1, const floa
   return check_launch("chamfer_finalize_kernel");
 }
 
+namespace pdr {
+namespace {
+// Backward of NmDistance (chamfer3D.cu:155-174, called twice by chamfer_cuda_backward :176-196): for the points A of
+// one cloud, grad_A[j] = 2 g_a[j] (A_j - B_{idx_a[j]})  -  sum_{k : idx_b[k] == j} 2 g_b[k] (B_k - A_j).
+// The reference scatters the second term with atomicAdd (order of the additions undefined); here a thread owns one
+// output point and walks the other cloud's index list in order: deterministic, no atomics, O(n m) integer compares.
+constexpr int kNmGradThreads = 256, kNmGradTile = 2048;
+__global__ void __launch_bounds__(kNmGradThreads)
+nm_distance_grad_kernel(int na, int nb, const float *__restrict__ A_all, const float *__restrict__ B_all,
+                        const float *__restrict__ ga_all, const int *__restrict__ idxa_all,
+                        const float *__restrict__ gb_all, const int *__restrict__ idxb_all, float *__restrict__ grad_all) {
+  __shared__ int s_idx[kNmGradTile];
+  __shared__ float4 s_b[kNmGradTile];         // (B_k, 2 g_b[k])
+  const int cloud = blockIdx.y;
+  const float *A = A_all + (size_t)cloud * na * 3, *B = B_all + (size_t)cloud * nb * 3;
+  const int j = blockIdx.x * kNmGradThreads + threadIdx.x;
+  const bool on = j < na;
+  const int jj = on ? j : na - 1;
+  const float ax = __ldg(A + jj * 3), ay = __ldg(A + jj * 3 + 1), az = __ldg(A + jj * 3 + 2);
+  float gx, gy, gz;
+  {
+    const int j2 = __ldg(idxa_all + (size_t)cloud * na + jj);
+    const float g = __ldg(ga_all + (size_t)cloud * na + jj) * 2.f;
+    gx = g * (ax - __ldg(B + j2 * 3)); gy = g * (ay - __ldg(B + j2 * 3 + 1)); gz = g * (az - __ldg(B + j2 * 3 + 2));
+  }
+  for (int k0 = 0; k0 < nb; k0 += kNmGradTile) {
+    const int cnt = min(kNmGradTile, nb - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += kNmGradThreads) {
+      const int k = k0 + i;
+      s_idx[i] = __ldg(idxb_all + (size_t)cloud * nb + k);
+      s_b[i] = make_float4(__ldg(B + k * 3), __ldg(B + k * 3 + 1), __ldg(B + k * 3 + 2),
+                           __ldg(gb_all + (size_t)cloud * nb + k) * 2.f);
+    }
+    __syncthreads();
+    for (int i = 0; i < cnt; ++i) {
+      if (s_idx[i] == j) {
+        const float4 p = s_b[i];
+        gx += -(p.w * (p.x - ax)); gy += -(p.w * (p.y - ay)); gz += -(p.w * (p.z - az));
+      }
+    }
+  }
+  if (on) {
+    float *o = grad_all + ((size_t)cloud * na + j) * 3;
+    o[0] = gx; o[1] = gy; o[2] = gz;
+  }
+}
+}  // namespace
+}  // namespace pdr
+
+extern "C" int pdr_nm_distance_grad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *grad_dist1,
+                                    const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
+                                    float *grad_xyz2, void *stream) {
+  PDR_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "nm_distance_grad: bad sizes b=%d n=%d m=%d", b, n, m);
+  if (b == 0) return PDR_OK;
+  PDR_REQUIRE(xyz1 && xyz2 && grad_dist1 && idx1 && grad_dist2 && idx2 && grad_xyz1 && grad_xyz2, "nm_distance_grad: null pointer");
+  nm_distance_grad_kernel<<<dim3(ceil_div(n, kNmGradThreads), b), kNmGradThreads, 0, (cudaStream_t)stream>>>(
+      n, m, xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1);
+  int rc = check_launch("nm_distance_grad_kernel<1>");
+  if (rc) return rc;
+  nm_distance_grad_kernel<<<dim3(ceil_div(m, kNmGradThreads), b), kNmGradThreads, 0, (cudaStream_t)stream>>>(
+      m, n, xyz2, xyz1, grad_dist2, idx2, grad_dist1, idx1, grad_xyz2);
+  return check_launch("nm_distance_grad_kernel<2>");
+}
+
 extern "C" int pdr_nm_distance(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1,
                                int *idx1, float *dist2, int *idx2, void *stream) {
   PDR_REQUIRE(b >= 0 && n >= 1 && m >= 1 && b <= 65535, "nm_distance: bad sizes b=%d n=%d m=%d", b, n, m);

@@ -27,13 +27,19 @@
 // memory in the canonical K-major SWIZZLE_128B layout; D = TMEM columns) followed by a list of epilogue operations
 // (XFORM / STATS / POOL over blocks of 32 accumulator columns).
 //
-// Persistent, warp-specialised, one CTA of 416 threads per SM, every CTA a contiguous range of row tiles:
-//   warps 0..7   epilogue: two GROUPS of four warps (one warp per TMEM lane quarter); group g owns the tiles g, g+2, ...
-//                of the CTA's range and TMEM columns [256 g, 256 g + 256), so two tiles are in flight and one group's
-//                epilogue overlaps the other group's MMAs.
-//   warps 8..11  producers: cp.async of the gathered X0 rows (table row + geometric channels) into a ring of
-//                SWIZZLE_128B tiles, completion by cp.async.mbarrier.arrive.
-//   warp 12      MMA issue (one lane): walks both groups' step programs in lock step.
+// Persistent, warp-specialised, one CTA per SM, every CTA a contiguous range of row tiles.  With W = 8 (or 4 when shared
+// memory is short) epilogue warps per tile group:
+//   warps [0, 2W)      epilogue: two GROUPS; group g owns the tiles g, g+2, ... of the CTA's range and TMEM columns
+//                      [256 g, 256 g + 256), so two tiles are in flight and one group's epilogue overlaps the other group's
+//                      MMAs.  W / 4 warps share a TMEM lane quarter and take alternate 32-column blocks of a step.
+//                      The per-column constants of every operation (GroupNorm scale / shift with the bias folded in,
+//                      embeddings) are folded ONCE per sample into a shared-memory table by the group itself.
+//   warps [2W, 2W+4)   producers: cp.async of the gathered X0 rows (table row + geometric channels) into a ring of
+//                      SWIZZLE_128B tiles, completion by cp.async.mbarrier.arrive.
+//   warp 2W+4          MMA issue (one lane): walks both groups' step programs in lock step.
+// (First version, r02d/r02e profiles: 4 warps per group re-reading the operation descriptors from the constant bank and
+//  their constants from global memory for every float4 -- 870, then 318 SASS instructions per 32-column block and an
+//  issue rate of 0.2 per epilogue warp; this version: ~120 instructions per block and twice the warps.)
 #include <stdlib.h>
 #include <string.h>
 
@@ -42,16 +48,17 @@
 namespace pdr {
 namespace {
 
-constexpr int kEpiWarps = 8, kProdWarps = 4;
-constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
-constexpr int kThreads = kEpiThreads + kProdThreads + 32;      // 416
-constexpr int kMmaWarp = kEpiWarps + kProdWarps;               // 12
+constexpr int kProdWarps = 4, kProdThreads = kProdWarps * 32;
+constexpr int kMaxWpg = 8;                                     // epilogue warps per tile group (4 or 8)
+constexpr int kMaxThreads = (2 * kMaxWpg + kProdWarps + 1) * 32;   // 672
 constexpr int kTileM = 128;
 constexpr int kChunkBytes = kTileM * 128;                      // one 32-float K chunk of a 128-row tile
 constexpr int kGroupCols = 256;                                // TMEM columns per tile group
 constexpr int kMaxSlots = 8;
 constexpr int kMaxStatCols = 128;                              // statistics columns per sweep
-constexpr int kScratchFloats = 32 * 36;                        // per-warp transposition tile (rows x 36 floats)
+constexpr int kScratchBytes = 32 * 36 * 4;                     // per-warp transposition tile (32 rows x 36 floats)
+constexpr int kConstCols = 512;                                // 32-padded columns of all operations of a sweep
+constexpr int kMaxOps = PDR_CHAIN_MAX_STEPS * PDR_CHAIN_MAX_EPI;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -154,78 +161,90 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// explicit shared-space accesses for the transposition tiles (they live in the dynamic region: through a generic pointer
+// these would be LD.E / ST.E at ~3x the latency)
+__device__ __forceinline__ float lds1(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 struct ChainPlan {
   int tiles_per_sample, total_tiles;
   int nk0;          // 32-float K chunks of the gathered X0 tile
   int slots;        // ring depth
   int w_region;     // bytes reserved for the weight image (multiple of 1024)
-  int any_stats;    // some step has a STATS operation
+  int wpg;          // epilogue warps per tile group (4 or 8)
 };
 
-// One epilogue operation with everything a thread needs resolved ONCE per (tile, operation): the descriptor lives in the
-// kernel parameter block, and indexing it inside the unrolled column loops made ptxas reload every field per float4 group
-// (LDC + branch + 64-bit address arithmetic in front of every load; r02d: 870 SASS instructions per 32-column block).
-struct EpiOp {
-  int kind, d_col, ncols, a_col, stat_col0, stat_skip, v_col;
-  float lo1, lo2;                    // clamps of the prologue: (-inf, 0) GN->ReLU, (0, -inf) ReLU->GN
-  const float *bias, *rowadd, *sc, *sh, *emb, *v_bias, *v_sc, *v_sh;      // rows of THIS sample / point, or nullptr
-};
-__device__ __forceinline__ EpiOp resolve(const PdrChainEpi &op, int b, size_t point) {
-  EpiOp r;
-  r.kind = op.kind; r.d_col = op.d_col; r.ncols = op.ncols; r.a_col = op.a_col;
-  r.stat_col0 = op.stat_col0; r.stat_skip = op.stat_skip; r.v_col = op.v_col;
-  const float ninf = __int_as_float(0xff800000);
-  r.lo1 = op.pro_mode == PDR_PRO_RELU_GN ? 0.f : ninf;
-  r.lo2 = op.pro_mode == PDR_PRO_GN_RELU ? 0.f : ninf;
-  r.bias = op.bias;
-  r.rowadd = op.rowadd ? op.rowadd + point * (size_t)op.ld_rowadd : nullptr;
-  const bool pro = op.pro_mode != PDR_PRO_NONE && op.sc != nullptr;
-  r.sc = pro ? op.sc + (size_t)b * op.ld_scsh : nullptr;
-  r.sh = pro ? op.sh + (size_t)b * op.ld_scsh : nullptr;
-  r.emb = op.emb ? op.emb + (size_t)b * op.ld_emb : nullptr;
-  r.v_bias = op.v_bias;
-  r.v_sc = op.v_sc ? op.v_sc + (size_t)b * op.v_ld_scsh : nullptr;
-  r.v_sh = op.v_sh ? op.v_sh + (size_t)b * op.v_ld_scsh : nullptr;
-  return r;
-}
-// y = accumulator + bias (+ the broadcast query row of the point this row belongs to), 32 columns of my row, in place.
-// No column guards: every per-column array is readable, and zero, up to the end of its last 32-column block (header).
-__device__ __forceinline__ void epi_prelude(const EpiOp &op, int c0, float (&y)[32]) {
-  // (same association as the per-layer GEMM epilogue: y = acc + (bias + rowadd))
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (op.bias) b = __ldg(reinterpret_cast<const float4 *>(op.bias + c0) + j4);
-    if (op.rowadd) {
-      const float4 r = __ldg(reinterpret_cast<const float4 *>(op.rowadd + c0) + j4);
-      b.x += r.x; b.y += r.y; b.z += r.z; b.w += r.w;
-    }
-    y[4 * j4 + 0] += b.x; y[4 * j4 + 1] += b.y; y[4 * j4 + 2] += b.z; y[4 * j4 + 3] += b.w;
+// Folded per-column constants of one operation for one sample: three arrays of 32 floats per 32-column block,
+//   XFORM GN->ReLU :  t = max(fma(acc, c0, c1), 0) + c2        c0 = sc, c1 = sh + bias sc, c2 = emb
+//   XFORM ReLU->GN :  t = fma(max(acc + c0 [+ rowadd], 0), c1, c2)   c0 = bias, c1 = sc, c2 = sh + emb
+//   XFORM none     :  t = acc + c0 [+ rowadd] + c2                c0 = bias, c2 = emb
+//   STATS          :  y = acc + c0 [+ rowadd]
+//   POOL           :  score = acc + c0;  value = max(fma(acc_v, c1, c2), 0)     c1 = v_sc, c2 = v_sh + v_bias v_sc
+// (columns >= ncols: zeros, so pad columns of an XFORM come out as zeros)
+__device__ __forceinline__ void fold_constants(const PdrChainEpi &op, int b, int c, float &c0, float &c1, float &c2) {
+  c0 = c1 = c2 = 0.f;
+  if (c >= op.ncols) return;
+  const float bias = op.bias ? __ldg(op.bias + c) : 0.f;
+  if (op.kind == PDR_CHAIN_XFORM) {
+    const bool pro = op.pro_mode != PDR_PRO_NONE;
+    const float sc = pro ? __ldg(op.sc + (size_t)b * op.ld_scsh + c) : 1.f;
+    const float sh = pro ? __ldg(op.sh + (size_t)b * op.ld_scsh + c) : 0.f;
+    const float e = op.emb ? __ldg(op.emb + (size_t)b * op.ld_emb + c) : 0.f;
+    if (op.pro_mode == PDR_PRO_GN_RELU) { c0 = sc; c1 = fmaf(bias, sc, sh); c2 = e; }
+    else if (op.pro_mode == PDR_PRO_RELU_GN) { c0 = bias; c1 = sc; c2 = sh + e; }
+    else { c0 = bias; c2 = e; }
+  } else if (op.kind == PDR_CHAIN_STATS) {
+    c0 = bias;
+  } else {
+    const float vb = op.v_bias ? __ldg(op.v_bias + c) : 0.f;
+    const float sc = __ldg(op.v_sc + (size_t)b * op.v_ld_scsh + c);
+    const float sh = __ldg(op.v_sh + (size_t)b * op.v_ld_scsh + c);
+    c0 = bias; c1 = sc; c2 = fmaf(vb, sc, sh);
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(96)
 stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[kMaxSlots], bar_empty[kMaxSlots], bar_mma_done[2], bar_epi_done[2];
   __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(16) float s_scratch[kEpiWarps][kScratchFloats];        // per-warp transposition tile (stats, pooling)
   __shared__ __align__(16) float s_part[2][4][kMaxStatCols][2];              // per group / lane quarter column partials
-
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *s_w = smem;                                   // weight image
-  uint8_t *s_x0 = smem + plan.w_region;                  // ring of gathered X0 tiles
-  const uint32_t slot_bytes = (uint32_t)plan.nk0 * kChunkBytes;
+  __shared__ __align__(16) float s_const[2][kConstCols * 3];                 // per group: folded constants of one sample
+  __shared__ int s_coff[kMaxOps + 1];                                        // first 32-column block of every operation
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wpg = plan.wpg;
+  const int n_epi_warps = 2 * wpg, mma_warp = n_epi_warps + kProdWarps;
+  const int nthreads = (mma_warp + 1) * 32;
+
+  // dynamic region: [transposition tiles 2 wpg x 4608 B][weight image][ring of X0 tiles], 1 KiB aligned
+  const uint32_t dyn0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_scr_u = dyn0;
+  const uint32_t s_w_u = (dyn0 + (uint32_t)(n_epi_warps * kScratchBytes) + 1023u) & ~1023u;
+  const uint32_t s_x0_u = s_w_u + (uint32_t)plan.w_region;
+  uint8_t *s_w = smem_raw + (s_w_u - smem_u32(smem_raw));
+  const uint32_t slot_bytes = (uint32_t)plan.nk0 * kChunkBytes;
 
   if (tid == 0) {
     for (int s = 0; s < plan.slots; ++s) { mbar_init(&bar_full[s], kProdThreads); mbar_init(&bar_empty[s], 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(&bar_mma_done[g], 1); mbar_init(&bar_epi_done[g], kEpiThreads / 2); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&bar_mma_done[g], 1); mbar_init(&bar_epi_done[g], (uint32_t)(wpg * 32)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int off = 0;
+    for (int s = 0; s < a.n_steps; ++s)
+      for (int e = 0; e < PDR_CHAIN_MAX_EPI; ++e) {
+        s_coff[s * PDR_CHAIN_MAX_EPI + e] = off;
+        if (e < a.steps[s].n_epi) off += (a.steps[s].epi[e].ncols + 31) >> 5;
+      }
   }
-  if (warp == kMmaWarp) {
+  if (warp == mma_warp) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                  "r"(512u)
@@ -236,7 +255,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(a.w_image);
     uint4 *dst = reinterpret_cast<uint4 *>(s_w);
-    for (int i = tid; i < a.w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < a.w_bytes / 16; i += nthreads) dst[i] = __ldg(src + i);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -250,9 +269,9 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
   const int t_lo = cta * base_n + min(cta, rem);
   const int n_my = base_n + (cta < rem ? 1 : 0);
 
-  if (warp >= kEpiWarps && warp < kMmaWarp) {
+  if (warp >= n_epi_warps && warp < mma_warp) {
     // =============================== PRODUCERS: gathered X0 tiles ================================
-    const int ptid = tid - kEpiThreads;
+    const int ptid = tid - n_epi_warps * 32;
     const int piece = ptid & 7;       // 16-byte piece of the 128-byte chunk row
     const int arow = ptid >> 3;       // rows arow + 16 i, i < 8 ((arow + 16 i) & 7 == arow & 7)
     const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ (arow & 7)) << 4));
@@ -264,7 +283,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
 #pragma unroll
       for (int r = 0; r < 8; ++r) idx[r] = __ldg(a.src_rows + row0 + 16 * r);
       mbar_wait_sleep(&bar_empty[slot], (uint32_t)(phase ^ 1));
-      const uint32_t sbase = smem_u32(s_x0 + (size_t)slot * slot_bytes) + sw_off;
+      const uint32_t sbase = s_x0_u + (uint32_t)slot * slot_bytes + sw_off;
       for (int kc = 0; kc < plan.nk0; ++kc) {
         const int k = kc * 32 + piece * 4;
         const uint32_t dst = sbase + (uint32_t)kc * kChunkBytes;
@@ -282,7 +301,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
       cp_async_arrive_noinc(&bar_full[slot]);
       if (++slot == plan.slots) { slot = 0; phase ^= 1; }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == mma_warp) {
     // =============================== MMA ISSUER ==================================================
     // both tile groups in lock step: step s of tile 2j (group 0), step s of tile 2j + 1 (group 1), step s + 1 ...
     uint32_t ph_epi[2] = {0u, 0u};
@@ -307,8 +326,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (lane == 0) {
             const uint32_t tg = tmem_base + (uint32_t)(g * kGroupCols);
-            const uint32_t x0 = smem_u32(s_x0 + (size_t)slot * slot_bytes);
-            const uint32_t wb = smem_u32(s_w);
+            const uint32_t x0 = s_x0_u + (uint32_t)slot * slot_bytes;
             for (int m = 0; m < st.n_mma; ++m) {
               const PdrChainMma &op = st.mma[m];
               const uint32_t idesc = kIdescBase | ((uint32_t)(op.n >> 3) << 17);
@@ -316,7 +334,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
               for (int kk = 0; kk < op.k; kk += 8) {
                 const int kw = op.w_k0 + kk;
                 const uint64_t bdesc =
-                    make_desc(wb + (uint32_t)op.w_off + (uint32_t)(kw >> 5) * (uint32_t)op.w_rows * 128u +
+                    make_desc(s_w_u + (uint32_t)op.w_off + (uint32_t)(kw >> 5) * (uint32_t)op.w_rows * 128u +
                               (uint32_t)op.w_row0 * 128u) + (uint64_t)((kw & 31) >> 2);
                 const uint32_t acc = (kk > 0 || op.accumulate) ? 1u : 0u;
                 if (op.a_tmem) {
@@ -337,142 +355,188 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     }
   } else {
     // =============================== EPILOGUE ====================================================
-    const int g = warp >> 2, quarter = warp & 3;
-    const int gtid = tid & (kEpiThreads / 2 - 1);            // thread index inside the group
+    const int g = warp / wpg, wi = warp - g * wpg;
+    const int quarter = wi & 3, half = wi >> 2, halves = wpg >> 2;
+    const int gthreads = wpg * 32;
+    const int gtid = tid - g * gthreads;                     // thread index inside the group
     const int gbar = 1 + g;                                  // named barrier of the group
     const uint32_t tq = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * kGroupCols);
-    float *scr = s_scratch[warp];
+    const uint32_t scr = s_scr_u + (uint32_t)warp * kScratchBytes;
+    const uint32_t scr_row = scr + (uint32_t)lane * 144u;    // my row of the transposition tile (lane = row)
+    const uint32_t scr_col = scr + (uint32_t)lane * 4u;      // my column (lane = column)
+    const float *cg = s_const[g];
     uint32_t ph = 0u;
+    int cached_b = -1;
     for (int i = g; i < n_my; i += 2) {
       const int tile = t_lo + i;
       const int b = tile / plan.tiles_per_sample;
       const size_t grow = (size_t)tile * kTileM + quarter * 32 + lane;     // my global grouped row
       const size_t point = grow / (size_t)a.group_k;
+      if (b != cached_b) {
+        // fold this sample's per-column constants of every operation of the sweep (once per sample and group)
+        asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(gthreads) : "memory");
+        for (int s = 0; s < a.n_steps; ++s)
+          for (int e = 0; e < a.steps[s].n_epi; ++e) {
+            const PdrChainEpi &op = a.steps[s].epi[e];
+            const int blk0 = s_coff[s * PDR_CHAIN_MAX_EPI + e];
+            const int ncp = ((op.ncols + 31) >> 5) << 5;
+            for (int c = gtid; c < ncp; c += gthreads) {
+              float c0, c1, c2;
+              fold_constants(op, b, c, c0, c1, c2);
+              float *dst = s_const[g] + (blk0 + (c >> 5)) * 96 + (c & 31);
+              dst[0] = c0; dst[32] = c1; dst[64] = c2;
+            }
+          }
+        asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(gthreads) : "memory");
+        cached_b = b;
+      }
       for (int s = 0; s < a.n_steps; ++s) {
         const PdrChainStep &st = a.steps[s];
         const int n_epi = st.n_epi;
-        // resolve the first operation's pointers while the MMAs run
-        EpiOp op = resolve(st.epi[0], b, point);
         mbar_wait(&bar_mma_done[g], ph);
         ph ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         bool wrote_tmem = false, did_stats = false;
+        int unit = 0;
         for (int e = 0; e < n_epi; ++e) {
-          if (e > 0) op = resolve(st.epi[e], b, point);
-          const int nblk = (op.ncols + 31) >> 5;
-          for (int blk = 0; blk < nblk; ++blk) {
+          const PdrChainEpi &opd = st.epi[e];
+          // the handful of fields the block loops need, read once per operation
+          const int kind = opd.kind, d_col = opd.d_col, ncols = opd.ncols, pro_mode = opd.pro_mode;
+          const int nblk = (ncols + 31) >> 5;
+          const float *rowadd = opd.rowadd ? opd.rowadd + point * (size_t)opd.ld_rowadd : nullptr;
+          const float *cop = cg + s_coff[s * PDR_CHAIN_MAX_EPI + e] * 96;
+          wrote_tmem |= kind == PDR_CHAIN_XFORM;
+          did_stats |= kind == PDR_CHAIN_STATS;
+          for (int blk = 0; blk < nblk; ++blk, ++unit) {
+            if (halves > 1 && (unit & 1) != half) continue;
             const int c0 = blk * 32;
+            const float *cb = cop + blk * 96;
             uint32_t v[32];
-            float y[32];
-            tmem_ld32(tq + (uint32_t)(op.d_col + c0), v);
+            tmem_ld32(tq + (uint32_t)(d_col + c0), v);
+            // the broadcast query row of my point (rows are read in whole 32-column blocks: zero padded by the caller)
+            float4 ra[8];
+            if (rowadd) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) ra[j4] = __ldg(reinterpret_cast<const float4 *>(rowadd + c0) + j4);
+            }
             tmem_wait_ld();
+            if (kind == PDR_CHAIN_XFORM) {
+              // -> TF32 A operand of a later MMA (TMEM, lane = row, one column per channel)
+              if (pro_mode == PDR_PRO_GN_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
-            epi_prelude(op, c0, y);
-            if (op.kind == PDR_CHAIN_XFORM) {
-              // t = pro(y) + emb -> TF32 -> the A operand of a later MMA (TMEM, lane = row, one column per channel)
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sh4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = sh4;
-                if (op.sc) {
-                  sc4 = __ldg(reinterpret_cast<const float4 *>(op.sc + c0) + j4);
-                  sh4 = __ldg(reinterpret_cast<const float4 *>(op.sh + c0) + j4);
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 k0 = *reinterpret_cast<const float4 *>(cb + 4 * j4);
+                  const float4 k1 = *reinterpret_cast<const float4 *>(cb + 32 + 4 * j4);
+                  const float4 k2 = *reinterpret_cast<const float4 *>(cb + 64 + 4 * j4);
+                  v[4 * j4 + 0] = __float_as_uint(to_tf32(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), k0.x, k1.x), 0.f) + k2.x));
+                  v[4 * j4 + 1] = __float_as_uint(to_tf32(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), k0.y, k1.y), 0.f) + k2.y));
+                  v[4 * j4 + 2] = __float_as_uint(to_tf32(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), k0.z, k1.z), 0.f) + k2.z));
+                  v[4 * j4 + 3] = __float_as_uint(to_tf32(fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), k0.w, k1.w), 0.f) + k2.w));
                 }
-                if (op.emb) e4 = __ldg(reinterpret_cast<const float4 *>(op.emb + c0) + j4);
-                const float t0 = fmaxf(fmaf(fmaxf(y[4 * j4 + 0], op.lo1), sc4.x, sh4.x), op.lo2) + e4.x;
-                const float t1 = fmaxf(fmaf(fmaxf(y[4 * j4 + 1], op.lo1), sc4.y, sh4.y), op.lo2) + e4.y;
-                const float t2 = fmaxf(fmaf(fmaxf(y[4 * j4 + 2], op.lo1), sc4.z, sh4.z), op.lo2) + e4.z;
-                const float t3 = fmaxf(fmaf(fmaxf(y[4 * j4 + 3], op.lo1), sc4.w, sh4.w), op.lo2) + e4.w;
-                v[4 * j4 + 0] = __float_as_uint(to_tf32(t0));
-                v[4 * j4 + 1] = __float_as_uint(to_tf32(t1));
-                v[4 * j4 + 2] = __float_as_uint(to_tf32(t2));
-                v[4 * j4 + 3] = __float_as_uint(to_tf32(t3));
-              }
-              tmem_st32(tq + (uint32_t)(op.a_col + c0), v);
-              wrote_tmem = true;
-            } else if (op.kind == PDR_CHAIN_STATS) {
-              // per-tile column statistics of y: park my row, read the tile back column-wise (lane = column).  Every
-              // consumer reads ONE of the two pairs (plain or relu), stat_skip says which one is not needed.
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4)
-                *reinterpret_cast<float4 *>(scr + lane * 36 + 4 * j4) =
-                    make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
-              __syncwarp();
-              float q0 = 0.f, q1 = 0.f;
-              if (op.stat_skip & 1) {
-#pragma unroll
-                for (int r = 0; r < 32; ++r) { const float p = fmaxf(scr[r * 36 + lane], 0.f); q0 += p; q1 = fmaf(p, p, q1); }
               } else {
+                // ReLU -> GN (or no prologue: k1 would be 1 -- not used by any stage; handled as scale 1 by the fold)
+                const bool relu = pro_mode == PDR_PRO_RELU_GN;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) { const float t = scr[r * 36 + lane]; q0 += t; q1 = fmaf(t, t, q1); }
-              }
-              *reinterpret_cast<float2 *>(&s_part[g][quarter][op.stat_col0 + c0 + lane][0]) = make_float2(q0, q1);
-              did_stats = true;
-              __syncwarp();
-            } else {
-              // soft-attention pooling over the group_k neighbour rows of each point (attention.py:85-96): scores = y,
-              // values = relu(GN(V accumulator + bias)).  One transposition tile, three phases:
-              //   (1) lane = row parks its scores; lane = column takes the masked maximum and the denominator of each
-              //       point and leaves exp(score - max) in place;
-              //   (2) lane = row multiplies its row of weights with its values (TMEM) in place;
-              //   (3) lane = column adds the group_k products of each point and divides.
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4)
-                *reinterpret_cast<float4 *>(scr + lane * 36 + 4 * j4) =
-                    make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
-              tmem_ld32(tq + (uint32_t)(op.v_col + c0), v);          // the values, in flight during phase 1
-              __syncwarp();
-              const int PK = a.group_k;
-              const size_t point0 = ((size_t)tile * kTileM + quarter * 32) / (size_t)PK;
-              float den[4] = {1.f, 1.f, 1.f, 1.f};                    // 32 / group_k <= 4 points per warp
-#pragma unroll
-              for (int pi = 0; pi < 4; ++pi) {
-                const int r0 = pi * PK;
-                if (r0 < 32) {
-                  int cnt = PK;
-                  if (a.counts) { cnt = __ldg(a.counts + point0 + pi); cnt = cnt < 1 ? 1 : cnt; }
-                  float mx = -3.0e38f;
-#pragma unroll 8
-                  for (int k = 0; k < PK; ++k) mx = fmaxf(mx, k < cnt ? scr[(r0 + k) * 36 + lane] : -1e9f);
-                  float dsum = 0.f;
-#pragma unroll 8
-                  for (int k = 0; k < PK; ++k) {
-                    const float sk = k < cnt ? scr[(r0 + k) * 36 + lane] : -1e9f;
-                    const float ex = expf(sk - mx);
-                    dsum += ex;
-                    scr[(r0 + k) * 36 + lane] = ex;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  float4 k0 = *reinterpret_cast<const float4 *>(cb + 4 * j4);
+                  const float4 k1 = *reinterpret_cast<const float4 *>(cb + 32 + 4 * j4);
+                  const float4 k2 = *reinterpret_cast<const float4 *>(cb + 64 + 4 * j4);
+                  if (rowadd) { k0.x += ra[j4].x; k0.y += ra[j4].y; k0.z += ra[j4].z; k0.w += ra[j4].w; }
+                  float y0 = __uint_as_float(v[4 * j4 + 0]) + k0.x, y1 = __uint_as_float(v[4 * j4 + 1]) + k0.y;
+                  float y2 = __uint_as_float(v[4 * j4 + 2]) + k0.z, y3 = __uint_as_float(v[4 * j4 + 3]) + k0.w;
+                  if (relu) {
+                    y0 = fmaf(fmaxf(y0, 0.f), k1.x, k2.x); y1 = fmaf(fmaxf(y1, 0.f), k1.y, k2.y);
+                    y2 = fmaf(fmaxf(y2, 0.f), k1.z, k2.z); y3 = fmaf(fmaxf(y3, 0.f), k1.w, k2.w);
+                  } else {
+                    y0 += k2.x; y1 += k2.y; y2 += k2.z; y3 += k2.w;
                   }
-                  den[pi] = dsum;
+                  v[4 * j4 + 0] = __float_as_uint(to_tf32(y0)); v[4 * j4 + 1] = __float_as_uint(to_tf32(y1));
+                  v[4 * j4 + 2] = __float_as_uint(to_tf32(y2)); v[4 * j4 + 3] = __float_as_uint(to_tf32(y3));
                 }
               }
-              tmem_wait_ld();
-              __syncwarp();
+              tmem_st32(tq + (uint32_t)(opd.a_col + c0), v);
+            } else {
+              // STATS and POOL start alike: y = acc + (bias + rowadd), my row parked in the transposition tile
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (op.v_bias) b4 = __ldg(reinterpret_cast<const float4 *>(op.v_bias + c0) + j4);
-                const float4 sc4 = __ldg(reinterpret_cast<const float4 *>(op.v_sc + c0) + j4);
-                const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(op.v_sh + c0) + j4);
-                float4 w = *reinterpret_cast<const float4 *>(scr + lane * 36 + 4 * j4);
-                w.x *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]) + b4.x, sc4.x, sh4.x), 0.f);
-                w.y *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]) + b4.y, sc4.y, sh4.y), 0.f);
-                w.z *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]) + b4.z, sc4.z, sh4.z), 0.f);
-                w.w *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]) + b4.w, sc4.w, sh4.w), 0.f);
-                *reinterpret_cast<float4 *>(scr + lane * 36 + 4 * j4) = w;
+                float4 k0 = *reinterpret_cast<const float4 *>(cb + 4 * j4);
+                if (rowadd) { k0.x += ra[j4].x; k0.y += ra[j4].y; k0.z += ra[j4].z; k0.w += ra[j4].w; }
+                sts4(scr_row + 16u * j4, make_float4(__uint_as_float(v[4 * j4 + 0]) + k0.x, __uint_as_float(v[4 * j4 + 1]) + k0.y,
+                                                     __uint_as_float(v[4 * j4 + 2]) + k0.z, __uint_as_float(v[4 * j4 + 3]) + k0.w));
               }
-              __syncwarp();
-              const int n = c0 + lane;                               // my output channel
+              if (kind == PDR_CHAIN_STATS) {
+                // per-tile column statistics: read the tile back column-wise (lane = column).  Every consumer reads ONE
+                // of the two pairs (plain or relu), stat_skip says which one is not needed.
+                __syncwarp();
+                float q0 = 0.f, q1 = 0.f;
+                if (opd.stat_skip & 1) {
 #pragma unroll
-              for (int pi = 0; pi < 4; ++pi) {
-                const int r0 = pi * PK;
-                if (r0 < 32) {
-                  float num = 0.f;
-#pragma unroll 8
-                  for (int k = 0; k < PK; ++k) num += scr[(r0 + k) * 36 + lane];
-                  if (n < op.ncols) a.out[(point0 + pi) * (size_t)a.ld_out + n] = num / den[pi];
+                  for (int r = 0; r < 32; ++r) { const float p = fmaxf(lds1(scr_col + 144u * r), 0.f); q0 += p; q1 = fmaf(p, p, q1); }
+                } else {
+#pragma unroll
+                  for (int r = 0; r < 32; ++r) { const float t = lds1(scr_col + 144u * r); q0 += t; q1 = fmaf(t, t, q1); }
                 }
+                *reinterpret_cast<float2 *>(&s_part[g][quarter][opd.stat_col0 + c0 + lane][0]) = make_float2(q0, q1);
+                __syncwarp();
+              } else {
+                // soft-attention pooling over the group_k neighbour rows of each point (attention.py:85-96): scores = y,
+                // values = relu(GN(V accumulator + bias)).  One transposition tile, three phases:
+                //   (1) lane = column takes the masked maximum and the denominator of each point and leaves
+                //       exp(score - max) in place;
+                //   (2) lane = row multiplies its row of weights with its values (TMEM) in place;
+                //   (3) lane = column adds the group_k products of each point and divides.
+                tmem_ld32(tq + (uint32_t)(opd.v_col + c0), v);        // the values, in flight during phase 1
+                __syncwarp();
+                const int PK = a.group_k;
+                const size_t point0 = ((size_t)tile * kTileM + quarter * 32) / (size_t)PK;
+                float den[4] = {1.f, 1.f, 1.f, 1.f};                  // 32 / group_k <= 4 points per warp
+#pragma unroll
+                for (int pi = 0; pi < 4; ++pi) {
+                  const int r0 = pi * PK;
+                  if (r0 < 32) {
+                    int cnt = PK;
+                    if (a.counts) { cnt = __ldg(a.counts + point0 + pi); cnt = cnt < 1 ? 1 : cnt; }
+                    float mx = -3.0e38f;
+#pragma unroll 8
+                    for (int k = 0; k < PK; ++k) mx = fmaxf(mx, k < cnt ? lds1(scr_col + 144u * (r0 + k)) : -1e9f);
+                    float dsum = 0.f;
+#pragma unroll 8
+                    for (int k = 0; k < PK; ++k) {
+                      const float sk = k < cnt ? lds1(scr_col + 144u * (r0 + k)) : -1e9f;
+                      const float ex = expf(sk - mx);
+                      dsum += ex;
+                      sts1(scr_col + 144u * (r0 + k), ex);
+                    }
+                    den[pi] = dsum;
+                  }
+                }
+                tmem_wait_ld();
+                __syncwarp();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 k1 = *reinterpret_cast<const float4 *>(cb + 32 + 4 * j4);
+                  const float4 k2 = *reinterpret_cast<const float4 *>(cb + 64 + 4 * j4);
+                  float4 w = lds4(scr_row + 16u * j4);
+                  w.x *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), k1.x, k2.x), 0.f);
+                  w.y *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), k1.y, k2.y), 0.f);
+                  w.z *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), k1.z, k2.z), 0.f);
+                  w.w *= fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), k1.w, k2.w), 0.f);
+                  sts4(scr_row + 16u * j4, w);
+                }
+                __syncwarp();
+                const int n = c0 + lane;                             // my output channel
+#pragma unroll
+                for (int pi = 0; pi < 4; ++pi) {
+                  const int r0 = pi * PK;
+                  if (r0 < 32) {
+                    float num = 0.f;
+#pragma unroll 8
+                    for (int k = 0; k < PK; ++k) num += lds1(scr_col + 144u * (r0 + k));
+                    if (n < ncols) a.out[(point0 + pi) * (size_t)a.ld_out + n] = num / den[pi];
+                  }
+                }
+                __syncwarp();
               }
-              __syncwarp();
             }
           }
         }
@@ -482,22 +546,22 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
         mbar_arrive(&bar_epi_done[g]);
         if (did_stats) {
           // fold the four lane quarters in a fixed order and publish this tile's column partials
-          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(kEpiThreads / 2) : "memory");
-          for (int col = gtid; col < a.stats_n; col += kEpiThreads / 2) {
+          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(gthreads) : "memory");
+          for (int col = gtid; col < a.stats_n; col += gthreads) {
             const float s0 = s_part[g][0][col][0] + s_part[g][1][col][0] + s_part[g][2][col][0] + s_part[g][3][col][0];
             const float s1 = s_part[g][0][col][1] + s_part[g][1][col][1] + s_part[g][2][col][1] + s_part[g][3][col][1];
             const bool relu = (a.stats_relu_mask[col >> 5] >> (col & 31)) & 1u;
             *reinterpret_cast<float4 *>(a.stats + ((size_t)tile * a.stats_n + col) * 4) =
                 relu ? make_float4(0.f, 0.f, s0, s1) : make_float4(s0, s1, 0.f, 0.f);
           }
-          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(kEpiThreads / 2) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(gthreads) : "memory");
         }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == mma_warp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -526,6 +590,8 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
   PDR_REQUIRE(a.n_steps >= 1 && a.n_steps <= PDR_CHAIN_MAX_STEPS, "stage_chain: n_steps=%d", a.n_steps);
   ChainPlan plan;
   memset(&plan, 0, sizeof(plan));
+  bool any_stats = false;
+  int const_blocks = 0;
   plan.nk0 = ceil_div(a.k0, 32);
   plan.tiles_per_sample = a.rows_per_sample / kTileM;
   const long long tiles = (long long)a.batch * plan.tiles_per_sample;
@@ -553,6 +619,7 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
     for (int e = 0; e < st.n_epi; ++e) {
       const PdrChainEpi &op = st.epi[e];
       const int padded = ceil_div(op.ncols, 32) * 32;
+      const_blocks += padded / 32;
       // (ncols need not be a multiple of 32: bias / sc / sh / emb / rowadd rows are read, unguarded, up to the end of their last
       //  32-column block; the caller keeps them readable and zero there, so the pad columns come out as zeros)
       PDR_REQUIRE(op.kind >= PDR_CHAIN_XFORM && op.kind <= PDR_CHAIN_POOL && op.ncols > 0 &&
@@ -567,11 +634,12 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
                                                      ((uintptr_t)op.sh % 16) == 0),
                     "stage_chain: XFORM needs aligned sc / sh");
         PDR_REQUIRE(!op.emb || (op.ld_emb % 4 == 0 && ((uintptr_t)op.emb % 16) == 0), "stage_chain: emb alignment");
+        PDR_REQUIRE(!(op.rowadd && op.pro_mode == PDR_PRO_GN_RELU), "stage_chain: rowadd with a GN->ReLU prologue is not implemented");
       } else if (op.kind == PDR_CHAIN_STATS) {
         PDR_REQUIRE(a.stats && op.stat_col0 >= 0 && op.stat_col0 + padded <= kMaxStatCols && op.stat_col0 + op.ncols <= a.stats_n,
                     "stage_chain: STATS columns [%d, +%d) do not fit (stats_n=%d, cap %d)", op.stat_col0, op.ncols, a.stats_n,
                     kMaxStatCols);
-        plan.any_stats = 1;
+        any_stats = true;
       } else {
         PDR_REQUIRE(a.out && a.ld_out >= op.ncols && op.v_sc && op.v_sh && op.v_ld_scsh % 4 == 0 && op.v_col >= 0 &&
                         op.v_col + padded <= kGroupCols && ((uintptr_t)op.v_sc % 16) == 0 && ((uintptr_t)op.v_sh % 16) == 0 &&
@@ -581,13 +649,21 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
     }
   }
   PDR_REQUIRE(releases == 1, "stage_chain: exactly one step must release the X0 tile (%d do)", releases);
-  PDR_REQUIRE(!plan.any_stats || (a.stats_n > 0 && a.stats_n <= kMaxStatCols), "stage_chain: stats_n=%d", a.stats_n);
-  // shared memory: weight image + ring of X0 tiles (static: barriers, transposition tiles, column partials)
-  const size_t static_smem = sizeof(float) * (size_t)(kEpiWarps * kScratchFloats + 2 * 4 * kMaxStatCols * 2) + 512;
+  PDR_REQUIRE(!any_stats || (a.stats_n > 0 && a.stats_n <= kMaxStatCols), "stage_chain: stats_n=%d", a.stats_n);
+  PDR_REQUIRE(const_blocks * 32 <= kConstCols, "stage_chain: %d columns of per-sample constants (cap %d)", const_blocks * 32, kConstCols);
+  // shared memory: transposition tiles (one per epilogue warp) + weight image + ring of X0 tiles, next to the static part
+  // (barriers, column partials, folded constants).  8 epilogue warps per tile group when that leaves room for >= 2 X0
+  // tiles (two tiles are in flight), else 4.
+  const size_t static_smem = sizeof(float) * (size_t)(2 * 4 * kMaxStatCols * 2 + 2 * kConstCols * 3) + 1024;
   const size_t budget = 226 * 1024 - static_smem;
   const size_t slot_bytes = (size_t)plan.nk0 * kChunkBytes;
-  const size_t fixed = 1024 + (size_t)plan.w_region;
-  if (fixed + 2 * slot_bytes > budget) {
+  size_t fixed = 0;
+  plan.wpg = 0;
+  for (int wpg = kMaxWpg; wpg >= 4; wpg -= 4) {
+    fixed = 2048 + (size_t)(2 * wpg) * kScratchBytes + (size_t)plan.w_region;
+    if (fixed + 2 * slot_bytes <= budget) { plan.wpg = wpg; break; }
+  }
+  if (plan.wpg == 0) {
     set_error("stage_chain: weights (%d B) + two X0 tiles (%zu B each) exceed shared memory", a.w_bytes, slot_bytes);
     return PDR_ERR_UNSUPPORTED;
   }
@@ -603,6 +679,7 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
   }
   const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
   const int grid = plan.total_tiles < sm_cap ? plan.total_tiles : sm_cap;
-  stage_chain_kernel<<<grid, kThreads, smem, (cudaStream_t)stream_>>>(a, plan);
+  const int threads = (2 * plan.wpg + kProdWarps + 1) * 32;
+  stage_chain_kernel<<<grid, threads, smem, (cudaStream_t)stream_>>>(a, plan);
   return check_launch("stage_chain_kernel");
 }

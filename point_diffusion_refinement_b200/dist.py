@@ -68,3 +68,59 @@ def sample_sharded(sample_fn, total_shapes, rank, world_size):
     local = sample_fn(start, stop)
     counts = [shard_range(total_shapes, r, world_size) for r in range(world_size)]
     return all_gather_shapes(local, counts=[b - a for a, b in counts])
+
+
+# ---- training-side collectives (reference pointnet2/distributed.py:67-146) -------------------------
+def broadcast_parameters(module, src=0):
+    """Every tensor of the state_dict from `src` to all ranks (distributed.py:104-107)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return module
+    for t in module.state_dict().values():
+        if torch.is_tensor(t):
+            dist.broadcast(t, src)
+    return module
+
+
+def all_reduce_gradients(module):
+    """Average the gradients over the ranks: one flat bucket per dtype, one all_reduce per bucket over NCCL / NVLink
+    (distributed.py:109-133 without the per-backward callback plumbing).  Returns the number of bytes reduced."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    world = dist.get_world_size()
+    buckets = {}
+    for p in module.parameters():
+        if p.requires_grad and p.grad is not None:
+            buckets.setdefault(p.grad.dtype, []).append(p.grad.data)
+    total = 0
+    for grads in buckets.values():
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= world
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+        total += flat.numel() * flat.element_size()
+    return total
+
+
+def apply_gradient_allreduce(module):
+    """The reference's wrapper (distributed.py:94-146): broadcast the parameters once, then average the gradients at
+    the end of every backward pass that follows a forward pass."""
+    broadcast_parameters(module)
+    module.needs_reduction = False
+
+    def reduce_once():
+        if module.needs_reduction:
+            module.needs_reduction = False
+            all_reduce_gradients(module)
+
+    def hook(*_):
+        torch.autograd.Variable._execution_engine.queue_callback(reduce_once)
+
+    for p in module.parameters():
+        if p.requires_grad:
+            p.register_hook(hook)
+    module.register_forward_hook(lambda m, i, o: setattr(m, "needs_reduction", True))
+    return module

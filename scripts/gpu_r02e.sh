@@ -4,7 +4,7 @@
 tag=${1:-r02e}
 out=gpurun_out/$tag
 mkdir -p $out
-( timeout 600 python -m pytest tests/test_chain_gpu.py tests/test_model_gpu.py tests/test_ops_gpu.py -m gpu -q -s -x ) > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
+( timeout 600 python -m pytest tests/test_chain_gpu.py tests/test_model_gpu.py tests/test_ops_gpu.py tests/test_train_side.py -m gpu -q -s -x ) > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
 grep -E "fused stages vs|passed|failed|FAILED|Error" $out/pytest_gpu.log | tail -12
 ( timeout 600 python bench.py --dump-ops $out/ops.json --no-gpu-reference --no-fast-ddpm --no-cpu-baseline ) > $out/bench.json 2> $out/bench.err; echo "bench exit $?"
 tail -3 $out/bench.err
