@@ -678,17 +678,32 @@ def _main(args, json_out):
     own_ms = sum(d["ms"] for d in agg.values())
     top = max(agg.items(), key=lambda kv: kv[1]["ms"]) if agg else (None, None)
     roofline = None
+    tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0      # TF32 dense = half the measured bf16 rate (TFLOP/s)
     if top[0]:
         d = top[1]
         per_launch_ms = d["ms"] / d["calls"]
         achieved = (d["bytes"] / d["calls"]) / (per_launch_ms * 1e-3) / 1e9 if d["bytes"] else None
+        tflops = (d.get("flops", 0) / (d["ms"] * 1e-3) / 1e12) if d.get("flops") else None
+        # both tensor-core kernels of the step against both roofs: the per-layer GEMMs are HBM-bound by design (AI 8-60
+        # flop/B); the fused stage kernel reads almost nothing and trades HBM bytes for recomputation, so neither roof is
+        # near -- it is bound by the epilogue warps' issue rate, which is why both fractions are given
+        both = {}
+        for name in ("pdr_gemm_fused", "pdr_stage_chain"):
+            if name in agg and agg[name]["ms"] > 0:
+                k = agg[name]
+                both[name] = {"ms_per_step": round(k["ms"], 4), "launches": k["calls"],
+                              "algorithmic_GB": round(k["bytes"] / 1e9, 3), "GFLOP": round(k.get("flops", 0) / 1e9, 1),
+                              "hbm_frac": (k["bytes"] / (k["ms"] * 1e-3) / 1e9) / hbm_peak,
+                              "tensor_frac": (k.get("flops", 0) / (k["ms"] * 1e-3) / 1e12) / tf32_peak}
         roofline = {"kernel": top[0], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "tflops": (d.get("flops", 0) / (d["ms"] * 1e-3) / 1e12) if d.get("flops") else None,
+                    "tflops": tflops, "tensor_peak_tf32_tflops": tf32_peak,
+                    "tensor_frac": (tflops / tf32_peak) if tflops else None,
                     "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json (burst)" if peaks else "fallback 6.65 TB/s",
+                    "peak_source": "MEASURED_PEAKS.json (burst hbm_gbs; bf16_tflops_sustained / 2 for TF32)" if peaks else "fallback 6.65 TB/s",
                     "launches_per_step": d["calls"], "ms_per_launch": per_launch_ms,
                     "share_of_step": d["ms"] / ms_per_step,
                     "own_kernels_share_of_step": own_ms / ms_per_step,
+                    "tensor_core_kernels": both,
                     "per_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}}
     if roofline:
         # dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), not measured live

@@ -34,9 +34,9 @@
 //                      MMAs.  W / 4 warps share a TMEM lane quarter and take alternate 32-column blocks of a step.
 //                      The per-column constants of every operation (GroupNorm scale / shift with the bias folded in,
 //                      embeddings) are folded ONCE per sample into a shared-memory table by the group itself.
-//   warps [2W, 2W+4)   producers: cp.async of the gathered X0 rows (table row + geometric channels) into a ring of
+//   warps [2W, 2W+2)   producers: cp.async of the gathered X0 rows (table row + geometric channels) into a ring of
 //                      SWIZZLE_128B tiles, completion by cp.async.mbarrier.arrive.
-//   warp 2W+4          MMA issue (one lane): walks both groups' step programs in lock step.
+//   warp 2W+2          MMA issue (one lane): walks both groups' step programs in lock step.
 // (First version, r02d/r02e profiles: 4 warps per group re-reading the operation descriptors from the constant bank and
 //  their constants from global memory for every float4 -- 870, then 318 SASS instructions per 32-column block and an
 //  issue rate of 0.2 per epilogue warp; this version: ~120 instructions per block and twice the warps.)
@@ -48,9 +48,9 @@
 namespace pdr {
 namespace {
 
-constexpr int kProdWarps = 4, kProdThreads = kProdWarps * 32;
+// (2 W + kProdWarps + 1 warps: registers are allocated for warps in fours -- 19 warps of 96 registers fit the file, 21 do not)
+constexpr int kProdWarps = 2, kProdThreads = kProdWarps * 32;
 constexpr int kMaxWpg = 8;                                     // epilogue warps per tile group (4 or 8)
-constexpr int kMaxThreads = (2 * kMaxWpg + kProdWarps + 1) * 32;   // 672
 constexpr int kTileM = 128;
 constexpr int kChunkBytes = kTileM * 128;                      // one 32-float K chunk of a 128-row tile
 constexpr int kGroupCols = 256;                                // TMEM columns per tile group
@@ -273,15 +273,15 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     // =============================== PRODUCERS: gathered X0 tiles ================================
     const int ptid = tid - n_epi_warps * 32;
     const int piece = ptid & 7;       // 16-byte piece of the 128-byte chunk row
-    const int arow = ptid >> 3;       // rows arow + 16 i, i < 8 ((arow + 16 i) & 7 == arow & 7)
-    const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ (arow & 7)) << 4));
+    const int arow = ptid >> 3;       // rows arow + 8 i, i < 16 ((arow + 8 i) & 7 == arow)
+    const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ arow) << 4));
     int slot = 0, phase = 0;
     for (int i = 0; i < n_my; ++i) {
       const int tile = t_lo + i;
       const size_t row0 = (size_t)tile * kTileM + arow;             // rows_per_sample % 128 == 0: tiles are dense
-      int idx[8];
+      int idx[16];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) idx[r] = __ldg(a.src_rows + row0 + 16 * r);
+      for (int r = 0; r < 16; ++r) idx[r] = __ldg(a.src_rows + row0 + 8 * r);
       mbar_wait_sleep(&bar_empty[slot], (uint32_t)(phase ^ 1));
       const uint32_t sbase = s_x0_u + (uint32_t)slot * slot_bytes + sw_off;
       for (int kc = 0; kc < plan.nk0; ++kc) {
@@ -289,13 +289,13 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
         const uint32_t dst = sbase + (uint32_t)kc * kChunkBytes;
         if (k < a.k_split) {
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            cp_async16_ignore(dst + r * 2048, a.table + (size_t)max(idx[r], 0) * a.ld_table + k, idx[r] < 0);
+          for (int r = 0; r < 16; ++r)
+            cp_async16_ignore(dst + r * 1024, a.table + (size_t)max(idx[r], 0) * a.ld_table + k, idx[r] < 0);
         } else {
           const bool in = k < a.k0;
           const float *p = a.geo + row0 * (size_t)a.ld_geo + (in ? k - a.k_split : 0);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) cp_async16_ignore(dst + r * 2048, in ? p + (size_t)16 * r * a.ld_geo : a.geo, !in);
+          for (int r = 0; r < 16; ++r) cp_async16_ignore(dst + r * 1024, in ? p + (size_t)8 * r * a.ld_geo : a.geo, !in);
         }
       }
       cp_async_arrive_noinc(&bar_full[slot]);
