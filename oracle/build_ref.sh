@@ -36,3 +36,11 @@ g++ -shared -o "$OUT/libpdr_ref_cuda.so" "$OUT"/obj/*.o \
   -L"$TORCH_DIR/lib" -Wl,-rpath,"$TORCH_DIR/lib" -lc10 -lc10_cuda -ltorch_cpu -ltorch_cuda -ltorch \
   -L/usr/local/cuda/lib64 -Wl,-rpath,/usr/local/cuda/lib64 -lcudart
 echo "built $OUT/libpdr_ref_cuda.so"
+# The reference's own Python for the literal drop-in test on the GPU box (tests/test_dropin_gpu.py imports
+# pointnet2/completion_eval.py ITSELF and runs it on libpdr_b200.so).  Staged UNMODIFIED into oracle/_ref/pyref/ only:
+# git-ignored test infrastructure that travels with the snapshot exactly like the .so above, never part of the repo.
+PYREF="$OUT/pyref"
+rm -rf "$PYREF"; mkdir -p "$PYREF/pointnet2" "$PYREF/pointnet2_ops_lib"
+( cd "$REF/pointnet2" && find . -maxdepth 3 -name "*.py" -not -path "./models/pvd/*" -not -path "./exp_configs/*" -print0 | tar --null -T - -cf - ) | tar -xf - -C "$PYREF/pointnet2"
+( cd "$REF/pointnet2_ops_lib" && find pointnet2_ops -maxdepth 1 -name "*.py" -print0 | tar --null -T - -cf - ) | tar -xf - -C "$PYREF/pointnet2_ops_lib"
+echo "staged $(find "$PYREF" -name '*.py' | wc -l) reference .py files into $PYREF"

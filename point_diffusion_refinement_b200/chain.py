@@ -199,15 +199,15 @@ class StagePlan:
     def smem_bytes(self, slots=2, wpg=4):
         """Dynamic shared memory of a launch with `slots` X0 tiles in the ring and `wpg` epilogue warps per tile group
         (stage_chain.cu: transposition tiles + weight image + ring, + alignment slack)."""
-        return 2048 + 2 * wpg * 32 * 36 * 4 + self.image.bytes + slots * (self.k0p // 32) * TILE_ROWS * 128
+        return 1024 + 2 * wpg * 32 * 36 * 4 + self.image.bytes + slots * (self.k0p // 32) * TILE_ROWS * 128
 
     def fits(self):
         """Shared memory (weights + at least two X0 tiles with 4 epilogue warps per group), statistics columns, folded-constant
         columns and MMA widths within the kernel's limits."""
-        static = 4 * (2 * 4 * MAX_STAT_COLS * 2 + 2 * MAX_CONST_COLS * 3) + 1024
+        static = 25600 + 512                   # stage_chain.cu: barriers, column partials, folded constants, decoded program
         s = self.spec
         const_cols = 2 * p32(s.co) + sum(p32(c) for c in s.c) + p32(s.ck) + p32(s.ci)       # the last sweep holds them all
-        return (self.smem_bytes(2, 4) <= 226 * 1024 - static and p32(s.c[0]) + p32(s.ck) <= 256
+        return (self.smem_bytes(2, 4) <= 227 * 1024 - static and p32(s.c[0]) + p32(s.ck) <= 256
                 and const_cols <= MAX_CONST_COLS
                 and all(self.sweep_stats_n(d) <= MAX_STAT_COLS for d in range(1, s.L + 2)))
 

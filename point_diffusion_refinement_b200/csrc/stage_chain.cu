@@ -174,6 +174,20 @@ __device__ __forceinline__ void sts4(uint32_t a, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// one tcgen05.mma (one K step of 8) of the step program, everything precomputed but the tile group / X0 slot bases
+struct MmaEntry {
+  uint64_t bdesc;        // complete shared-memory descriptor of the weight slice
+  uint32_t d_col;        // accumulator column inside the group
+  uint32_t a;            // A in TMEM: column inside the group; A = X0: (byte offset inside the slot) >> 4
+  uint32_t idesc;
+  uint32_t flags;        // bit 0: A in TMEM, bit 1: accumulate
+};
+constexpr int kMaxMmaEntries = 160;
+struct EpiEntry {
+  int kind, d_col, ncols, nblk, pro_mode, a_col, stat_col0, stat_skip, v_col, cblk, ld_rowadd;
+  const float *rowadd;
+};
+
 struct ChainPlan {
   int tiles_per_sample, total_tiles;
   int nk0;          // 32-float K chunks of the gathered X0 tile
@@ -218,7 +232,12 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_part[2][4][kMaxStatCols][2];              // per group / lane quarter column partials
   __shared__ __align__(16) float s_const[2][kConstCols * 3];                 // per group: folded constants of one sample
-  __shared__ int s_coff[kMaxOps + 1];                                        // first 32-column block of every operation
+  // The step program, decoded ONCE into shared memory.  Read through the kernel parameter block with a dynamic index every
+  // field is an LDC with its own scoreboard wait (r02g profile: the single issuing lane of the MMA warp spent ~1 us per step
+  // on them while both epilogue groups waited; the epilogue warps stalled on them between blocks).
+  __shared__ MmaEntry s_mma[kMaxMmaEntries];
+  __shared__ int s_mma_first[PDR_CHAIN_MAX_STEPS + 1];
+  __shared__ EpiEntry s_epi[kMaxOps];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wpg = plan.wpg;
@@ -240,9 +259,39 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     int off = 0;
     for (int s = 0; s < a.n_steps; ++s)
       for (int e = 0; e < PDR_CHAIN_MAX_EPI; ++e) {
-        s_coff[s * PDR_CHAIN_MAX_EPI + e] = off;
-        if (e < a.steps[s].n_epi) off += (a.steps[s].epi[e].ncols + 31) >> 5;
+        EpiEntry &t = s_epi[s * PDR_CHAIN_MAX_EPI + e];
+        t.cblk = off;
+        if (e < a.steps[s].n_epi) {
+          const PdrChainEpi &op = a.steps[s].epi[e];
+          t.kind = op.kind; t.d_col = op.d_col; t.ncols = op.ncols; t.nblk = (op.ncols + 31) >> 5; t.pro_mode = op.pro_mode;
+          t.a_col = op.a_col; t.stat_col0 = op.stat_col0; t.stat_skip = op.stat_skip; t.v_col = op.v_col;
+          t.ld_rowadd = op.ld_rowadd; t.rowadd = op.rowadd;
+          off += t.nblk;
+        }
       }
+  }
+  if (tid == 32) {
+    // every MMA of the sweep, one entry per K step of 8
+    constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+    int n = 0;
+    for (int s = 0; s < a.n_steps; ++s) {
+      s_mma_first[s] = n;
+      for (int m = 0; m < a.steps[s].n_mma; ++m) {
+        const PdrChainMma &op = a.steps[s].mma[m];
+        for (int kk = 0; kk < op.k; kk += 8, ++n) {
+          const int kw = op.w_k0 + kk;
+          MmaEntry &t = s_mma[n];
+          t.bdesc = make_desc(s_w_u + (uint32_t)op.w_off + (uint32_t)(kw >> 5) * (uint32_t)op.w_rows * 128u +
+                              (uint32_t)op.w_row0 * 128u) + (uint64_t)((kw & 31) >> 2);
+          t.d_col = (uint32_t)op.d_col;
+          t.idesc = kIdescBase | ((uint32_t)(op.n >> 3) << 17);
+          t.flags = (op.a_tmem ? 1u : 0u) | ((kk > 0 || op.accumulate) ? 2u : 0u);
+          const int ka = op.a_col + kk;
+          t.a = op.a_tmem ? (uint32_t)ka : (((uint32_t)(ka >> 5) * kChunkBytes) >> 4) + (uint32_t)((ka & 31) >> 2);
+        }
+      }
+    }
+    s_mma_first[a.n_steps] = n;
   }
   if (warp == mma_warp) {
     __syncwarp();
@@ -276,12 +325,20 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     const int arow = ptid >> 3;       // rows arow + 8 i, i < 16 ((arow + 8 i) & 7 == arow)
     const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ arow) << 4));
     int slot = 0, phase = 0;
+    int idx[16], nidx[16];
+    if (n_my > 0) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) nidx[r] = __ldg(a.src_rows + (size_t)t_lo * kTileM + arow + 8 * r);
+    }
     for (int i = 0; i < n_my; ++i) {
       const int tile = t_lo + i;
       const size_t row0 = (size_t)tile * kTileM + arow;             // rows_per_sample % 128 == 0: tiles are dense
-      int idx[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) idx[r] = __ldg(a.src_rows + row0 + 8 * r);
+      for (int r = 0; r < 16; ++r) idx[r] = nidx[r];
+      if (i + 1 < n_my) {                                          // the next tile's rows: one full tile of latency hidden
+#pragma unroll
+        for (int r = 0; r < 16; ++r) nidx[r] = __ldg(a.src_rows + row0 + kTileM + 8 * r);
+      }
       mbar_wait_sleep(&bar_empty[slot], (uint32_t)(phase ^ 1));
       const uint32_t sbase = s_x0_u + (uint32_t)slot * slot_bytes + sw_off;
       for (int kc = 0; kc < plan.nk0; ++kc) {
@@ -306,10 +363,11 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     // both tile groups in lock step: step s of tile 2j (group 0), step s of tile 2j + 1 (group 1), step s + 1 ...
     uint32_t ph_epi[2] = {0u, 0u};
     bool first[2] = {true, true};
-    constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+    uint32_t release_mask = 0u;
+    for (int s = 0; s < a.n_steps; ++s) release_mask |= a.steps[s].release_x0 ? (1u << s) : 0u;
+    const int n_steps = a.n_steps;
     for (int pair = 0; pair * 2 < n_my; ++pair) {
-      for (int s = 0; s < a.n_steps; ++s) {
-        const PdrChainStep &st = a.steps[s];
+      for (int s = 0; s < n_steps; ++s) {
         for (int g = 0; g < 2; ++g) {
           const int i = pair * 2 + g;
           if (i >= n_my) continue;
@@ -326,28 +384,15 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (lane == 0) {
             const uint32_t tg = tmem_base + (uint32_t)(g * kGroupCols);
-            const uint32_t x0 = s_x0_u + (uint32_t)slot * slot_bytes;
-            for (int m = 0; m < st.n_mma; ++m) {
-              const PdrChainMma &op = st.mma[m];
-              const uint32_t idesc = kIdescBase | ((uint32_t)(op.n >> 3) << 17);
-              const uint32_t d = tg + (uint32_t)op.d_col;
-              for (int kk = 0; kk < op.k; kk += 8) {
-                const int kw = op.w_k0 + kk;
-                const uint64_t bdesc =
-                    make_desc(s_w_u + (uint32_t)op.w_off + (uint32_t)(kw >> 5) * (uint32_t)op.w_rows * 128u +
-                              (uint32_t)op.w_row0 * 128u) + (uint64_t)((kw & 31) >> 2);
-                const uint32_t acc = (kk > 0 || op.accumulate) ? 1u : 0u;
-                if (op.a_tmem) {
-                  umma_ts(d, tg + (uint32_t)(op.a_col + kk), bdesc, idesc, acc);
-                } else {
-                  const int ka = op.a_col + kk;
-                  const uint64_t adesc = make_desc(x0 + (uint32_t)(ka >> 5) * kChunkBytes) + (uint64_t)((ka & 31) >> 2);
-                  umma_ss(d, adesc, bdesc, idesc, acc);
-                }
-              }
+            const uint64_t x0desc = make_desc(s_x0_u + (uint32_t)slot * slot_bytes);
+            const int m_end = s_mma_first[s + 1];
+            for (int m = s_mma_first[s]; m < m_end; ++m) {
+              const MmaEntry t = s_mma[m];
+              if (t.flags & 1u) umma_ts(tg + t.d_col, tg + t.a, t.bdesc, t.idesc, t.flags >> 1);
+              else umma_ss(tg + t.d_col, x0desc + (uint64_t)t.a, t.bdesc, t.idesc, t.flags >> 1);
             }
             umma_commit(&bar_mma_done[g]);
-            if (st.release_x0) umma_commit(&bar_empty[slot]);
+            if (release_mask & (1u << s)) umma_commit(&bar_empty[slot]);
           }
           __syncwarp();
         }
@@ -367,6 +412,9 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     const float *cg = s_const[g];
     uint32_t ph = 0u;
     int cached_b = -1;
+    const int n_steps = a.n_steps;
+    int n_epi_packed = 0;
+    for (int s = 0; s < n_steps; ++s) n_epi_packed |= a.steps[s].n_epi << (4 * s);
     for (int i = g; i < n_my; i += 2) {
       const int tile = t_lo + i;
       const int b = tile / plan.tiles_per_sample;
@@ -378,7 +426,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
         for (int s = 0; s < a.n_steps; ++s)
           for (int e = 0; e < a.steps[s].n_epi; ++e) {
             const PdrChainEpi &op = a.steps[s].epi[e];
-            const int blk0 = s_coff[s * PDR_CHAIN_MAX_EPI + e];
+            const int blk0 = s_epi[s * PDR_CHAIN_MAX_EPI + e].cblk;
             const int ncp = ((op.ncols + 31) >> 5) << 5;
             for (int c = gtid; c < ncp; c += gthreads) {
               float c0, c1, c2;
@@ -390,21 +438,19 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
         asm volatile("bar.sync %0, %1;" ::"r"(gbar), "r"(gthreads) : "memory");
         cached_b = b;
       }
-      for (int s = 0; s < a.n_steps; ++s) {
-        const PdrChainStep &st = a.steps[s];
-        const int n_epi = st.n_epi;
+      for (int s = 0; s < n_steps; ++s) {
+        const int n_epi = (n_epi_packed >> (4 * s)) & 15;
         mbar_wait(&bar_mma_done[g], ph);
         ph ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         bool wrote_tmem = false, did_stats = false;
         int unit = 0;
         for (int e = 0; e < n_epi; ++e) {
-          const PdrChainEpi &opd = st.epi[e];
-          // the handful of fields the block loops need, read once per operation
+          const EpiEntry opd = s_epi[s * PDR_CHAIN_MAX_EPI + e];
           const int kind = opd.kind, d_col = opd.d_col, ncols = opd.ncols, pro_mode = opd.pro_mode;
-          const int nblk = (ncols + 31) >> 5;
+          const int nblk = opd.nblk;
           const float *rowadd = opd.rowadd ? opd.rowadd + point * (size_t)opd.ld_rowadd : nullptr;
-          const float *cop = cg + s_coff[s * PDR_CHAIN_MAX_EPI + e] * 96;
+          const float *cop = cg + opd.cblk * 96;
           wrote_tmem |= kind == PDR_CHAIN_XFORM;
           did_stats |= kind == PDR_CHAIN_STATS;
           for (int blk = 0; blk < nblk; ++blk, ++unit) {
@@ -648,19 +694,23 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
       }
     }
   }
+  int mma_entries = 0;
+  for (int s = 0; s < a.n_steps; ++s)
+    for (int m = 0; m < a.steps[s].n_mma; ++m) mma_entries += a.steps[s].mma[m].k / 8;
+  PDR_REQUIRE(mma_entries <= kMaxMmaEntries, "stage_chain: %d MMA instructions per tile (cap %d)", mma_entries, kMaxMmaEntries);
   PDR_REQUIRE(releases == 1, "stage_chain: exactly one step must release the X0 tile (%d do)", releases);
   PDR_REQUIRE(!any_stats || (a.stats_n > 0 && a.stats_n <= kMaxStatCols), "stage_chain: stats_n=%d", a.stats_n);
   PDR_REQUIRE(const_blocks * 32 <= kConstCols, "stage_chain: %d columns of per-sample constants (cap %d)", const_blocks * 32, kConstCols);
   // shared memory: transposition tiles (one per epilogue warp) + weight image + ring of X0 tiles, next to the static part
   // (barriers, column partials, folded constants).  8 epilogue warps per tile group when that leaves room for >= 2 X0
   // tiles (two tiles are in flight), else 4.
-  const size_t static_smem = sizeof(float) * (size_t)(2 * 4 * kMaxStatCols * 2 + 2 * kConstCols * 3) + 1024;
-  const size_t budget = 226 * 1024 - static_smem;
+  const size_t static_smem = 25600;          // barriers, column partials, folded constants, decoded step program (25.2 KB)
+  const size_t budget = 227 * 1024 - 512 - static_smem;      // 227 KB per CTA (static + dynamic) on sm_100
   const size_t slot_bytes = (size_t)plan.nk0 * kChunkBytes;
   size_t fixed = 0;
   plan.wpg = 0;
   for (int wpg = kMaxWpg; wpg >= 4; wpg -= 4) {
-    fixed = 2048 + (size_t)(2 * wpg) * kScratchBytes + (size_t)plan.w_region;
+    fixed = 1024 + (size_t)(2 * wpg) * kScratchBytes + (size_t)plan.w_region;     // (4608 B tiles: 8 of them are 36 KiB)
     if (fixed + 2 * slot_bytes <= budget) { plan.wpg = wpg; break; }
   }
   if (plan.wpg == 0) {

@@ -124,12 +124,14 @@ def test_denoiser_on_fused_stages_matches_the_per_layer_engine(monkeypatch):
         a, b = res[False][i], res[True][i]
         err = (a - b).abs()
         print("%s: fused stages vs per-layer |diff| mean %.2e max %.2e (|ref| mean %.2e)" % (what, err.mean(), err.max(), a.abs().mean()))
-    # The first fused stage sees bit-identical inputs: its output differs from the per-layer GEMMs only by fp32 summation
-    # order (measured 1e-6).  Further down a last-bit difference can flip the TF32 rounding of an activation, so the two
-    # TF32 engines drift apart like either drifts from fp32: judged with the TF32 distribution bars of test_model_gpu.py.
+    # The first fused stage sees bit-identical inputs: its output differs from the per-layer GEMMs by fp32 association only
+    # (statistics summed in another order, the conv bias folded into the GroupNorm shift) -- except where that last-bit
+    # difference flips the TF32 rounding of an activation (one TF32 ulp = 5e-4 relative on that element): mean 2e-7, max 6e-4
+    # measured.  Further down the two TF32 engines drift apart like either drifts from fp32: judged with the TF32
+    # distribution bars of test_model_gpu.py.
     from tests.test_model_gpu import TF32_MAX, TF32_MEDIAN, TF32_P999, _tf32_error_profile
     first = (res[False][2] - res[True][2]).abs()
-    assert first.max() < 2e-5, first.max()
+    assert first.mean() < 2e-6 and first.max() < 3e-3, (first.mean(), first.max())
     for i in (0, 1):
         med, p999, mx = _tf32_error_profile(res[True][i], res[False][i])
         assert med <= TF32_MEDIAN and p999 <= TF32_P999 and mx <= TF32_MAX, (i, med, p999, mx)
