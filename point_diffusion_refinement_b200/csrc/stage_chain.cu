@@ -48,8 +48,8 @@
 namespace pdr {
 namespace {
 
-// (2 W + kProdWarps + 1 warps: registers are allocated for warps in fours -- 19 warps of 96 registers fit the file, 21 do not)
-constexpr int kProdWarps = 2, kProdThreads = kProdWarps * 32;
+// (registers are allocated for warps in fours: W = 8 runs 16 + 2 + 1 = 19 warps of 96 registers, 21 would not fit the file;
+//  W = 4 runs 8 + 4 + 1 = 13 warps and gets 152 registers)
 constexpr int kMaxWpg = 8;                                     // epilogue warps per tile group (4 or 8)
 constexpr int kTileM = 128;
 constexpr int kChunkBytes = kTileM * 128;                      // one 32-float K chunk of a 128-row tile
@@ -225,8 +225,12 @@ __device__ __forceinline__ void fold_constants(const PdrChainEpi &op, int b, int
   }
 }
 
-__global__ void __maxnreg__(96)
+template <int WPG, int kProdWarps>
+__global__ void __launch_bounds__((2 * WPG + kProdWarps + 1) * 32, 1)
 stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan) {
+  constexpr int kProdThreads = kProdWarps * 32;
+  constexpr int kRowsPerProd = kTileM * 8 / kProdThreads;        // rows a producer thread copies per chunk (16 or 8)
+  constexpr int kRowStep = kTileM / kRowsPerProd;                // arow + kRowStep * r
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[kMaxSlots], bar_empty[kMaxSlots], bar_mma_done[2], bar_epi_done[2];
   __shared__ uint32_t s_tmem_base;
@@ -240,7 +244,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
   __shared__ EpiEntry s_epi[kMaxOps];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wpg = plan.wpg;
+  constexpr int wpg = WPG;
   const int n_epi_warps = 2 * wpg, mma_warp = n_epi_warps + kProdWarps;
   const int nthreads = (mma_warp + 1) * 32;
 
@@ -322,22 +326,22 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
     // =============================== PRODUCERS: gathered X0 tiles ================================
     const int ptid = tid - n_epi_warps * 32;
     const int piece = ptid & 7;       // 16-byte piece of the 128-byte chunk row
-    const int arow = ptid >> 3;       // rows arow + 8 i, i < 16 ((arow + 8 i) & 7 == arow)
-    const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ arow) << 4));
+    const int arow = ptid >> 3;       // rows arow + kRowStep i ((arow + kRowStep i) & 7 == arow & 7)
+    const uint32_t sw_off = (uint32_t)(arow * 128 + ((piece ^ (arow & 7)) << 4));
     int slot = 0, phase = 0;
-    int idx[16], nidx[16];
+    int idx[kRowsPerProd], nidx[kRowsPerProd];
     if (n_my > 0) {
 #pragma unroll
-      for (int r = 0; r < 16; ++r) nidx[r] = __ldg(a.src_rows + (size_t)t_lo * kTileM + arow + 8 * r);
+      for (int r = 0; r < kRowsPerProd; ++r) nidx[r] = __ldg(a.src_rows + (size_t)t_lo * kTileM + arow + kRowStep * r);
     }
     for (int i = 0; i < n_my; ++i) {
       const int tile = t_lo + i;
       const size_t row0 = (size_t)tile * kTileM + arow;             // rows_per_sample % 128 == 0: tiles are dense
 #pragma unroll
-      for (int r = 0; r < 16; ++r) idx[r] = nidx[r];
+      for (int r = 0; r < kRowsPerProd; ++r) idx[r] = nidx[r];
       if (i + 1 < n_my) {                                          // the next tile's rows: one full tile of latency hidden
 #pragma unroll
-        for (int r = 0; r < 16; ++r) nidx[r] = __ldg(a.src_rows + row0 + kTileM + 8 * r);
+        for (int r = 0; r < kRowsPerProd; ++r) nidx[r] = __ldg(a.src_rows + row0 + kTileM + kRowStep * r);
       }
       mbar_wait_sleep(&bar_empty[slot], (uint32_t)(phase ^ 1));
       const uint32_t sbase = s_x0_u + (uint32_t)slot * slot_bytes + sw_off;
@@ -346,13 +350,14 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
         const uint32_t dst = sbase + (uint32_t)kc * kChunkBytes;
         if (k < a.k_split) {
 #pragma unroll
-          for (int r = 0; r < 16; ++r)
-            cp_async16_ignore(dst + r * 1024, a.table + (size_t)max(idx[r], 0) * a.ld_table + k, idx[r] < 0);
+          for (int r = 0; r < kRowsPerProd; ++r)
+            cp_async16_ignore(dst + r * (kRowStep * 128), a.table + (size_t)max(idx[r], 0) * a.ld_table + k, idx[r] < 0);
         } else {
           const bool in = k < a.k0;
           const float *p = a.geo + row0 * (size_t)a.ld_geo + (in ? k - a.k_split : 0);
 #pragma unroll
-          for (int r = 0; r < 16; ++r) cp_async16_ignore(dst + r * 1024, in ? p + (size_t)8 * r * a.ld_geo : a.geo, !in);
+          for (int r = 0; r < kRowsPerProd; ++r)
+            cp_async16_ignore(dst + r * (kRowStep * 128), in ? p + (size_t)kRowStep * r * a.ld_geo : a.geo, !in);
         }
       }
       cp_async_arrive_noinc(&bar_full[slot]);
@@ -459,12 +464,8 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
             const float *cb = cop + blk * 96;
             uint32_t v[32];
             tmem_ld32(tq + (uint32_t)(d_col + c0), v);
-            // the broadcast query row of my point (rows are read in whole 32-column blocks: zero padded by the caller)
-            float4 ra[8];
-            if (rowadd) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) ra[j4] = __ldg(reinterpret_cast<const float4 *>(rowadd + c0) + j4);
-            }
+            // (the broadcast query row of my point is read in whole 32-column blocks: zero padded by the caller)
+            const float4 *ra = reinterpret_cast<const float4 *>(rowadd + c0);
             tmem_wait_ld();
             if (kind == PDR_CHAIN_XFORM) {
               // -> TF32 A operand of a later MMA (TMEM, lane = row, one column per channel)
@@ -487,7 +488,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
                   float4 k0 = *reinterpret_cast<const float4 *>(cb + 4 * j4);
                   const float4 k1 = *reinterpret_cast<const float4 *>(cb + 32 + 4 * j4);
                   const float4 k2 = *reinterpret_cast<const float4 *>(cb + 64 + 4 * j4);
-                  if (rowadd) { k0.x += ra[j4].x; k0.y += ra[j4].y; k0.z += ra[j4].z; k0.w += ra[j4].w; }
+                  if (rowadd) { const float4 r = __ldg(ra + j4); k0.x += r.x; k0.y += r.y; k0.z += r.z; k0.w += r.w; }
                   float y0 = __uint_as_float(v[4 * j4 + 0]) + k0.x, y1 = __uint_as_float(v[4 * j4 + 1]) + k0.y;
                   float y2 = __uint_as_float(v[4 * j4 + 2]) + k0.z, y3 = __uint_as_float(v[4 * j4 + 3]) + k0.w;
                   if (relu) {
@@ -506,7 +507,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 float4 k0 = *reinterpret_cast<const float4 *>(cb + 4 * j4);
-                if (rowadd) { k0.x += ra[j4].x; k0.y += ra[j4].y; k0.z += ra[j4].z; k0.w += ra[j4].w; }
+                if (rowadd) { const float4 r = __ldg(ra + j4); k0.x += r.x; k0.y += r.y; k0.z += r.z; k0.w += r.w; }
                 sts4(scr_row + 16u * j4, make_float4(__uint_as_float(v[4 * j4 + 0]) + k0.x, __uint_as_float(v[4 * j4 + 1]) + k0.y,
                                                      __uint_as_float(v[4 * j4 + 2]) + k0.z, __uint_as_float(v[4 * j4 + 3]) + k0.w));
               }
@@ -709,7 +710,8 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
   const size_t slot_bytes = (size_t)plan.nk0 * kChunkBytes;
   size_t fixed = 0;
   plan.wpg = 0;
-  for (int wpg = kMaxWpg; wpg >= 4; wpg -= 4) {
+  static const int wpg_max = getenv("PDR_CHAIN_WPG") ? atoi(getenv("PDR_CHAIN_WPG")) : kMaxWpg;      // A/B: 4 or 8
+  for (int wpg = (wpg_max == 4 ? 4 : kMaxWpg); wpg >= 4; wpg -= 4) {
     fixed = 1024 + (size_t)(2 * wpg) * kScratchBytes + (size_t)plan.w_region;     // (4608 B tiles: 8 of them are 36 KiB)
     if (fixed + 2 * slot_bytes <= budget) { plan.wpg = wpg; break; }
   }
@@ -721,15 +723,16 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
   if (slots > kMaxSlots) slots = kMaxSlots;
   plan.slots = slots;
   const size_t smem = fixed + (size_t)slots * slot_bytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stage_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-    if (e != cudaSuccess) { set_error("stage_chain: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
-    configured = true;
-  }
   const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
   const int grid = plan.total_tiles < sm_cap ? plan.total_tiles : sm_cap;
-  const int threads = (2 * plan.wpg + kProdWarps + 1) * 32;
-  stage_chain_kernel<<<grid, threads, smem, (cudaStream_t)stream_>>>(a, plan);
+  const int threads = plan.wpg == 8 ? (16 + 2 + 1) * 32 : (8 + 4 + 1) * 32;
+  auto kern = plan.wpg == 8 ? stage_chain_kernel<8, 2> : stage_chain_kernel<4, 4>;
+  static bool configured[2] = {false, false};
+  if (!configured[plan.wpg == 8]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e != cudaSuccess) { set_error("stage_chain: smem attr: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
+    configured[plan.wpg == 8] = true;
+  }
+  kern<<<grid, threads, smem, (cudaStream_t)stream_>>>(a, plan);
   return check_launch("stage_chain_kernel");
 }

@@ -6,7 +6,8 @@ GPU box has no /root/reference) and executed on libpdr_b200.so through ``dropin.
   * task='refine_completion' is deterministic: the reference's evaluate() and the package's evaluate() must return the same
     CD / EMD / F1 for the same weights and inputs (same kernels underneath, reference module tree vs ours);
   * task='completion' runs the reference's sampling loop (its CPU-generator noise) for a short schedule end to end.
-Libraries the reference imports but the hot path never touches (matplotlib, h5py) are stubbed."""
+Libraries the reference's data / plotting modules import but the hot path never touches (matplotlib, h5py, transforms3d,
+open3d ...) are stubbed with empty modules."""
 import contextlib
 import os
 import sys
@@ -27,7 +28,7 @@ def reference_drivers():
     from point_diffusion_refinement_b200 import dropin
     saved_path, saved_mods = list(sys.path), set(sys.modules)
     stubs = {}
-    for name in ("matplotlib", "matplotlib.pyplot", "h5py"):
+    for name in ("matplotlib", "matplotlib.pyplot", "h5py", "transforms3d", "open3d", "tensorboardX", "termcolor"):
         if name not in sys.modules:
             m = types.ModuleType(name)
             m.use = lambda *a, **k: None
