@@ -69,12 +69,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "CH_WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra CH_WAIT_DONE;\n\t"
       "bra CH_WAIT_LOOP;\n\t"
       "CH_WAIT_DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)      // suspend-time hint: the warp sleeps in hardware until
+      : "memory");                                                   // the phase completes instead of re-issuing the poll
 }
 // for waits that are expected to be long (a producer ahead of the ring): sleep between polls, the retry loop must not take
 // issue slots from the epilogue warps

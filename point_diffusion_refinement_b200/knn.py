@@ -43,8 +43,11 @@ class _KnnFunction(torch.autograd.Function):
 
 
 def knn_points(p1, p2, lengths1=None, lengths2=None, K=1, version=-1, return_nn=False, return_sorted=True):
-    if lengths1 is not None or lengths2 is not None:
-        raise NotImplementedError("knn_points: heterogeneous batches (lengths1/lengths2) are not supported")
+    # The reference's chamfer_distance always passes lengths (chamfer_loss_new.py:149-150), full ones for padded tensors
+    # (_handle_pointcloud_input, :52-57): full lengths are the homogeneous case; anything shorter is not implemented.
+    for lengths, p in ((lengths1, p1), (lengths2, p2)):
+        if lengths is not None and not bool((torch.as_tensor(lengths) == p.shape[1]).all()):
+            raise NotImplementedError("knn_points: heterogeneous batches (lengths1/lengths2 < P) are not supported")
     if p1.shape[0] != p2.shape[0] or p1.shape[2] != 3 or p2.shape[2] != 3:
         raise ValueError("knn_points expects (N,P1,3) and (N,P2,3)")
     p1c = p1.contiguous().float()
