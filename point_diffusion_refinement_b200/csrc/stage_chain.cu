@@ -710,8 +710,9 @@ extern "C" int pdr_stage_chain(const PdrChainArgs *args, void *stream_) {
   const size_t slot_bytes = (size_t)plan.nk0 * kChunkBytes;
   size_t fixed = 0;
   plan.wpg = 0;
-  static const int wpg_max = getenv("PDR_CHAIN_WPG") ? atoi(getenv("PDR_CHAIN_WPG")) : kMaxWpg;      // A/B: 4 or 8
-  for (int wpg = (wpg_max == 4 ? 4 : kMaxWpg); wpg >= 4; wpg -= 4) {
+  // 4 epilogue warps per tile group by default: 8 measured SLOWER (r02i/r02j: 2.23 ms against 1.61 ms on the 2 M-row stage)
+  static const int wpg_max = getenv("PDR_CHAIN_WPG") ? atoi(getenv("PDR_CHAIN_WPG")) : 4;      // A/B: 4 or 8
+  for (int wpg = (wpg_max == 8 ? kMaxWpg : 4); wpg >= 4; wpg -= 4) {
     fixed = 1024 + (size_t)(2 * wpg) * kScratchBytes + (size_t)plan.w_region;     // (4608 B tiles: 8 of them are 36 KiB)
     if (fixed + 2 * slot_bytes <= budget) { plan.wpg = wpg; break; }
   }

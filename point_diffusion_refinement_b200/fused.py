@@ -94,9 +94,13 @@ _FUSE_POOL = os.environ.get("PDR_FUSE_POOL", "0") == "1"
 _FOLD_RES = os.environ.get("PDR_FOLD_RES", "1") != "0"
 
 
-# PDR_STAGE_CHAIN=0 keeps every stage on the per-layer GEMMs.  Default: stages whose weights fit in shared memory run as
-# fused sweeps (csrc/stage_chain.cu, chain.py): intermediates stay in tensor memory, only the gathered rows are read.
-_STAGE_CHAIN = os.environ.get("PDR_STAGE_CHAIN", "1") != "0"
+# PDR_STAGE_CHAIN=1 runs the stages whose weights fit in shared memory as fused sweeps (csrc/stage_chain.cu, chain.py):
+# intermediates stay in tensor memory, only the gathered rows are read -- 12.5 GB of DRAM traffic per step instead of 20.5.
+# OFF by default: measured SLOWER on B200 (profiles/r02_stage_chain_notes.txt: 12.2 ms / step against 10.2).  A GroupNorm
+# between any two layers forces L + 2 sweeps that recompute the chain, i.e. ~9 dependent MMA -> epilogue hops per tile
+# instead of 5, and a hop costs ~2 us of latency whether or not its result goes to HBM; the narrow stages it covers were
+# latency-bound already, not HBM-bound.  Parity-tested either way (tests/test_chain_gpu.py).
+_STAGE_CHAIN = os.environ.get("PDR_STAGE_CHAIN", "0") == "1"
 # PDR_STAGE_CHAIN_ONLY=name[,name...] restricts it to the named stages (enc_map0, dec_map1, sa0, ...): A/B and debugging
 _STAGE_CHAIN_ONLY = [n for n in os.environ.get("PDR_STAGE_CHAIN_ONLY", "").split(",") if n]
 
