@@ -248,6 +248,8 @@ typedef struct PdrGnArgs {
   float *sc; float *sh; int ld_out;                        /* (batch, ld_out) */
 } PdrGnArgs;
 int pdr_gn_finalize(const PdrGnArgs *args, void *stream);
+/* `count` (1 or 2) independent finalisations in ONE launch: args[0 .. count). */
+int pdr_gn_finalize_batch(const PdrGnArgs *args, int count, void *stream);
 
 /* out[row, c] = pro(x[row, c]) (+add +R) materialised; same prologue semantics as the GEMM. */
 int pdr_affine_rows(int batch, int rows_per_sample, int C, const float *x, int ldx, int pro_mode,

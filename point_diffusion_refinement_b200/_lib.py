@@ -54,6 +54,7 @@ SIGNATURES = {
     "pdr_gemm_tile_rows": [],
     "pdr_gemm_fused": [_ptr, _ptr],
     "pdr_gn_finalize": [_ptr, _ptr],
+    "pdr_gn_finalize_batch": [_ptr, _c_int, _ptr],
     "pdr_affine_rows": [_c_int, _c_int, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _c_int, _ptr, _c_int, _ptr, _c_int,
                         _ptr, _c_int, _ptr],
     "pdr_attention_pool": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _ptr,

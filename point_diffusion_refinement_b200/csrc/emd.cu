@@ -24,6 +24,7 @@
 //                                                   1e-9 regulariser); -DPDR_EMD_EXACT_EXPF restores it
 // Per-row accumulation order (sequential over the other cloud's index) is the reference's.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -431,6 +432,12 @@ matchcost_grad_kernel(int n, int m, const float *__restrict__ grad_cost, const f
 
 int pick_cluster(int b, int n, int m) {
   const int big = n > m ? n : m;
+  static const int forced = getenv("PDR_EMD_CLUSTER") ? atoi(getenv("PDR_EMD_CLUSTER")) : 0;     // A/B: 1, 2, 4 or 8
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
+    int cs = forced;
+    while (cs > 1 && big / cs < 128) cs /= 2;
+    return cs;
+  }
   int cs = 1;
   while (cs < kEmdMaxCluster && (long long)b * cs < 2 * kNumSMs && big / (cs * 2) >= 128) cs *= 2;
   return cs;

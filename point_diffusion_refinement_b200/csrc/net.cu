@@ -9,6 +9,8 @@
 //
 // This file: the fp32 SIMT GEMM (validation mode and small-problem path), GroupNorm finalisation,
 // attention pooling, grouping/gather kernels.  The tcgen05 (TF32) GEMM lives in gemm_tc.cu.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace pdr {
@@ -194,10 +196,16 @@ gemm_simt_kernel(const PdrGemmArgs a) {
 constexpr int kGnThreads = 256;
 constexpr int kGnSplit = 4;
 
+// Up to two independent GroupNorms per launch (blockIdx.z): the engine finalises the normalisations that become ready
+// together -- (first MLP layer, attention query|key) and (second MLP layer, attention scores) of a stage -- in one launch.
+struct GnBatch { PdrGnArgs g[2]; };
+
 __global__ void __launch_bounds__(kGnThreads)
-gn_finalize_kernel(const PdrGnArgs a) {
+gn_finalize_kernel(const GnBatch batch) {
   extern __shared__ double s_tot[];                 // [channels in range][3] = weighted sum, sum of squares, count
   __shared__ double s_red[kGnThreads][2];
+  const PdrGnArgs &a = batch.g[blockIdx.z];
+  if ((int)blockIdx.x >= a.batch) return;
   const int b = blockIdx.x;
   const int cpg = a.gn_channels / a.groups;
   const int gpc = (a.groups + gridDim.y - 1) / gridDim.y;           // groups per CTA
@@ -567,9 +575,7 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
   return check_launch("gemm_simt_kernel");
 }
 
-extern "C" int pdr_gn_finalize(const PdrGnArgs *args, void *stream) {
-  PDR_REQUIRE(args, "gn_finalize: null args");
-  const PdrGnArgs &a = *args;
+static int gn_check(const PdrGnArgs &a) {
   PDR_REQUIRE(a.nsrc >= 1 && a.nsrc <= 2 && a.batch > 0 && a.channels > 0, "gn_finalize: bad sizes");
   PDR_REQUIRE(a.gn_channels <= a.channels && a.groups > 0 && a.gn_channels % a.groups == 0,
               "gn_finalize: channels=%d gn=%d groups=%d ld=%d", a.channels, a.gn_channels, a.groups, a.ld_out);
@@ -577,11 +583,31 @@ extern "C" int pdr_gn_finalize(const PdrGnArgs *args, void *stream) {
   for (int s = 0; s < a.nsrc; ++s) tot += a.src[s].ncols;
   PDR_REQUIRE(tot == a.channels, "gn_finalize: sources cover %d of %d channels", tot, a.channels);
   PDR_REQUIRE(a.gamma && a.beta && a.sc && a.sh, "gn_finalize: null pointer");
-  const int split = a.groups >= kGnSplit ? kGnSplit : 1;
-  const size_t smem = (size_t)a.channels * 3 * sizeof(double);      // upper bound for any split
-  PDR_REQUIRE(smem <= 48 * 1024, "gn_finalize: too many channels");
-  gn_finalize_kernel<<<dim3(a.batch, split), kGnThreads, smem, (cudaStream_t)stream>>>(a);
+  PDR_REQUIRE((size_t)a.channels * 3 * sizeof(double) <= 48 * 1024, "gn_finalize: too many channels");
+  return PDR_OK;
+}
+
+extern "C" int pdr_gn_finalize_batch(const PdrGnArgs *args, int count, void *stream) {
+  PDR_REQUIRE(args && count >= 1 && count <= 2, "gn_finalize: count=%d not in {1, 2}", count);
+  GnBatch batch;
+  memset(&batch, 0, sizeof(batch));
+  int nb = 0, channels = 0, split = kGnSplit;
+  for (int i = 0; i < count; ++i) {
+    const int rc = gn_check(args[i]);
+    if (rc) return rc;
+    batch.g[i] = args[i];
+    nb = args[i].batch > nb ? args[i].batch : nb;
+    channels = args[i].channels > channels ? args[i].channels : channels;
+    if (args[i].groups < kGnSplit) split = 1;
+  }
+  const size_t smem = (size_t)channels * 3 * sizeof(double);      // upper bound for any split
+  gn_finalize_kernel<<<dim3(nb, split, count), kGnThreads, smem, (cudaStream_t)stream>>>(batch);
   return check_launch("gn_finalize_kernel");
+}
+
+extern "C" int pdr_gn_finalize(const PdrGnArgs *args, void *stream) {
+  PDR_REQUIRE(args, "gn_finalize: null args");
+  return pdr_gn_finalize_batch(args, 1, stream);
 }
 
 extern "C" int pdr_affine_rows(int batch, int rows_per_sample, int C, const float *x, int ldx, int pro_mode,

@@ -354,10 +354,10 @@ class FusedDenoiser:
                    info={"bytes": nbytes, "flops": 2 * M * N * K, "M": M, "N": N, "K": K})
         return st
 
-    def gn(self, sources, gn_module, batch=None, pad=4):
-        """sources: list of (Stats, col0, ncols, use_relu, mult).  Returns (sc View, sh View) with each source
-        padded to a multiple of `pad` columns (4; 32 for the consumers of pdr_stage_chain, which reads whole 32-column
-        blocks unguarded -- the pad entries are never written and stay zero)."""
+    def _gn_args(self, a, sources, gn_module, batch=None, pad=4):
+        """Fill the GnArgs `a` for sources = [(Stats, col0, ncols, use_relu, mult)].  Returns (sc View, sh View) with each
+        source padded to a multiple of `pad` columns (4; 32 for the consumers of pdr_stage_chain, which reads whole
+        32-column blocks -- the pad entries are never written and stay zero)."""
         rp = lambda c: (c + pad - 1) // pad * pad
         batch = self.B if batch is None else batch
         if isinstance(gn_module, MyGroupNorm):
@@ -367,7 +367,6 @@ class FusedDenoiser:
         channels = sum(s[2] for s in sources)
         ld_out = sum(rp(s[2]) for s in sources)
         sc, sh = self._zeros(batch, ld_out), self._zeros(batch, ld_out)
-        a = GnArgs()
         off = 0
         for i, (st, col0, ncols, use_relu, mult) in enumerate(sources):
             s = a.src[i]
@@ -382,9 +381,27 @@ class FusedDenoiser:
         beta = gnm.bias.detach().float().contiguous()
         a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(gnm.eps)
         a.sc, a.sh, a.ld_out = sc.data_ptr(), sh.data_ptr(), ld_out
-        self.keep += [a, gamma, beta]
-        self._emit("pdr_gn_finalize", ctypes.c_void_p(ctypes.addressof(a)))
+        self.keep += [gamma, beta]
         return View(sc), View(sh)
+
+    def gn(self, sources, gn_module, batch=None, pad=4):
+        """One GroupNorm finalisation (pdr_gn_finalize): statistics of the producing GEMMs -> per-sample (sc, sh)."""
+        a = GnArgs()
+        out = self._gn_args(a, sources, gn_module, batch, pad)
+        self.keep.append(a)
+        self._emit("pdr_gn_finalize", ctypes.c_void_p(ctypes.addressof(a)))
+        return out
+
+    def gn2(self, first, second):
+        """Two independent finalisations whose inputs are ready at the same point of the program, in ONE launch
+        (pdr_gn_finalize_batch): first / second = (sources, gn_module) or (sources, gn_module, pad).  98 single launches of
+        6-9 us each were 0.9 ms of the step; the pairs (first MLP layer, attention query|key) and (second MLP layer,
+        attention scores) of every stage go out together."""
+        arr = (GnArgs * 2)()
+        outs = [self._gn_args(arr[i], *spec) for i, spec in enumerate((first, second))]
+        self.keep.append(arr)
+        self._emit("pdr_gn_finalize_batch", ctypes.c_void_p(ctypes.addressof(arr)), 2)
+        return outs
 
     # ------------------------------------------------------------------------------------------------
     # module pieces
@@ -543,19 +560,9 @@ class FusedDenoiser:
             assert C0 == c_last and gathered is None, "identity residual needs the materialised grouped tensor"
             Rv = X0
             key = Y1.cols(offs[1], r4(c_key)); key_col = offs[1]
-        # remaining MLP layers
-        st_prev, prev_cols, prev_gn = st1, y_cols, first_gn
-        for li in range(1, len(layers)):
-            conv, gnm = layers[li]
-            scsh = self.gn([(st_prev, prev_cols[0], prev_cols[1], False, 1.0)], prev_gn)
-            W = _pack([(_conv_w(conv), [(0, conv.in_channels, r4(conv.in_channels))])], self.dev)
-            Yn = self._mat(M, conv.out_channels)
-            st_prev = self.gemm(y, W, _bias(conv, conv.out_channels, self.dev), Yn, rows_per_sample, pro=PRO_GN_RELU,
-                                scsh=scsh, add=self._resolve_emb(emb_views[li - 1]), want_stats=True)
-            y, prev_cols, prev_gn = Yn, (0, conv.out_channels), gnm
-        scsh_last = self.gn([(st_prev, prev_cols[0], prev_cols[1], False, 1.0)], prev_gn)
-        add_last = self._resolve_emb(emb_views[len(layers) - 1])
-        # ---- attention ---------------------------------------------------------------------------------
+        # ---- second MLP layer and the attention query / key path, interleaved so that the GroupNorm finalisations that
+        #      become ready together go out in one launch (gn2): (y1, query|key) after the first GEMM and the per-point query
+        #      GEMM, (y2, scores) after the second layer and the key-part GEMM --------------------------------------------
         qconv = att.feat_conv
         cq_in, cq = qconv.in_channels, qconv.out_channels
         Wq = _pack([(_conv_w(qconv), [(0, cq_in, r4(cq_in))])], self.dev)
@@ -564,7 +571,13 @@ class FusedDenoiser:
         stq = self.gemm(View(query.t, r4(cq_in), query.col0), Wq, _bias(qconv, cq, self.dev), Q, P, want_stats=True)
         wc = list(att.weight_conv)   # [ReLU, GN, Conv, ReLU, GN, Conv]
         gn_w1, conv_w1, gn_w2, conv_w2 = wc[1], wc[2], wc[4], wc[5]
-        sc1, sh1 = self.gn([(stq, 0, cq, True, float(K)), (st1, key_col, c_key, True, 1.0)], gn_w1)
+        scsh_y1, (sc1, sh1) = self.gn2(([(st1, y_cols[0], y_cols[1], False, 1.0)], first_gn),
+                                       ([(stq, 0, cq, True, float(K)), (st1, key_col, c_key, True, 1.0)], gn_w1))
+        conv2, gn2m = layers[1]
+        W2 = _pack([(_conv_w(conv2), [(0, conv2.in_channels, r4(conv2.in_channels))])], self.dev)
+        Y2 = self._mat(M, conv2.out_channels)
+        st_y2 = self.gemm(y, W2, _bias(conv2, conv2.out_channels, self.dev), Y2, rows_per_sample, pro=PRO_GN_RELU,
+                          scsh=scsh_y1, add=self._resolve_emb(emb_views[0]), want_stats=True)
         inter = conv_w1.out_channels
         w1 = _conv_w(conv_w1)
         W1q = _pack([(w1, [(0, cq, r4(cq))])], self.dev)
@@ -575,7 +588,20 @@ class FusedDenoiser:
         st_s1 = self.gemm(key, W1k, _bias(conv_w1, inter, self.dev), S1, rows_per_sample, pro=PRO_RELU_GN,
                           scsh=(sc1.cols(r4(cq), r4(c_key)), sh1.cols(r4(cq), r4(c_key))), rowadd=YQ, rowadd_div=K,
                           want_stats=True)
-        scsh2 = self.gn([(st_s1, 0, inter, True, 1.0)], gn_w2)
+        scsh_prev, scsh2 = self.gn2(([(st_y2, 0, conv2.out_channels, False, 1.0)], gn2m),
+                                    ([(st_s1, 0, inter, True, 1.0)], gn_w2))
+        y = Y2
+        # remaining MLP layers (mlp_depth 3: rest_mlp)
+        for li in range(2, len(layers)):
+            conv, gnm = layers[li]
+            W = _pack([(_conv_w(conv), [(0, conv.in_channels, r4(conv.in_channels))])], self.dev)
+            Yn = self._mat(M, conv.out_channels)
+            st_n = self.gemm(y, W, _bias(conv, conv.out_channels, self.dev), Yn, rows_per_sample, pro=PRO_GN_RELU,
+                             scsh=scsh_prev, add=self._resolve_emb(emb_views[li - 1]), want_stats=True)
+            scsh_prev = self.gn([(st_n, 0, conv.out_channels, False, 1.0)], gnm)
+            y = Yn
+        scsh_last = scsh_prev
+        add_last = self._resolve_emb(emb_views[len(layers) - 1])
         c_out = conv_w2.out_channels
         fo = list(att.feat_out_conv)  # [Conv, GN, ReLU]
         conv_v, gn_v = fo[0], fo[1]

@@ -44,8 +44,10 @@ def reference_drivers():
             yield ref_eval
     finally:
         sys.path[:] = saved_path
-        for name in set(sys.modules) - saved_mods:
-            del sys.modules[name]
+        for name in set(sys.modules) - saved_mods:         # only what came from the staging directory or is a stub
+            mod = sys.modules[name]
+            if name in stubs or (getattr(mod, "__file__", None) or "").startswith(PYREF):
+                del sys.modules[name]
         dropin.uninstall()
 
 
