@@ -229,8 +229,10 @@ int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ce
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);
 
 /* GroupNorm statistics -> per-sample per-channel affine (sc, sh), for a channel concatenation of up to
- * two sources (e.g. [query conv | key conv] in AttentionModule).  Channels >= gn_channels pass through
+ * PDR_GN_MAX_SOURCES sources (e.g. [query conv | key conv] in AttentionModule, the key conv possibly produced by
+ * several GEMM calls).  Channels >= gn_channels pass through
  * (sc = 1, sh = 0; MyGroupNorm, attention.py:6-23); pad columns of sc/sh are never written (keep them 0). */
+#define PDR_GN_MAX_SOURCES 4
 typedef struct PdrGnSource {
   const float *stats; int tiles_per_sample; int ld_stats;  /* (batch*tiles, ld_stats, 4) from pdr_gemm_fused */
   int col0; int ncols;                                     /* columns of that GEMM output used here */
@@ -242,7 +244,7 @@ typedef struct PdrGnSource {
                                                               of AttentionModule, which is expanded over K) */
 } PdrGnSource;
 typedef struct PdrGnArgs {
-  PdrGnSource src[2]; int nsrc;
+  PdrGnSource src[PDR_GN_MAX_SOURCES]; int nsrc;
   int batch; int channels; int gn_channels; int groups;
   const float *gamma; const float *beta; float eps;        /* (gn_channels) */
   float *sc; float *sh; int ld_out;                        /* (batch, ld_out) */

@@ -576,7 +576,7 @@ extern "C" int pdr_gemm_fused(const PdrGemmArgs *args, void *stream_) {
 }
 
 static int gn_check(const PdrGnArgs &a) {
-  PDR_REQUIRE(a.nsrc >= 1 && a.nsrc <= 2 && a.batch > 0 && a.channels > 0, "gn_finalize: bad sizes");
+  PDR_REQUIRE(a.nsrc >= 1 && a.nsrc <= PDR_GN_MAX_SOURCES && a.batch > 0 && a.channels > 0, "gn_finalize: bad sizes");
   PDR_REQUIRE(a.gn_channels <= a.channels && a.groups > 0 && a.gn_channels % a.groups == 0,
               "gn_finalize: channels=%d gn=%d groups=%d ld=%d", a.channels, a.gn_channels, a.groups, a.ld_out);
   int tot = 0;
