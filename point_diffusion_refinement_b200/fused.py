@@ -86,9 +86,6 @@ _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
 # a whole SM and would otherwise serialise against the 32-CTA FPS kernel.  Measured -0.27 ms / step (profiles/r02_experiments_ab.txt).
 _GEOM_OVERLAP = os.environ.get("PDR_GEOM_OVERLAP", "1") != "0"
 _GEOM_OVERLAP_CTAS = int(os.environ.get("PDR_GEOM_OVERLAP_CTAS", "116"))
-# PDR_SPLIT_WIDE=0 keeps the first GEMM of a stage in one piece whatever its width (see grouped_block)
-_SPLIT_WIDE = os.environ.get("PDR_SPLIT_WIDE", "1") != "0"
-_SPLIT_WIDE_MIN_ROWS = int(os.environ.get("PDR_SPLIT_WIDE_MIN_ROWS", "65536"))
 # PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
 _FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
 # PDR_FUSE_POOL=1 pools inside the score GEMM's epilogue (PdrGemmArgs.pool_*; bit-identical, scores never stored).
@@ -553,34 +550,9 @@ class FusedDenoiser:
         M = B * rows_per_sample
         Y1 = self._mat(M, col)
         A0 = gathered if gathered is not None else (X0.cols(0, Kp) if X0.C != Kp else X0)
-        # One GEMM for all sections -- unless its weights cannot stay resident in shared memory (N > 128: the kernel then
-        # streams a 32 KB weight tile with every 16 KB of A through a 2-3 stage ring and runs at 1.6 TB/s,
-        # profiles/r01_ncu_gemm16_v10_notes.txt).  Then it is cut at the section boundaries and into <= 128-column pieces,
-        # each a GEMM with resident weights; the gathered table rows they all re-read come from L2.
-        pieces = [(0, col)]
-        if _SPLIT_WIDE and gathered is not None and self.use_tf32 and M >= _SPLIT_WIDE_MIN_ROWS and col > 128:
-            cut = []
-            for o, (conv, n) in zip(offs, secs):
-                n4 = r4(n)
-                cut += [(o + c, min(128, n4 - c)) for c in range(0, n4, 128)]
-            key_pieces = sum(1 for c0, _ in cut if c0 >= offs[-1])
-            if key_pieces <= GN_MAX_SOURCES - 1:
-                pieces = cut
-        st_pieces = []
-        for pi, (c0, n) in enumerate(pieces):
-            last = pi == len(pieces) - 1
-            stp = self.gemm(A0, W1[c0:c0 + n].contiguous(), b1[c0:c0 + n].contiguous(), Y1.cols(c0, n), rows_per_sample,
-                            want_stats=True, zero_to=None if last else n)
-            st_pieces.append((stp, c0, n))
-
-        def st1_sources(col0, ncols, use_relu, mult):
-            """GroupNorm sources for columns [col0, col0 + ncols) of Y1, piece by piece."""
-            out = []
-            for stp, c0, n in st_pieces:
-                lo, hi = max(col0, c0), min(col0 + ncols, c0 + n)
-                if lo < hi:
-                    out.append((stp, lo - c0, hi - lo, use_relu, mult))
-            return out
+        # (Cutting a wide first GEMM into <= 128-column pieces with resident weights was measured SLOWER, r02l: every piece
+        #  re-gathers the A rows from L2 in 16-byte pieces, which is what bounds these GEMMs -- profiles/r02_experiments_ab.txt)
+        st1 = self.gemm(A0, W1, b1, Y1, rows_per_sample, want_stats=True)
         y = Y1.cols(offs[0], r4(c1))
         y_cols = (offs[0], c1)
         if fold_res:
@@ -604,8 +576,8 @@ class FusedDenoiser:
         stq = self.gemm(View(query.t, r4(cq_in), query.col0), Wq, _bias(qconv, cq, self.dev), Q, P, want_stats=True)
         wc = list(att.weight_conv)   # [ReLU, GN, Conv, ReLU, GN, Conv]
         gn_w1, conv_w1, gn_w2, conv_w2 = wc[1], wc[2], wc[4], wc[5]
-        scsh_y1, (sc1, sh1) = self.gn2((st1_sources(y_cols[0], y_cols[1], False, 1.0), first_gn),
-                                       ([(stq, 0, cq, True, float(K))] + st1_sources(key_col, c_key, True, 1.0), gn_w1))
+        scsh_y1, (sc1, sh1) = self.gn2(([(st1, y_cols[0], y_cols[1], False, 1.0)], first_gn),
+                                       ([(stq, 0, cq, True, float(K)), (st1, key_col, c_key, True, 1.0)], gn_w1))
         conv2, gn2m = layers[1]
         W2 = _pack([(_conv_w(conv2), [(0, conv2.in_channels, r4(conv2.in_channels))])], self.dev)
         Y2 = self._mat(M, conv2.out_channels)
