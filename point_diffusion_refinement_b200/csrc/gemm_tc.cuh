@@ -168,7 +168,10 @@ struct TcPlan {
 };
 
 // bytes of the TMA-store staging tiles (EPI 3): two 32 x 32 fp32 boxes per epilogue warp
-constexpr int kTmaStageBytes = kEpiWarps * 2 * 4096;
+// two staging tiles per epilogue warp; ONE for the 256-column tiles, whose 48 KB ring stages (A + streamed W) otherwise get
+// a 2-deep ring next to 96 KB of epilogue buffers (46 launches, 2.6 ms / step at ~1.5 TB/s: latency-bound, r02k)
+constexpr int tma_bufs(int bn) { return bn == 256 ? 1 : 2; }
+constexpr int tma_stage_bytes(int bn) { return kEpiWarps * tma_bufs(bn) * 4096; }
 
 // EPI: 0 = scalar epilogue, 1 = float4 epilogue, 2 = attention pooling over the K neighbour rows (no C store),
 //      3 = TMA-store epilogue (32 x 32 boxes through a 128B-swizzled staging tile, statistics read back column-wise)
@@ -978,12 +981,15 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   #pragma unroll
           for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4 *>(sadd + 4 * j);
           // the store that last read the tile about to be overwritten (two blocks ago) must have finished reading
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (lane == 0) {
+            if constexpr (tma_bufs(BN) == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           __syncwarp();
           // (explicit shared-space accesses: through a generic pointer into the dynamic region these would be LD.E/ST.E)
-          const uint32_t tile = s_tma + ((uint32_t)warp * 2u + tma_buf) * 4096u;
-          tma_buf ^= 1u;
+          const uint32_t tile = s_tma + ((uint32_t)warp * (uint32_t)tma_bufs(BN) + tma_buf) * 4096u;
+          if constexpr (tma_bufs(BN) == 2) tma_buf ^= 1u;
           {
             const uint32_t trow = tile + (uint32_t)lane * 128u;
             const uint32_t sw = (uint32_t)lane & 7u;
@@ -1259,7 +1265,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   else if (mode == 3) vec = (a.rowadd && a.rowadd_div < 8) ? (BN > 32 ? 1 : 0) : 3;
   else vec = (mode == 2 ? (a.rowadd != nullptr && BN > 32) : mode == 1) ? 1 : 0;
   const size_t epi = (size_t)(BN <= 128 ? 4 : 2) * 4 * BN * 16 +   // column partials: 2 epilogue groups (x 2 tile parities)
-                     (vec == 3 ? (size_t)kTmaStageBytes : 0);       // + the staging tiles of the TMA stores
+                     (vec == 3 ? (size_t)tma_stage_bytes(BN) : 0);  // + the staging tiles of the TMA stores
   const size_t static_smem = (size_t)(kEpiWarps * (vec == 3 ? 192 : 32 * 36)) * sizeof(float) + 512;
   const size_t budget = 226 * 1024 - static_smem;
   size_t smem = 0;
