@@ -253,17 +253,20 @@ int pdr_gn_finalize(const PdrGnArgs *args, void *stream);
 /* `count` (1 or 2) independent finalisations in ONE launch: args[0 .. count). */
 int pdr_gn_finalize_batch(const PdrGnArgs *args, int count, void *stream);
 
+/* `round_tf32` (pdr_affine_rows, pdr_attention_pool, pdr_gather_rows, pdr_group_geo_*): round the values written to the
+ * nearest TF32 number.  Set by callers whose output is read RAW by a tensor-core GEMM (gathered A operand, raw K tail,
+ * prologue-free A): the tensor core truncates fp32 operands, so unrounded tables would carry a toward-zero bias. */
 /* out[row, c] = pro(x[row, c]) (+add +R) materialised; same prologue semantics as the GEMM. */
 int pdr_affine_rows(int batch, int rows_per_sample, int C, const float *x, int ldx, int pro_mode,
                     const float *sc, const float *sh, int ld_scsh, const float *add, int ld_add, const float *R,
-                    int ldr, float *out, int ldo, void *stream);
+                    int ldr, float *out, int ldo, int round_tf32, void *stream);
 
 /* Soft-attention pooling over the K neighbours (attention.py:85-96):
  * out[b,p,c] = sum_k softmax_k(S[b,p,k,c] masked to k < max(count[b,p],1)) * relu(V[b,p,k,c]*sc[b,c]+sh[b,c]).
  * counts == NULL means 'all'.  S, V: (B*P*K, ld); out: (B*P, ldo) written at column offset 0 of `out`. */
 int pdr_attention_pool(int batch, int P, int K, int C, const float *S, int lds, const float *V, int ldv,
                        const float *sc, const float *sh, int ld_scsh, const int *counts, float *out, int ldo,
-                       void *stream);
+                       int round_tf32, void *stream);
 
 /* Ball-query grouping into channels-last rows [feat(C) | rel(3) | abs(3) | centre(3) | 0-pad] with the
  * subset=False fill rule (pointnet2_utils.py:376-410): counts == 0 -> feat = 0, abs = centre, rel = 0.
@@ -279,9 +282,9 @@ int pdr_group_knn(int batch, int n, int P, int K, int C, const float *feat, int 
  * [rel(3) | abs(3) | centre(3) | 0 0 0] (ball) or [d2 | w | nn_abs(3) | nn_rel(3) | x(3) | 0] (kNN), bit-identical to
  * the geometric channels pdr_group_ball / pdr_group_knn write, and src_row as pdr_group_src_rows. */
 int pdr_group_geo_ball(int batch, int n, int P, int K, const float *xyz, const float *centres, const int *idx,
-                       const int *counts, int fill_missing, float *geo, int *src_row, void *stream);
+                       const int *counts, int fill_missing, float *geo, int *src_row, int round_tf32, void *stream);
 int pdr_group_geo_knn(int batch, int n, int P, int K, const float *y, const float *x, const int64_t *idx,
-                      const float *dists, float *geo, int *src_row, void *stream);
+                      const float *dists, float *geo, int *src_row, int round_tf32, void *stream);
 /* Flat feature-table row of every grouped row: src_row[(b*P+p)*K+k] = b*n + idx[b,p,k], or -1 where the subset=False
  * fill rule zeroes the features (fill_missing != 0 and counts[b,p] == 0).  idx is int32 (ball query) or, with
  * idx_is_int64 != 0, int64 (pdr_knn_points).  Feeds PdrGemmArgs.a_rows. */
@@ -290,7 +293,7 @@ int pdr_group_src_rows(int batch, int n, int P, int K, const void *idx, int idx_
 /* out[b, j, 0:C] = src[b, idx[b,j], 0:C] (rows); idx == NULL copies row j.  Used for FPS centre features and
  * for placing a feature block into a column slice of a wider buffer (free concatenation). */
 int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, const int *idx, float *out,
-                    int ldo, void *stream);
+                    int ldo, int round_tf32, void *stream);
 
 /* ================================================================================================
  * Fused stage: one grouped stage of the network -- the chain of 1x1 convolutions over the same grouped rows that

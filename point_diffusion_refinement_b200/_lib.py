@@ -56,16 +56,16 @@ SIGNATURES = {
     "pdr_gn_finalize": [_ptr, _ptr],
     "pdr_gn_finalize_batch": [_ptr, _c_int, _ptr],
     "pdr_affine_rows": [_c_int, _c_int, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr, _c_int, _ptr, _c_int, _ptr, _c_int,
-                        _ptr, _c_int, _ptr],
+                        _ptr, _c_int, _c_int, _ptr],
     "pdr_attention_pool": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _ptr,
-                           _c_int, _ptr],
+                           _c_int, _c_int, _ptr],
     "pdr_group_ball": [_c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr,
                        _c_int, _ptr],
     "pdr_group_knn": [_c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
-    "pdr_group_geo_ball": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr],
-    "pdr_group_geo_knn": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "pdr_group_geo_ball": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr],
+    "pdr_group_geo_knn": [_c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
     "pdr_group_src_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _ptr],
-    "pdr_gather_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr],
+    "pdr_gather_rows": [_c_int, _c_int, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr, _c_int, _c_int, _ptr],
     "pdr_stage_chain_tile_rows": [],
     "pdr_stage_chain": [_ptr, _ptr],
 }

@@ -193,6 +193,13 @@ gemm_simt_kernel(const PdrGemmArgs a) {
 // w, w+8, ...; the 8 warp partials are then added in warp order), in double, so the result is
 // deterministic; variance is E[x^2] - mean^2 (biased, like nn.GroupNorm).
 // ------------------------------------------------------------------------------------------------
+// Round-to-nearest (ties away) to TF32, applied by the kernels that PRODUCE the tables the tensor-core GEMMs read raw (gathered
+// A operand, raw K tail, prologue-free dense A): cp.async copies them straight into the MMA stage and the tensor core
+// TRUNCATES fp32 operands to 10 mantissa bits, so unrounded producers would put a toward-zero bias on every such operand.
+__device__ __forceinline__ float rtf32(float x, int on) {
+  return on ? __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u) : x;
+}
+
 constexpr int kGnThreads = 256;
 constexpr int kGnSplit = 4;
 
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(256)
 affine_rows_kernel(int rows_per_sample, int C, const float *__restrict__ x, int ldx, int mode,
                    const float *__restrict__ sc, const float *__restrict__ sh, int ld_scsh,
                    const float *__restrict__ add, int ld_add, const float *__restrict__ R, int ldr,
-                   float *__restrict__ out, int ldo, long long total) {
+                   float *__restrict__ out, int ldo, long long total, int round_tf32) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -303,7 +310,7 @@ affine_rows_kernel(int rows_per_sample, int C, const float *__restrict__ x, int 
   if (mode != PDR_PRO_NONE) v = pro_apply(mode, v, __ldg(sc + (size_t)b * ld_scsh + c), __ldg(sh + (size_t)b * ld_scsh + c));
   if (add) v += __ldg(add + (size_t)b * ld_add + c);
   if (R) v += R[row * ldr + c];
-  out[row * ldo + c] = v;
+  out[row * ldo + c] = rtf32(v, round_tf32);
 }
 
 // Attention pooling: one thread per (b, p, c); the K scores/values of a (p, c) are strided by ld, consecutive
@@ -313,7 +320,7 @@ template <int KT>
 __global__ void __launch_bounds__(256)
 attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds, const float *__restrict__ V,
                       int ldv, const float *__restrict__ sc, const float *__restrict__ sh, int ld_scsh,
-                      const int *__restrict__ counts, float *__restrict__ out, int ldo, long long total) {
+                      const int *__restrict__ counts, float *__restrict__ out, int ldo, long long total, int round_tf32) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -346,7 +353,7 @@ attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds,
       num = fmaf(e, fmaxf(fmaf(v[(size_t)k * ldv], gs, gh), 0.f), num);
     }
   }
-  out[bp * ldo + c] = num / den;
+  out[bp * ldo + c] = rtf32(num / den, round_tf32);
 }
 
 // Ball-query grouping.  A warp assembles 32 consecutive output rows: lane u first fetches the neighbour index,
@@ -432,14 +439,14 @@ group_knn_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int
 
 __global__ void __launch_bounds__(256)
 gather_rows_kernel2(int n, int P, int C, const float *__restrict__ src, int lds, const int *__restrict__ idx,
-                    float *__restrict__ out, int ldo, long long total) {
+                    float *__restrict__ out, int ldo, long long total, int round_tf32) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
   const long long bp = i / C;
   const int b = (int)(bp / P);
   const int j = idx ? __ldg(idx + bp) : (int)(bp % P);
-  out[bp * ldo + c] = __ldg(src + ((size_t)b * n + j) * lds + c);
+  out[bp * ldo + c] = rtf32(__ldg(src + ((size_t)b * n + j) * lds + c), round_tf32);
 }
 
 // Geometric channels + table row of every grouped row in one pass, thread per row (the form the gathered-A GEMM
@@ -448,7 +455,7 @@ gather_rows_kernel2(int n, int P, int C, const float *__restrict__ src, int lds,
 __global__ void __launch_bounds__(256)
 group_geo_ball_kernel(int n, int P, int K, const float *__restrict__ xyz, const float *__restrict__ centres,
                       const int *__restrict__ idx, const int *__restrict__ counts, int fill_missing,
-                      float *__restrict__ geo, int *__restrict__ src_row, int rows) {
+                      float *__restrict__ geo, int *__restrict__ src_row, int rows, int rt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;             // (b*P + p)*K + k
   if (row >= rows) return;
   const int bp = row / K;
@@ -459,9 +466,9 @@ group_geo_ball_kernel(int n, int P, int K, const float *__restrict__ xyz, const 
   float ax = cx, ay = cy, az = cz;
   if (!miss) { ax = __ldg(xyz + (size_t)fb * 3); ay = __ldg(xyz + (size_t)fb * 3 + 1); az = __ldg(xyz + (size_t)fb * 3 + 2); }
   float4 *o = reinterpret_cast<float4 *>(geo + (size_t)row * 12);
-  o[0] = make_float4(ax - cx, ay - cy, az - cz, ax);
-  o[1] = make_float4(ay, az, cx, cy);
-  o[2] = make_float4(cz, 0.f, 0.f, 0.f);
+  o[0] = make_float4(rtf32(ax - cx, rt), rtf32(ay - cy, rt), rtf32(az - cz, rt), rtf32(ax, rt));
+  o[1] = make_float4(rtf32(ay, rt), rtf32(az, rt), rtf32(cx, rt), rtf32(cy, rt));
+  o[2] = make_float4(rtf32(cz, rt), 0.f, 0.f, 0.f);
   src_row[row] = miss ? -1 : fb;
 }
 
@@ -469,7 +476,7 @@ group_geo_ball_kernel(int n, int P, int K, const float *__restrict__ xyz, const 
 __global__ void __launch_bounds__(256)
 group_geo_knn_kernel(int n, int P, int K, const float *__restrict__ y, const float *__restrict__ x,
                      const long long *__restrict__ idx, const float *__restrict__ dists, float *__restrict__ geo,
-                     int *__restrict__ src_row, int rows) {
+                     int *__restrict__ src_row, int rows, int rt) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const int bp = row / K;
@@ -481,9 +488,9 @@ group_geo_knn_kernel(int n, int P, int K, const float *__restrict__ y, const flo
   const float xx = __ldg(x + (size_t)bp * 3), xy = __ldg(x + (size_t)bp * 3 + 1), xz = __ldg(x + (size_t)bp * 3 + 2);
   const float yx = __ldg(y + (size_t)fb * 3), yy = __ldg(y + (size_t)fb * 3 + 1), yz = __ldg(y + (size_t)fb * 3 + 2);
   float4 *o = reinterpret_cast<float4 *>(geo + (size_t)row * 12);
-  o[0] = make_float4(d, w, yx, yy);
-  o[1] = make_float4(yz, yx - xx, yy - xy, yz - xz);
-  o[2] = make_float4(xx, xy, xz, 0.f);
+  o[0] = make_float4(rtf32(d, rt), rtf32(w, rt), rtf32(yx, rt), rtf32(yy, rt));
+  o[1] = make_float4(rtf32(yz, rt), rtf32(yx - xx, rt), rtf32(yy - xy, rt), rtf32(yz - xz, rt));
+  o[2] = make_float4(rtf32(xx, rt), rtf32(xy, rt), rtf32(xz, rt), 0.f);
   src_row[row] = fb;
 }
 
@@ -612,28 +619,28 @@ extern "C" int pdr_gn_finalize(const PdrGnArgs *args, void *stream) {
 
 extern "C" int pdr_affine_rows(int batch, int rows_per_sample, int C, const float *x, int ldx, int pro_mode,
                                const float *sc, const float *sh, int ld_scsh, const float *add, int ld_add,
-                               const float *R, int ldr, float *out, int ldo, void *stream) {
+                               const float *R, int ldr, float *out, int ldo, int round_tf32, void *stream) {
   PDR_REQUIRE(batch > 0 && rows_per_sample > 0 && C > 0 && ldo >= C && x && out, "affine_rows: bad arguments");
   const long long total = (long long)batch * rows_per_sample * C;
   affine_rows_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(rows_per_sample, C, x, ldx, pro_mode, sc, sh,
-                                                                          ld_scsh, add, ld_add, R, ldr, out, ldo, total);
+                                                                          ld_scsh, add, ld_add, R, ldr, out, ldo, total, round_tf32);
   return check_launch("affine_rows_kernel");
 }
 
 extern "C" int pdr_attention_pool(int batch, int P, int K, int C, const float *S, int lds, const float *V, int ldv,
                                   const float *sc, const float *sh, int ld_scsh, const int *counts, float *out,
-                                  int ldo, void *stream) {
+                                  int ldo, int round_tf32, void *stream) {
   PDR_REQUIRE(batch > 0 && P > 0 && K > 0 && C > 0 && S && V && sc && sh && out, "attention_pool: bad arguments");
   const long long total = (long long)batch * P * C;
   if (K == 32)
     attention_pool_kernel<32><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
-                                                                                   ld_scsh, counts, out, ldo, total);
+                                                                                   ld_scsh, counts, out, ldo, total, round_tf32);
   else if (K == 8)
     attention_pool_kernel<8><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
-                                                                                  ld_scsh, counts, out, ldo, total);
+                                                                                  ld_scsh, counts, out, ldo, total, round_tf32);
   else
     attention_pool_kernel<0><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
-                                                                                  ld_scsh, counts, out, ldo, total);
+                                                                                  ld_scsh, counts, out, ldo, total, round_tf32);
   return check_launch("attention_pool_kernel");
 }
 
@@ -662,24 +669,25 @@ extern "C" int pdr_group_knn(int batch, int n, int P, int K, int C, const float 
 }
 
 extern "C" int pdr_group_geo_ball(int batch, int n, int P, int K, const float *xyz, const float *centres, const int *idx,
-                                  const int *counts, int fill_missing, float *geo, int *src_row, void *stream) {
+                                  const int *counts, int fill_missing, float *geo, int *src_row, int round_tf32,
+                                  void *stream) {
   PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && xyz && centres && idx && geo && src_row, "group_geo_ball: bad arguments");
   const long long rows = (long long)batch * P * K;
   PDR_REQUIRE(rows < (1ll << 31) && (long long)batch * n < (1ll << 31) && ((uintptr_t)geo % 16) == 0,
               "group_geo_ball: too many rows or unaligned output");
   group_geo_ball_kernel<<<blocks_for(rows), 256, 0, (cudaStream_t)stream>>>(n, P, K, xyz, centres, idx, counts, fill_missing,
-                                                                           geo, src_row, (int)rows);
+                                                                           geo, src_row, (int)rows, round_tf32);
   return check_launch("group_geo_ball_kernel");
 }
 
 extern "C" int pdr_group_geo_knn(int batch, int n, int P, int K, const float *y, const float *x, const int64_t *idx,
-                                 const float *dists, float *geo, int *src_row, void *stream) {
+                                 const float *dists, float *geo, int *src_row, int round_tf32, void *stream) {
   PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && K > 0 && y && x && idx && dists && geo && src_row, "group_geo_knn: bad arguments");
   const long long rows = (long long)batch * P * K;
   PDR_REQUIRE(rows < (1ll << 31) && (long long)batch * n < (1ll << 31) && ((uintptr_t)geo % 16) == 0,
               "group_geo_knn: too many rows or unaligned output");
   group_geo_knn_kernel<<<blocks_for(rows), 256, 0, (cudaStream_t)stream>>>(n, P, K, y, x, (const long long *)idx, dists, geo,
-                                                                          src_row, (int)rows);
+                                                                          src_row, (int)rows, round_tf32);
   return check_launch("group_geo_knn_kernel");
 }
 
@@ -695,9 +703,9 @@ extern "C" int pdr_group_src_rows(int batch, int n, int P, int K, const void *id
 }
 
 extern "C" int pdr_gather_rows(int batch, int n, int P, int C, const float *src, int lds, const int *idx, float *out,
-                               int ldo, void *stream) {
+                               int ldo, int round_tf32, void *stream) {
   PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && C > 0 && src && out, "gather_rows: bad arguments");
   const long long total = (long long)batch * P * C;
-  gather_rows_kernel2<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, C, src, lds, idx, out, ldo, total);
+  gather_rows_kernel2<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, C, src, lds, idx, out, ldo, total, round_tf32);
   return check_launch("gather_rows_kernel");
 }

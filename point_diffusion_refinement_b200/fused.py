@@ -86,6 +86,8 @@ _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
 # a whole SM and would otherwise serialise against the 32-CTA FPS kernel.  Measured -0.27 ms / step (profiles/r02_experiments_ab.txt).
 _GEOM_OVERLAP = os.environ.get("PDR_GEOM_OVERLAP", "1") != "0"
 _GEOM_OVERLAP_CTAS = int(os.environ.get("PDR_GEOM_OVERLAP_CTAS", "116"))
+# PDR_ROUND_TABLES=0: the kernels that produce raw GEMM operands (feature tables, geometric channels) do not round them to TF32
+_ROUND_TABLES = os.environ.get("PDR_ROUND_TABLES", "1") != "0"
 # PDR_FUSE_GATHER=0 materialises every grouped tensor (pdr_group_ball / pdr_group_knn) as the fp32 path always does
 _FUSE_GATHER = os.environ.get("PDR_FUSE_GATHER", "1") != "0"
 # PDR_FUSE_POOL=1 pools inside the score GEMM's epilogue (PdrGemmArgs.pool_*; bit-identical, scores never stored).
@@ -210,6 +212,8 @@ class FusedDenoiser:
         self.B, self.N = batch, n_points
         self.dev = next(net.parameters()).device
         self.use_tf32 = int(bool(use_tf32))
+        # producers of tables the tensor-core GEMMs read RAW round them to TF32 (the tensor core would truncate: header)
+        self.rt = self.use_tf32 if _ROUND_TABLES else 0
         self.use_graph = use_graph
         self.include_t = bool(hp["include_t"])
         self.lib = _lib.lib()
@@ -477,7 +481,7 @@ class FusedDenoiser:
             geo = self._mat(rows, 12)
             src = self._zeros(rows, dtype=torch.int32)
             self._emit("pdr_group_geo_ball", B, n, P, K, ptr(pts), ptr(centres), ptr(idx), ptr(cnt), int(fill),
-                       ctypes.c_void_p(geo.ptr), ptr(src))
+                       ctypes.c_void_p(geo.ptr), ptr(src), self.rt)
             return GatheredA(feat, src, geo, C, 9)
         X0 = self._mat(rows, C + 9)
         self._emit("pdr_group_ball", B, n, P, K, C, ctypes.c_void_p(feat.ptr), feat.ld, ptr(pts), ptr(centres), ptr(idx),
@@ -493,7 +497,7 @@ class FusedDenoiser:
             geo = self._mat(rows, 12)
             src = self._zeros(rows, dtype=torch.int32)
             self._emit("pdr_group_geo_knn", B, n_k, n_u, K, ptr(known_xyz), ptr(unknown_xyz), ptr(kidx), ptr(kd),
-                       ctypes.c_void_p(geo.ptr), ptr(src))
+                       ctypes.c_void_p(geo.ptr), ptr(src), self.rt)
             return GatheredA(feat, src, geo, C, 11)
         X0 = self._mat(rows, C + 11)
         self._emit("pdr_group_knn", B, n_k, n_u, K, C, ctypes.c_void_p(feat.ptr), feat.ld, ptr(known_xyz),
@@ -638,7 +642,8 @@ class FusedDenoiser:
         scv, shv = self.gn([(st_v, 0, c_out, False, 1.0)], gn_v)
         self._emit("pdr_attention_pool", B, P, K, c_out, ctypes.c_void_p(S.ptr), S.ld, ctypes.c_void_p(V.ptr), V.ld,
                    ctypes.c_void_p(scv.ptr), ctypes.c_void_p(shv.ptr), scv.ld,
-                   ctypes.c_void_p(counts.data_ptr()) if counts is not None else None, ctypes.c_void_p(out.ptr), out.ld)
+                   ctypes.c_void_p(counts.data_ptr()) if counts is not None else None, ctypes.c_void_p(out.ptr), out.ld,
+                   self.rt)
 
     def _stage_chain(self, name, gathered, K, rows_per_sample, layers, lay, res_conv, key_conv, att, query, counts, out,
                      emb_views):
@@ -760,7 +765,7 @@ class FusedDenoiser:
         self._emit("pdr_affine_rows", B, rows_per_sample, c_last, ctypes.c_void_p(y.ptr), y.ld, PRO_GN_RELU,
                    ctypes.c_void_p(sc.ptr), ctypes.c_void_p(sh.ptr), sc.ld,
                    ctypes.c_void_p(add.ptr) if add is not None else None, add.ld if add is not None else 0,
-                   ctypes.c_void_p(Rv.ptr), Rv.ld, ctypes.c_void_p(out.ptr), out.ld)
+                   ctypes.c_void_p(Rv.ptr), Rv.ld, ctypes.c_void_p(out.ptr), out.ld, self.rt)
 
     # ------------------------------------------------------------------------------------------------
     # program construction
@@ -861,7 +866,7 @@ class FusedDenoiser:
                        ctypes.c_void_p(idx.data_ptr()))
             nx = self._zeros(B, n_lvl[i + 1], 3)
             self._emit("pdr_gather_rows", B, n_lvl[i], n_lvl[i + 1], 3, ctypes.c_void_p(xyz[i].data_ptr()), 3,
-                       ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(nx.data_ptr()), 3)
+                       ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(nx.data_ptr()), 3, 0)      # coordinates: never rounded
             fps_idx.append(idx); xyz.append(nx)
 
         for i in range(L):
@@ -887,7 +892,7 @@ class FusedDenoiser:
             cm = enc_map_dim[i] if i < L else 0
             Fl.append(self._mat(B * n_lvl[i], cm + own_dim[i]))
         self._emit("pdr_gather_rows", B, N, N, 3, ctypes.c_void_p(xyz[0].data_ptr()), 3, None,
-                   ctypes.c_void_p(Fl[0].cols(enc_map_dim[0], 3).ptr), Fl[0].ld)
+                   ctypes.c_void_p(Fl[0].cols(enc_map_dim[0], 3).ptr), Fl[0].ld, self.rt)
         for i in range(L):
             cm = enc_map_dim[i]
             fm = net.encoder_feature_map[i]
@@ -907,7 +912,7 @@ class FusedDenoiser:
             X0 = group_ball(Fl[i].cols(0, Cin), Cin, xyz[i], n_lvl[i], xyz[i + 1], n_lvl[i + 1], idx.shape[2], idx, cnt, False)
             Qf = self._mat(B * n_lvl[i + 1], Cin)
             self._emit("pdr_gather_rows", B, n_lvl[i], n_lvl[i + 1], Cin, ctypes.c_void_p(Fl[i].ptr), Fl[i].ld,
-                       ctypes.c_void_p(fps_idx[i].data_ptr()), ctypes.c_void_p(Qf.ptr), Qf.ld)
+                       ctypes.c_void_p(fps_idx[i].data_ptr()), ctypes.c_void_p(Qf.ptr), Qf.ld, self.rt)
             cm_next = enc_map_dim[i + 1] if i + 1 < L else 0
             self.grouped_block("sa%d" % i, X0, Cin + 9, idx.shape[2], n_lvl[i + 1] * idx.shape[2], sa.mlps[0],
                                sa.attention_modules[0], Qf, cnt, Fl[i + 1].cols(cm_next, own_dim[i + 1]), plans[("sa", i)])
@@ -920,7 +925,7 @@ class FusedDenoiser:
             cd = dec_dim[lvl] if lvl < L else own_dim[L]
             Gl[lvl] = self._mat(B * n_lvl[lvl], dec_map_dim[lvl] + cd + (3 if lvl == 0 else 0))
         self._emit("pdr_gather_rows", B, n_lvl[L], n_lvl[L], own_dim[L], ctypes.c_void_p(Fl[L].ptr), Fl[L].ld, None,
-                   ctypes.c_void_p(Gl[L].cols(dec_map_dim[L], own_dim[L]).ptr), Gl[L].ld)
+                   ctypes.c_void_p(Gl[L].cols(dec_map_dim[L], own_dim[L]).ptr), Gl[L].ld, self.rt)
         for lvl in range(L, -1, -1):
             cdm = dec_map_dim[lvl]
             cd = dec_dim[lvl] if lvl < L else own_dim[L]
@@ -945,16 +950,16 @@ class FusedDenoiser:
             self.grouped_block("fp%d.mlp1" % (lvl - 1), X0, Ck + 11, Kknn, n_u * Kknn, fp.mlp1, fp.attention_module, skip,
                                None, H.cols(0, D), plans[("fp1", lvl - 1)])
             self._emit("pdr_gather_rows", B, n_u, n_u, cskip, ctypes.c_void_p(skip.ptr), skip.ld, None,
-                       ctypes.c_void_p(H.cols(D, cskip).ptr), H.ld)
+                       ctypes.c_void_p(H.cols(D, cskip).ptr), H.ld, self.rt)
             self._emit("pdr_gather_rows", B, n_u, n_u, 3, ctypes.c_void_p(xyz[lvl - 1].data_ptr()), 3, None,
-                       ctypes.c_void_p(H.cols(D + cskip, 3).ptr), H.ld)
+                       ctypes.c_void_p(H.cols(D + cskip, 3).ptr), H.ld, self.rt)
             self.pointwise_mlp("fp%d.mlp2" % (lvl - 1), H, D + cskip + 3, n_u, fp.mlp2,
                                Gl[lvl - 1].cols(dec_map_dim[lvl - 1], D), plans[("fp2", lvl - 1)])
 
         # ---- head: cat[mapped, feat, xyz] -> Conv1d -> GN -> ReLU -> Conv1d ------------------------------
         c_head_in = dec_map_dim[0] + dec_dim[0] + 3
         self._emit("pdr_gather_rows", B, N, N, 3, ctypes.c_void_p(xyz[0].data_ptr()), 3, None,
-                   ctypes.c_void_p(Gl[0].cols(dec_map_dim[0] + dec_dim[0], 3).ptr), Gl[0].ld)
+                   ctypes.c_void_p(Gl[0].cols(dec_map_dim[0] + dec_dim[0], 3).ptr), Gl[0].ld, self.rt)
         head = list(net.fc_lyaer)   # [Conv1d, GroupNorm, act, Conv1d]
         conv_a, gn_a, conv_b = head[0], head[1], head[3]
         assert isinstance(gn_a, nn.GroupNorm) and conv_a.in_channels == c_head_in
@@ -994,7 +999,7 @@ class FusedDenoiser:
                 n, P, K = m_lvl[i], m_lvl[i + 1], c_arch["nsample"][i]
                 idx = self._zeros(B, P, dtype=torch.int32)
                 self._emit("pdr_furthest_point_sampling", B, n, P, ptr(uvw[i]), None, ptr(idx))
-                self._emit("pdr_gather_rows", B, n, P, 3, ptr(uvw[i]), 3, ptr(idx), ptr(uvw[i + 1]), 3)
+                self._emit("pdr_gather_rows", B, n, P, 3, ptr(uvw[i]), 3, ptr(idx), ptr(uvw[i + 1]), 3, 0)
                 fps_idx.append(idx)
                 bidx = self._zeros(B, P, K, dtype=torch.int32)
                 cnt = self._zeros(B, P, dtype=torch.int32)
@@ -1004,13 +1009,13 @@ class FusedDenoiser:
                 X0 = self.group_ball(Fc[i], Cin, uvw[i], n, uvw[i + 1], P, K, bidx, cnt, False)
                 Qf = self._mat(B * P, Cin)
                 self._emit("pdr_gather_rows", B, n, P, Cin, ctypes.c_void_p(Fc[i].ptr), Fc[i].ld, ptr(idx),
-                           ctypes.c_void_p(Qf.ptr), Qf.ld)
+                           ctypes.c_void_p(Qf.ptr), Qf.ld, self.rt)
                 m = sa.mlps[0]
                 self.grouped_block("cond_sa%d" % i, X0, Cin + 9, K, P * K, m, sa.attention_modules[0], Qf, cnt,
                                    Fc[i + 1], [None] * len(self._mlp_layers(m)))
             # decoder: dec[L] = enc[L]; dec[i] = KnnFP_i(uvw[i], uvw[i+1], enc[i], dec[i+1])
             self._emit("pdr_gather_rows", B, m_lvl[L], m_lvl[L], enc_C[L], ctypes.c_void_p(Fc[L].ptr), Fc[L].ld, None,
-                       ctypes.c_void_p(Dc[L].ptr), Dc[L].ld)
+                       ctypes.c_void_p(Dc[L].ptr), Dc[L].ld, self.rt)
             for i in range(L - 1, -1, -1):
                 fp = net.FP_modules_condition[i]
                 n_u, n_k = m_lvl[i], m_lvl[i + 1]
@@ -1024,9 +1029,9 @@ class FusedDenoiser:
                 self.grouped_block("cond_fp%d.mlp1" % i, X0, Ck + 11, Kknn, n_u * Kknn, fp.mlp1, fp.attention_module,
                                    Fc[i], None, H.cols(0, D), [None] * len(self._mlp_layers(fp.mlp1)))
                 self._emit("pdr_gather_rows", B, n_u, n_u, cskip, ctypes.c_void_p(Fc[i].ptr), Fc[i].ld, None,
-                           ctypes.c_void_p(H.cols(D, cskip).ptr), H.ld)
+                           ctypes.c_void_p(H.cols(D, cskip).ptr), H.ld, self.rt)
                 self._emit("pdr_gather_rows", B, n_u, n_u, 3, ptr(uvw[i]), 3, None,
-                           ctypes.c_void_p(H.cols(D + cskip, 3).ptr), H.ld)
+                           ctypes.c_void_p(H.cols(D + cskip, 3).ptr), H.ld, self.rt)
                 self.pointwise_mlp("cond_fp%d.mlp2" % i, H, D + cskip + 3, n_u, fp.mlp2, Dc[i],
                                    [None] * len(self._mlp_layers(fp.mlp2)))
         finally:
@@ -1043,7 +1048,8 @@ class FusedDenoiser:
             dst.copy_(src)
         for views, feats in ((self._enc_cl, cs.encoder), (self._dec_cl, cs.decoder)):
             for v, f in zip(views, feats):
-                v.t[:, :v.C] = f.transpose(1, 2).reshape(-1, v.C)
+                vals = f.transpose(1, 2).reshape(-1, v.C)
+                v.t[:, :v.C] = tf32_round(vals.contiguous()) if self.rt else vals
         self._condition_embeddings(cs.global_feature, label)
 
     def encode_condition(self, condition, label):
@@ -1059,9 +1065,10 @@ class FusedDenoiser:
             uvw = condition[:, :, 0:3]
             self._uvw[0].copy_(uvw)
             F0 = self._enc_cl[0].t.view(B, M, -1)           # level-0 condition features: [partial feats | uvw]
+            rnd = (lambda t: tf32_round(t.contiguous())) if self.rt else (lambda t: t)
             if n_in > 0:
-                F0[:, :, 0:n_in] = condition[:, :, 3:3 + n_in]
-            F0[:, :, n_in:n_in + 3] = uvw
+                F0[:, :, 0:n_in] = rnd(condition[:, :, 3:3 + n_in])
+            F0[:, :, n_in:n_in + 3] = rnd(uvw)
             if self.use_graph:
                 if self.cond_graph is None:
                     for op in self.cond_ops:                 # warm-up outside capture

@@ -251,8 +251,11 @@ def test_group_geo_kernels_match_the_grouping_kernels(cuda_lib):
         call("pdr_group_ball", B, n, P, K, 0, None, 0, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(ref), 12, stream_ptr(xyz))
         call("pdr_group_src_rows", B, n, P, K, dptr(idx), 0, dptr(cnt), fill, dptr(src_ref), stream_ptr(xyz))
         geo = torch.full((rows, 12), float("nan"), device=DEV); src = torch.empty(rows, dtype=torch.int32, device=DEV)
-        call("pdr_group_geo_ball", B, n, P, K, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(geo), dptr(src), stream_ptr(xyz))
+        call("pdr_group_geo_ball", B, n, P, K, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(geo), dptr(src), 0, stream_ptr(xyz))
         assert torch.equal(geo, ref) and torch.equal(src, src_ref)
+        # round_tf32: the same values rounded to the nearest TF32 number (what the tensor core would otherwise truncate)
+        call("pdr_group_geo_ball", B, n, P, K, dptr(xyz), dptr(centres), dptr(idx), dptr(cnt), fill, dptr(geo), dptr(src), 1, stream_ptr(xyz))
+        assert torch.equal(geo, ((ref.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32))
     Kn = 8
     kn = knn.knn_points(centres, xyz, K=Kn)
     rows = B * P * Kn
@@ -260,7 +263,7 @@ def test_group_geo_kernels_match_the_grouping_kernels(cuda_lib):
     call("pdr_group_knn", B, n, P, Kn, 0, None, 0, dptr(xyz), dptr(centres), dptr(kn.idx), dptr(kn.dists), dptr(ref), 12, stream_ptr(xyz))
     call("pdr_group_src_rows", B, n, P, Kn, dptr(kn.idx), 1, None, 0, dptr(src_ref), stream_ptr(xyz))
     geo = torch.full((rows, 12), float("nan"), device=DEV); src = torch.empty(rows, dtype=torch.int32, device=DEV)
-    call("pdr_group_geo_knn", B, n, P, Kn, dptr(xyz), dptr(centres), dptr(kn.idx), dptr(kn.dists), dptr(geo), dptr(src), stream_ptr(xyz))
+    call("pdr_group_geo_knn", B, n, P, Kn, dptr(xyz), dptr(centres), dptr(kn.idx), dptr(kn.dists), dptr(geo), dptr(src), 0, stream_ptr(xyz))
     assert torch.equal(geo, ref) and torch.equal(src, src_ref)
 
 
@@ -288,7 +291,7 @@ def test_gemm_pooling_epilogue_equals_attention_pool(cuda_lib, shape):
     S, _ = _run(cuda_lib, A, W, bias, B, rps, N, 2, sc, sh, None, None, None, 0, use_tf32=True, want_stats=False)
     ref = torch.zeros(B * P, ldn + 4, device=DEV)
     call("pdr_attention_pool", B, P, PK, N, dptr(S), S.stride(0), dptr(V), ldn, dptr(vsc), dptr(vsh), ldn, dptr(counts),
-         dptr(ref), ldn + 4, stream_ptr(S))
+         dptr(ref), ldn + 4, 0, stream_ptr(S))
     out = torch.zeros(B * P, ldn + 4, device=DEV)
     a = GemmArgs()
     a.A, a.lda, a.K = A.data_ptr(), A.stride(0), K

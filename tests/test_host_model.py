@@ -225,3 +225,15 @@ def test_geometry_overlap_program_layout(cuda_lib, monkeypatch):
     caps = [g.max_ctas for g in on.keep if isinstance(g, fused.GemmArgs)]
     assert sum(1 for c in caps if c) == 7 and set(caps) == {0, fused._GEOM_OVERLAP_CTAS}
     assert all(g.max_ctas == 0 for g in off.keep if isinstance(g, fused.GemmArgs))
+
+
+def test_builtin_hdf5_writer_is_readable_by_h5py(tmp_path):
+    """the built-in HDF5 writer against the real library -- runs wherever h5py is installed (not in this image)."""
+    h5py = pytest.importorskip("h5py")
+    from point_diffusion_refinement_b200 import results_io
+    data = np.random.default_rng(0).standard_normal((5, 64, 3)).astype(np.float32)
+    path = str(tmp_path / "mvp_generated_data_64pts.h5")
+    results_io.write_hdf5_dataset(path, data, "data")
+    with h5py.File(path, "r") as hf:
+        assert list(hf.keys()) == ["data"] and hf["data"].dtype == np.float32
+        assert np.array_equal(np.array(hf["data"]), data)

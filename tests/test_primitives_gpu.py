@@ -73,7 +73,7 @@ def test_attention_pool_matches_masked_softmax(cuda_lib, K, C, use_counts):
     vals = torch.relu(V * sc[:, None, None, :] + sh[:, None, None, :])
     ref = masked_softmax_pool(S.permute(0, 3, 1, 2), vals.permute(0, 3, 1, 2), counts if use_counts else "all")  # (B,C,P)
     out = torch.zeros(B * P, C + 4, device=DEV)
-    rc = cuda_lib.pdr_attention_pool(B, P, K, C, _p(S), C, _p(V), C, _p(sc), _p(sh), C, _p(counts), _p(out), C + 4, _stream())
+    rc = cuda_lib.pdr_attention_pool(B, P, K, C, _p(S), C, _p(V), C, _p(sc), _p(sh), C, _p(counts), _p(out), C + 4, 0, _stream())
     assert rc == 0, cuda_lib.pdr_last_error_string()
     torch.testing.assert_close(out.view(B, P, C + 4)[..., :C], ref.permute(0, 2, 1), rtol=1e-5, atol=1e-6)
     assert out[:, C:].abs().sum() == 0                                     # only C columns are written
@@ -152,13 +152,13 @@ def test_affine_and_gather_rows(cuda_lib):
     add = torch.randn(B, 32, generator=g).to(DEV); R = torch.randn(B * rps, 28, generator=g).to(DEV)
     wide = torch.full((B * rps, 40), 7.0, device=DEV)
     rc = cuda_lib.pdr_affine_rows(B, rps, C, _p(x), 24, 1, _p(sc), _p(sh), 24, _p(add), 32, _p(R), 28,
-                                  ctypes.c_void_p(wide.data_ptr() + 8 * 4), 40, _stream())
+                                  ctypes.c_void_p(wide.data_ptr() + 8 * 4), 40, 0, _stream())
     assert rc == 0
     ref = torch.relu(x[:, :C].view(B, rps, C) * sc[:, None, :C] + sh[:, None, :C]) + add[:, None, :C] + R[:, :C].view(B, rps, C)
     torch.testing.assert_close(wide[:, 8:8 + C].view(B, rps, C), ref, rtol=1e-6, atol=1e-6)
     assert (wide[:, :8] == 7).all() and (wide[:, 8 + C:] == 7).all()       # a column slice: neighbours untouched
     idx = torch.randint(0, rps, (B, 11), generator=g, dtype=torch.int32).to(DEV)
     out = torch.zeros(B * 11, 24, device=DEV)
-    assert cuda_lib.pdr_gather_rows(B, rps, 11, C, _p(x), 24, _p(idx), _p(out), 24, _stream()) == 0
+    assert cuda_lib.pdr_gather_rows(B, rps, 11, C, _p(x), 24, _p(idx), _p(out), 24, 0, _stream()) == 0
     ref = x.view(B, rps, 24).gather(1, idx.long().unsqueeze(-1).expand(-1, -1, 24))[..., :C]
     assert torch.equal(out.view(B, 11, 24)[..., :C], ref)
