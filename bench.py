@@ -240,7 +240,10 @@ def run_reference_arm(args, rank):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "the reference has no CPU implementation of these ops "
-                       "(AT_ASSERT CPU not supported); this arm is the oracle port on the host cores"},
+                       "(AT_ASSERT CPU not supported); this arm is the oracle port on the host cores",
+                       "scope": "ONE host CPU whatever --gpus is (rank 0 only): this value does not grow with N, so a "
+                                "ratio against an N-GPU value is N-inflated -- compare at n_gpus = 1",
+                       "n_hosts": 1},
             "cpu_baseline": {"value": value, "unit": "shapes/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

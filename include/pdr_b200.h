@@ -224,6 +224,10 @@ typedef struct PdrGemmArgs {
    * kernel next to this GEMM on a second stream (the engine's geometry chain, PDR_GEOM_OVERLAP) leaves it some SMs:
    * CTAs of this kernel take a whole SM each and never share it. */
   int max_ctas;
+  /* 1: W (and bias) are not written by any kernel still in flight on the stream (inference weights).  The tensor-core kernel
+   * is launched as a programmatic dependent of the kernel in front of it and may then stage a resident W while that kernel
+   * drains; with 0 it touches nothing before the previous kernel has completed. */
+  int w_static;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);
@@ -363,6 +367,7 @@ typedef struct PdrChainArgs {
                                         (slots 0, 1); the other pair is written as zeros */
   const int *counts; float *out; int ld_out;      /* POOL: counts (points) or NULL, out (points, ld_out) */
   int max_ctas;                      /* upper bound on the CTAs of the persistent grid (0 = one per SM), as PdrGemmArgs.max_ctas */
+  int round_out;                     /* POOL writes `out` rounded to TF32 (nearest), like pdr_attention_pool's round_tf32 */
   int n_steps; PdrChainStep steps[PDR_CHAIN_MAX_STEPS];
 } PdrChainArgs;
 int pdr_stage_chain_tile_rows(void);

@@ -60,7 +60,7 @@ class ChainArgs(ctypes.Structure):
                 ("w_image", c_void), ("w_bytes", ctypes.c_int),
                 ("batch", ctypes.c_int), ("rows_per_sample", ctypes.c_int), ("group_k", ctypes.c_int),
                 ("stats", c_void), ("stats_n", ctypes.c_int), ("stats_relu_mask", ctypes.c_uint * 4),
-                ("counts", c_void), ("out", c_void), ("ld_out", ctypes.c_int), ("max_ctas", ctypes.c_int),
+                ("counts", c_void), ("out", c_void), ("ld_out", ctypes.c_int), ("max_ctas", ctypes.c_int), ("round_out", ctypes.c_int),
                 ("n_steps", ctypes.c_int), ("steps", ChainStep * MAX_STEPS)]
 
 
@@ -381,6 +381,7 @@ class StagePlan:
             a.counts = rt.get("counts")
             a.out, a.ld_out = rt["out"]
         a.max_ctas = rt.get("max_ctas", 0)
+        a.round_out = rt.get("round_out", 0)
         a.n_steps = len(steps)
         for i, st in enumerate(steps):
             cs = a.steps[i]

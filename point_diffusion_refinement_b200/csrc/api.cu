@@ -1,5 +1,6 @@
 // Error plumbing and library identity for libpdr_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -14,6 +15,16 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+int pdl_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("PDR_PDL");
+    mode = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2;
+  }
+  return mode;
+}
+bool pdl_enabled() { return pdl_mode() != 0; }
 
 int check_launch(const char *what) {
   cudaError_t e = cudaGetLastError();

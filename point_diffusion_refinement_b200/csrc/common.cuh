@@ -35,6 +35,34 @@ __device__ __forceinline__ float dist2_xyz(float dx, float dy, float dz) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Programmatic dependent launch (PDL).  The compiled step is ~270 small-to-medium kernels back to back on one stream:
+// without PDL a kernel's grid is launched only after the previous grid has drained, so every launch pays the launch latency
+// and the ramp of its prologue (barrier init, TMEM allocation, resident weights) on an idle GPU.  A kernel launched with
+// launch_pdl() may start as soon as the kernel in front of it has called pdl_launch_dependents() (or exited) and resources
+// free up; it must call pdl_wait() before it reads or writes anything the earlier kernels touch -- the wait returns once
+// every earlier grid has completed and its memory operations are visible.  Kernels launched the classic way are fully
+// ordered as before, so the two kinds mix freely on a stream (and in a captured graph: programmatic edges).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int pdl_mode();         // PDR_PDL: 0 off, 1 the GEMM triggers its dependents at kernel start, 2 after its last MMA
+bool pdl_enabled();     // PDR_PDL=0 launches everything the classic way (api.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -155,6 +155,9 @@ constexpr int kDirectDepth = 3;   // chunks of cp.async in flight per producer t
 
 struct TcPlan {
   int n_tiles_n;        // column tiles (N / BN rounded up)
+  int bn;               // columns per column tile: BN, or for the widest template the balanced width ceil(N / n_tiles_n)
+                        // rounded up to 32 (N = 300: 160 + 140 instead of 256 + 44, whose light tiles always fell to the
+                        // same CTAs of an even-sized persistent grid)
   int tiles_per_sample; // row tiles per sample
   int total_items;      // n_tiles_n * batch * tiles_per_sample, column tile fastest
   int nk;               // K chunks
@@ -165,6 +168,8 @@ struct TcPlan {
   int epi_alt;          // 1: the two groups of 4 epilogue warps take alternate TILES (one accumulator each);
                         // 0: both groups share every tile and alternate its column blocks
   int prod_sleep_ns;    // > 0: producers / loaders sleep this long between polls of an EMPTY-stage barrier
+  int w_early;          // 1: the resident weight matrix is staged BEFORE the wait on the previous kernel (PdrGemmArgs.w_static)
+  int pdl_late;         // 1: the MMA warp releases the dependent launch after its last MMA, 0: every thread at kernel start
 };
 
 // bytes of the TMA-store staging tiles (EPI 3): two 32 x 32 fp32 boxes per epilogue warp
@@ -210,6 +215,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = plan.stages, nk = plan.nk;
+  if (!plan.pdl_late) pdl_launch_dependents();      // PDL (common.cuh): the next kernel's grid may be launched; it waits for this one
 
   if (tid == 0) {
     const int full_count = plan.direct ? kProdThreads : kProdThreads + kLoadThreads;
@@ -232,9 +238,13 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
+  // barrier init and the TMEM allocation above overlap the tail of the previous kernel; from here on global memory is touched
+  const bool stages_w_first = WRES && plan.w_early && warp >= kEpiWarps && warp < kEpiWarps + kProdWarps;
+  if (!stages_w_first) pdl_wait();
 
   // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
+  const int bn = BN == 256 ? plan.bn : BN;       // runtime tile width for the widest template only
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
 
   if (warp >= kEpiWarps && warp < kMmaWarp) {
     // =============================== PRODUCERS ===============================================
@@ -255,6 +265,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&bar_wready);
+      if (plan.w_early) pdl_wait();
     }
     // chunk sequence of this CTA: items blockIdx.x, +gridDim.x, ... ; nk chunks each.
     // The producer loop runs once per 16 KiB chunk in every producer thread, so it is kept lean: item geometry
@@ -274,7 +285,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     };
     auto locate = [&](Cur &c) {  // full (division) geometry of c.item
       const int tile = c.item / plan.n_tiles_n;
-      c.n0 = (c.item - tile * plan.n_tiles_n) * BN;
+      c.n0 = (c.item - tile * plan.n_tiles_n) * bn;
       c.b = tile / plan.tiles_per_sample;
       c.tis = tile - c.b * plan.tiles_per_sample;
     };
@@ -383,16 +394,17 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         }
         if (!WRES) {
           const float *wsrc = a.W + (size_t)(c.n0 + arow) * a.ldw + kofs + chunk * 4;
-          if (c.n0 + BN <= a.N) {
+          if (c.n0 + bn <= a.N) {
             const float *p = kin ? wsrc : a.W;
             const size_t st = kin ? w_step : 0;
 #pragma unroll
-            for (int i = 0; i < kWLoads; ++i) { cp_async16_sz(sa + kATileBytes + i * 4096, p, ksz); p += st; }
+            for (int i = 0; i < kWLoads; ++i)
+              if (BN < 256 || i * 32 < bn) { cp_async16_sz(sa + kATileBytes + i * 4096, p, ksz); p += st; }
           } else {
 #pragma unroll
             for (int i = 0; i < kWLoads; ++i) {
               const bool ok = kin && c.n0 + arow + 32 * i < a.N;
-              cp_async16(sa + kATileBytes + i * 4096, ok ? wsrc + i * w_step : a.W, ok);
+              if (BN < 256 || i * 32 < bn) cp_async16(sa + kATileBytes + i * 4096, ok ? wsrc + i * w_step : a.W, ok);
             }
           }
         }
@@ -466,16 +478,17 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         cp_async_arrive_noinc(&bar_rfull[stage]);
         if (!WRES) {
           const float *wsrc = a.W + (size_t)(cl.n0 + lrow) * a.ldw + kofs + lchunk * 4;
-          if (cl.n0 + BN <= a.N) {
+          if (cl.n0 + bn <= a.N) {
             const float *src = kin ? wsrc : a.W;
             const size_t st = kin ? w8 : 0;
 #pragma unroll
-            for (int i = 0; i < BN / 8; ++i) { cp_async16_sz(sa + kATileBytes + i * 1024, src, ksz); src += st; }
+            for (int i = 0; i < BN / 8; ++i)
+              if (BN < 256 || i * 8 < bn) { cp_async16_sz(sa + kATileBytes + i * 1024, src, ksz); src += st; }
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 8; ++i) {
               const bool ok = kin && cl.n0 + lrow + 8 * i < a.N;
-              cp_async16(sa + kATileBytes + i * 1024, ok ? wsrc + i * w8 : a.W, ok);
+              if (BN < 256 || i * 8 < bn) cp_async16(sa + kATileBytes + i * 1024, ok ? wsrc + i * w8 : a.W, ok);
             }
           }
         }
@@ -618,7 +631,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
           const uint64_t adesc = make_desc(sa), bdesc = make_desc(sb);
 #pragma unroll
           for (int k8 = 0; k8 < kTcBK / 8; ++k8)
-            umma_tf32(d_tmem, adesc + (uint64_t)(k8 * 2), bdesc + (uint64_t)(k8 * 2), kIdesc, (kc | k8) ? 1u : 0u);
+            umma_tf32(d_tmem, adesc + (uint64_t)(k8 * 2), bdesc + (uint64_t)(k8 * 2), idesc, (kc | k8) ? 1u : 0u);
           umma_commit(&bar_empty[stage]);
           if (kc == nk - 1) umma_commit(&bar_tfull[acc]);
         }
@@ -627,6 +640,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (plan.pdl_late) pdl_launch_dependents();
   } else {
     // =============================== EPILOGUE ================================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
@@ -662,7 +676,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     const bool radd_split = a.rowadd && a.rows_per_sample % a.rowadd_div == 0;   // groups never straddle samples
     const int groups_per_sample = a.rowadd ? a.rows_per_sample / a.rowadd_div : 0;
     for (int item = (int)blockIdx.x + (alt ? half * G : 0); item < plan.total_items; item += item_step) {
-      const int tile = item / plan.n_tiles_n, n0 = (item - tile * plan.n_tiles_n) * BN;
+      const int tile = item / plan.n_tiles_n, n0 = (item - tile * plan.n_tiles_n) * bn;
       const int b = tile / plan.tiles_per_sample, tis = tile - b * plan.tiles_per_sample;
       const uint32_t s_part_g = s_part_base + (kPartDB ? part_parity * kPartBytes : 0u);
       const int r0 = tis * kTcTileM;
@@ -711,7 +725,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       mbar_wait(&bar_tfull[acc], (uint32_t)acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cb = cb0; cb < BN; cb += cb_step) {
+      for (int cb = cb0; cb < bn; cb += cb_step) {
         // CW-column blocks: CW = 32 normally, 16 for the narrowest tile (BN = 32)
         if (n0 + cb >= a.N && (POOL || n0 + cb >= a.ldc_zero_to)) break;   // nothing to write in this or later blocks
         uint32_t v[CW];
@@ -1141,7 +1155,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       mbar_arrive(&bar_tempty[acc]);
       if (a.stats) {
         asm volatile("bar.sync %0, %1;" ::"r"(stat_bar), "r"(stat_threads) : "memory");
-        for (int f = stat_tid; f < BN * 4; f += stat_threads) {
+        for (int f = stat_tid; f < bn * 4; f += stat_threads) {
           const int col = f >> 2, q = f & 3;
           if (n0 + col < a.N) {
             float p0, p1, p2, p3;
@@ -1179,6 +1193,12 @@ constexpr int kPlanDoesNotFit = 12345;
 //  * profiles/r01_tma_epilogue_ab_v10.txt: the TMA-store flavour takes the dense 2 M x 32 x 32 GEMMs from 3.9 to
 //    4.9-5.9 TB/s and is neutral to +3 % elsewhere.
 // Default = tma (row groups of at least 8 rows; shorter ones fall back to the old choice).
+// PDR_GEMM_BALANCED=0: column tiles of the full template width (A/B of TcPlan.bn)
+bool balanced_tiles() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("PDR_GEMM_BALANCED"); on = !(e && e[0] == '0'); }
+  return on == 1;
+}
 // PDR_GEMM_EPILOGUE=auto|scalar|vec4|tma forces one (tests, A/B); auto = the pre-TMA hybrid.
 int epilogue_mode() {
   static int mode = -1;
@@ -1250,6 +1270,7 @@ template <int BN, bool WRES>
 int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   TcPlan plan;
   plan.n_tiles_n = ceil_div(a.N, BN);
+  plan.bn = BN == 256 && balanced_tiles() ? ceil_div(ceil_div(a.N, plan.n_tiles_n), 32) * 32 : BN;
   plan.tiles_per_sample = ceil_div(a.rows_per_sample, kTcTileM);
   const long long items = (long long)plan.n_tiles_n * a.batch * plan.tiles_per_sample;
   if (items > 0x7fffffffll) { set_error("gemm_tf32: too many tiles"); return PDR_ERR_INVALID_ARGUMENT; }
@@ -1257,6 +1278,8 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   plan.nk = ceil_div(a.K, kTcBK);
   plan.epi_alt = epilogue_alternates_tiles() ? 1 : 0;
   plan.prod_sleep_ns = producer_sleep_ns();
+  plan.pdl_late = pdl_mode() == 2;
+  plan.w_early = pdl_mode() != 0 && a.w_static;
   // epilogue flavour: pooling when asked for; float4 for the broadcast row-add on 32-column blocks; otherwise scalar, or
   // (PDR_GEMM_EPILOGUE=tma) the TMA-store flavour (row groups of at least 8 rows)
   const int mode = epilogue_mode();
@@ -1311,7 +1334,10 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   }
   const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
   const int grid = plan.total_items < sm_cap ? plan.total_items : sm_cap;
-  kern<<<grid, kTcThreads, smem, stream>>>(a, plan, tmap);
+  {
+    const cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, stream, a, plan, tmap);
+    if (e != cudaSuccess) { set_error("gemm_tf32_persistent: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
+  }
   return check_launch("gemm_tf32_persistent");
 }
 

@@ -209,6 +209,8 @@ struct GnBatch { PdrGnArgs g[2]; };
 
 __global__ void __launch_bounds__(kGnThreads)
 gn_finalize_kernel(const GnBatch batch) {
+  pdl_launch_dependents();      // (PDL, common.cuh) the next kernel may ramp up; nothing below touches global memory before
+  pdl_wait();                   // every earlier kernel has completed
   extern __shared__ double s_tot[];                 // [channels in range][3] = weighted sum, sum of squares, count
   __shared__ double s_red[kGnThreads][2];
   const PdrGnArgs &a = batch.g[blockIdx.z];
@@ -301,6 +303,8 @@ affine_rows_kernel(int rows_per_sample, int C, const float *__restrict__ x, int 
                    const float *__restrict__ sc, const float *__restrict__ sh, int ld_scsh,
                    const float *__restrict__ add, int ld_add, const float *__restrict__ R, int ldr,
                    float *__restrict__ out, int ldo, long long total, int round_tf32) {
+  pdl_launch_dependents();      // (PDL, common.cuh) the next kernel may ramp up; nothing below touches global memory before
+  pdl_wait();                   // every earlier kernel has completed
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -321,6 +325,8 @@ __global__ void __launch_bounds__(256)
 attention_pool_kernel(int P, int K, int C, const float *__restrict__ S, int lds, const float *__restrict__ V,
                       int ldv, const float *__restrict__ sc, const float *__restrict__ sh, int ld_scsh,
                       const int *__restrict__ counts, float *__restrict__ out, int ldo, long long total, int round_tf32) {
+  pdl_launch_dependents();      // (PDL, common.cuh) the next kernel may ramp up; nothing below touches global memory before
+  pdl_wait();                   // every earlier kernel has completed
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -440,6 +446,8 @@ group_knn_kernel(int n, int P, int K, int C, const float *__restrict__ feat, int
 __global__ void __launch_bounds__(256)
 gather_rows_kernel2(int n, int P, int C, const float *__restrict__ src, int lds, const int *__restrict__ idx,
                     float *__restrict__ out, int ldo, long long total, int round_tf32) {
+  pdl_launch_dependents();      // (PDL, common.cuh) the next kernel may ramp up; nothing below touches global memory before
+  pdl_wait();                   // every earlier kernel has completed
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -456,6 +464,8 @@ __global__ void __launch_bounds__(256)
 group_geo_ball_kernel(int n, int P, int K, const float *__restrict__ xyz, const float *__restrict__ centres,
                       const int *__restrict__ idx, const int *__restrict__ counts, int fill_missing,
                       float *__restrict__ geo, int *__restrict__ src_row, int rows, int rt) {
+  pdl_launch_dependents();      // (PDL, common.cuh) the next kernel may ramp up; nothing below touches global memory before
+  pdl_wait();                   // every earlier kernel has completed
   const int row = blockIdx.x * blockDim.x + threadIdx.x;             // (b*P + p)*K + k
   if (row >= rows) return;
   const int bp = row / K;
@@ -477,6 +487,8 @@ __global__ void __launch_bounds__(256)
 group_geo_knn_kernel(int n, int P, int K, const float *__restrict__ y, const float *__restrict__ x,
                      const long long *__restrict__ idx, const float *__restrict__ dists, float *__restrict__ geo,
                      int *__restrict__ src_row, int rows, int rt) {
+  pdl_launch_dependents();      // (PDL, common.cuh) the next kernel may ramp up; nothing below touches global memory before
+  pdl_wait();                   // every earlier kernel has completed
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const int bp = row / K;
@@ -608,7 +620,8 @@ extern "C" int pdr_gn_finalize_batch(const PdrGnArgs *args, int count, void *str
     if (args[i].groups < kGnSplit) split = 1;
   }
   const size_t smem = (size_t)channels * 3 * sizeof(double);      // upper bound for any split
-  gn_finalize_kernel<<<dim3(nb, split, count), kGnThreads, smem, (cudaStream_t)stream>>>(batch);
+  const cudaError_t e = launch_pdl(gn_finalize_kernel, dim3(nb, split, count), dim3(kGnThreads), smem, (cudaStream_t)stream, batch);
+  if (e != cudaSuccess) { set_error("gn_finalize_kernel: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
   return check_launch("gn_finalize_kernel");
 }
 
@@ -622,8 +635,8 @@ extern "C" int pdr_affine_rows(int batch, int rows_per_sample, int C, const floa
                                const float *R, int ldr, float *out, int ldo, int round_tf32, void *stream) {
   PDR_REQUIRE(batch > 0 && rows_per_sample > 0 && C > 0 && ldo >= C && x && out, "affine_rows: bad arguments");
   const long long total = (long long)batch * rows_per_sample * C;
-  affine_rows_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(rows_per_sample, C, x, ldx, pro_mode, sc, sh,
-                                                                          ld_scsh, add, ld_add, R, ldr, out, ldo, total, round_tf32);
+  launch_pdl(affine_rows_kernel, dim3(blocks_for(total)), dim3(256), 0, (cudaStream_t)stream, rows_per_sample, C, x, ldx, pro_mode, sc,
+             sh, ld_scsh, add, ld_add, R, ldr, out, ldo, total, round_tf32);
   return check_launch("affine_rows_kernel");
 }
 
@@ -633,14 +646,14 @@ extern "C" int pdr_attention_pool(int batch, int P, int K, int C, const float *S
   PDR_REQUIRE(batch > 0 && P > 0 && K > 0 && C > 0 && S && V && sc && sh && out, "attention_pool: bad arguments");
   const long long total = (long long)batch * P * C;
   if (K == 32)
-    attention_pool_kernel<32><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
-                                                                                   ld_scsh, counts, out, ldo, total, round_tf32);
+    launch_pdl(attention_pool_kernel<32>, dim3(blocks_for(total)), dim3(256), 0, (cudaStream_t)stream, P, K, C, S, lds, V, ldv, sc, sh,
+               ld_scsh, counts, out, ldo, total, round_tf32);
   else if (K == 8)
-    attention_pool_kernel<8><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
-                                                                                  ld_scsh, counts, out, ldo, total, round_tf32);
+    launch_pdl(attention_pool_kernel<8>, dim3(blocks_for(total)), dim3(256), 0, (cudaStream_t)stream, P, K, C, S, lds, V, ldv, sc, sh,
+               ld_scsh, counts, out, ldo, total, round_tf32);
   else
-    attention_pool_kernel<0><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(P, K, C, S, lds, V, ldv, sc, sh,
-                                                                                  ld_scsh, counts, out, ldo, total, round_tf32);
+    launch_pdl(attention_pool_kernel<0>, dim3(blocks_for(total)), dim3(256), 0, (cudaStream_t)stream, P, K, C, S, lds, V, ldv, sc, sh,
+               ld_scsh, counts, out, ldo, total, round_tf32);
   return check_launch("attention_pool_kernel");
 }
 
@@ -675,8 +688,8 @@ extern "C" int pdr_group_geo_ball(int batch, int n, int P, int K, const float *x
   const long long rows = (long long)batch * P * K;
   PDR_REQUIRE(rows < (1ll << 31) && (long long)batch * n < (1ll << 31) && ((uintptr_t)geo % 16) == 0,
               "group_geo_ball: too many rows or unaligned output");
-  group_geo_ball_kernel<<<blocks_for(rows), 256, 0, (cudaStream_t)stream>>>(n, P, K, xyz, centres, idx, counts, fill_missing,
-                                                                           geo, src_row, (int)rows, round_tf32);
+  launch_pdl(group_geo_ball_kernel, dim3(blocks_for(rows)), dim3(256), 0, (cudaStream_t)stream, n, P, K, xyz, centres, idx, counts,
+             fill_missing, geo, src_row, (int)rows, round_tf32);
   return check_launch("group_geo_ball_kernel");
 }
 
@@ -686,8 +699,8 @@ extern "C" int pdr_group_geo_knn(int batch, int n, int P, int K, const float *y,
   const long long rows = (long long)batch * P * K;
   PDR_REQUIRE(rows < (1ll << 31) && (long long)batch * n < (1ll << 31) && ((uintptr_t)geo % 16) == 0,
               "group_geo_knn: too many rows or unaligned output");
-  group_geo_knn_kernel<<<blocks_for(rows), 256, 0, (cudaStream_t)stream>>>(n, P, K, y, x, (const long long *)idx, dists, geo,
-                                                                          src_row, (int)rows, round_tf32);
+  launch_pdl(group_geo_knn_kernel, dim3(blocks_for(rows)), dim3(256), 0, (cudaStream_t)stream, n, P, K, y, x, (const long long *)idx,
+             dists, geo, src_row, (int)rows, round_tf32);
   return check_launch("group_geo_knn_kernel");
 }
 
@@ -706,6 +719,7 @@ extern "C" int pdr_gather_rows(int batch, int n, int P, int C, const float *src,
                                int ldo, int round_tf32, void *stream) {
   PDR_REQUIRE(batch > 0 && n > 0 && P > 0 && C > 0 && src && out, "gather_rows: bad arguments");
   const long long total = (long long)batch * P * C;
-  gather_rows_kernel2<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(n, P, C, src, lds, idx, out, ldo, total, round_tf32);
+  launch_pdl(gather_rows_kernel2, dim3(blocks_for(total)), dim3(256), 0, (cudaStream_t)stream, n, P, C, src, lds, idx, out, ldo, total,
+             round_tf32);
   return check_launch("gather_rows_kernel");
 }

@@ -579,7 +579,11 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
                     float num = 0.f;
 #pragma unroll 8
                     for (int k = 0; k < PK; ++k) num += lds1(scr_col + 144u * (r0 + k));
-                    if (n < ncols) a.out[(point0 + pi) * (size_t)a.ld_out + n] = num / den[pi];
+                    if (n < ncols) {
+                      const float o = num / den[pi];
+                      a.out[(point0 + pi) * (size_t)a.ld_out + n] =
+                          a.round_out ? __uint_as_float((__float_as_uint(o) + 0x1000u) & 0xffffe000u) : o;
+                    }
                   }
                 }
                 __syncwarp();

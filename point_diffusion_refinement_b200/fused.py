@@ -58,7 +58,7 @@ class GemmArgs(ctypes.Structure):
                 ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
                 ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
                 ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int),
-                ("max_ctas", ctypes.c_int)]
+                ("max_ctas", ctypes.c_int), ("w_static", ctypes.c_int)]
 
 
 GN_MAX_SOURCES = 4
@@ -323,6 +323,7 @@ class FusedDenoiser:
             self.keep.append(pool)
         g.batch, g.rows_per_sample = batch, rows_per_sample
         g.max_ctas = self._cta_limit if self._ops is self.ops else 0
+        g.w_static = 1                   # the engine's weights are written at compile time only
         g.pro_mode = pro
         if pro != PRO_NONE:
             sc, sh = scsh
@@ -685,7 +686,7 @@ class FusedDenoiser:
         rt = dict(table=(gathered.table.ptr, gathered.table.ld), src_rows=gathered.src_row.data_ptr(),
                   geo=(gathered.geo.ptr, gathered.geo.ld), batch=B, rows_per_sample=rows_per_sample, group_k=K, gn={}, emb={},
                   counts=counts.data_ptr() if counts is not None else None, out=(out.ptr, out.ld),
-                  max_ctas=self._cta_limit if self._ops is self.ops else 0)
+                  max_ctas=self._cta_limit if self._ops is self.ops else 0, round_out=self.rt)
         for l in range(L):
             v = self._resolve_emb(emb_views[l])
             rt["emb"][l + 1] = (v.ptr, v.ld) if v is not None else None
