@@ -75,7 +75,10 @@ CASES = [  # B, rows_per_sample, K, N, pro, add, R, rowadd_div
     (2, 4096, 172, 128, 1, True, False, 0),      # prologue, weights resident (96 KiB)
     (1, 8192, 332, 588, 0, False, False, 0),     # no prologue, 3 column tiles, streamed weights
     (3, 640, 44, 64, 2, False, False, 5),        # broadcast row groups that straddle the 16-row epilogue halves
-    (2, 200, 32, 32, 1, True, False, 8),         # narrow tile, ragged rows, row groups of 8
+    (2, 200, 32, 32, 1, True, False, 8),         # narrow tile, ragged rows, row groups of 8    (1, 32, 512, 1248, 0, False, False, 0),      # t-embedding GEMM: one row tile -> spread over 39 column tiles of 32
+    (4, 128, 512, 512, 1, True, True, 0),        # deepest level: 4 row tiles -> 32-column tiles, prologue + residual
+    (2, 1024, 256, 256, 1, True, False, 0),      # 16 row tiles -> 64-column tiles
+    (2, 4096, 256, 256, 2, False, False, 32),    # 64 row tiles -> 128-column tiles, broadcast row groups
 ]
 
 
