@@ -228,6 +228,9 @@ typedef struct PdrGemmArgs {
    * is launched as a programmatic dependent of the kernel in front of it and may then stage a resident W while that kernel
    * drains; with 0 it touches nothing before the previous kernel has completed. */
   int w_static;
+  /* gathered A: number of rows of the table A (every a_rows[r] < table_rows).  > 0 lets the tensor-core kernel fetch whole
+   * 32-column chunks of the table part with TMA tile::gather4; 0 = unknown (cp.async pieces). */
+  int table_rows;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);

@@ -147,6 +147,19 @@ __device__ __forceinline__ void cp_async16_ignore(uint32_t dst, const void *src,
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// TMA tile::gather4: four rows (one 128-byte K chunk each) of a 2-D row-major table, picked by four row indices, land as
+// four consecutive 128-byte rows of the SWIZZLE_128B stage (the swizzle is a function of the shared-memory address, so rows
+// 4l .. 4l+3 of the canonical K-major tile are exactly what the copy writes at tile + 512 l).  A row index outside the
+// table ([0, rows)) reads as zeros and still counts its bytes on the mbarrier.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, int col, int4 rows, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(tm), "r"(col), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -169,6 +182,8 @@ struct TcPlan {
                         // 0: both groups share every tile and alternate its column blocks
   int prod_sleep_ns;    // > 0: producers / loaders sleep this long between polls of an EMPTY-stage barrier
   int w_early;          // 1: the resident weight matrix is staged BEFORE the wait on the previous kernel (PdrGemmArgs.w_static)
+  int tma_gather;       // 1: whole 32-column chunks of the gathered table come by TMA tile::gather4 (one warp, one
+                        //    instruction per 4 rows) instead of 8 cp.async pieces per row with per-thread address arithmetic
   int pdl_late;         // 1: the MMA warp releases the dependent launch after its last MMA, 0: every thread at kernel start
 };
 
@@ -187,7 +202,8 @@ constexpr int tma_stage_bytes(int bn) { return kEpiWarps * tma_bufs(bn) * 4096; 
 // gathered-A indices, GroupNorm finalisation inside the epilogue -- measured slower and were removed, same file.)
 template <int BN, bool WRES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c) {
+gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_constant__ CUtensorMap tmap_c,
+                     const __grid_constant__ CUtensorMap tmap_a) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kWLoads = BN * 8 / kProdThreads;        // float4 of W per producer thread per chunk
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -300,24 +316,73 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     for (int d = 0; d < kIdxAhead; ++d)
 #pragma unroll
       for (int i = 0; i < 4; ++i) nidx[d][i] = -1;
-    auto fetch_idx = [&](int item, int (&out)[4]) {
-      if (item >= plan.total_items) return;
-      const int tile = item / plan.n_tiles_n;
-      const int b = tile / plan.tiles_per_sample, r0 = (tile - b * plan.tiles_per_sample) * kTcTileM;
+    // the look-ahead position (the item whose neighbour rows are requested next) is stepped, not divided: the index
+    // prefetch runs once per item in every producer warp, and two integer divisions were a fifth of the instructions a
+    // producer warp spends on an item (ncu, profiles/r02_gather_producer_notes.txt)
+    struct Pos { int item, b, tis, ct; };
+    const int step_q = G / plan.n_tiles_n, step_r = G - step_q * plan.n_tiles_n;
+    const bool step_divides = step_q + 1 >= plan.tiles_per_sample;      // a step may cross more than one sample
+    auto locate_pos = [&](Pos &q) {
+      const int tile = q.item / plan.n_tiles_n;
+      q.ct = q.item - tile * plan.n_tiles_n;
+      q.b = tile / plan.tiles_per_sample;
+      q.tis = tile - q.b * plan.tiles_per_sample;
+    };
+    auto step_pos = [&](Pos &q) {
+      q.item += G;
+      if (step_divides) { locate_pos(q); return; }
+      q.ct += step_r;
+      int dt = step_q;
+      if (q.ct >= plan.n_tiles_n) { q.ct -= plan.n_tiles_n; ++dt; }
+      q.tis += dt;
+      if (q.tis >= plan.tiles_per_sample) { q.tis -= plan.tiles_per_sample; ++q.b; }
+    };
+    auto fetch_idx = [&](const Pos &q, int (&out)[4]) {
+      if (q.item >= plan.total_items) return;
+      const int b = q.b, r0 = q.tis * kTcTileM;
       const int *p = a.a_rows + (size_t)b * a.rows_per_sample + r0 + arow;
 #pragma unroll
       for (int i = 0; i < 4; ++i) out[i] = (r0 + arow + 32 * i < a.rows_per_sample) ? __ldg(p + 32 * i) : -1;
+    };
+    // TMA gather (TcPlan.tma_gather): lanes 0..3 of the 8 producer warps each own 4 rows (rows 4 g4 .. 4 g4 + 3, g4 < 32) and
+    // hold their neighbour rows for the current and for the next item -- UTMALDG takes its operands from uniform registers,
+    // so ptxas serialises the lanes of a warp; four per warp keeps that loop short and the eight warps issue side by side.
+    // The per-thread indices above are needed only when the table part ends inside a chunk.
+    const bool tg = gath && plan.tma_gather;
+    const bool tg_warp = tg && !is_loader && lane < 4;
+    const int g4 = (warp - kEpiWarps) * 4 + lane;
+    const bool need_cidx = gath && !is_loader && !(tg && a.k_split % kTcBK == 0);
+    const bool g4_vec = a.rows_per_sample % 4 == 0 && (reinterpret_cast<uintptr_t>(a.a_rows) & 15) == 0;
+    int4 g4c = make_int4(-1, -1, -1, -1), g4n = make_int4(-1, -1, -1, -1);
+    Pos ahead = {0, 0, 0, 0};
+    auto fetch_g4 = [&](const Pos &q, int4 &out) {
+      out = make_int4(-1, -1, -1, -1);
+      if (q.item >= plan.total_items) return;
+      const int b = q.b, r = q.tis * kTcTileM + 4 * g4;
+      const int *p = a.a_rows + (size_t)b * a.rows_per_sample + r;
+      if (g4_vec) {
+        if (r < a.rows_per_sample) out = __ldg(reinterpret_cast<const int4 *>(p));
+      } else {
+        if (r < a.rows_per_sample) out.x = __ldg(p);
+        if (r + 1 < a.rows_per_sample) out.y = __ldg(p + 1);
+        if (r + 2 < a.rows_per_sample) out.z = __ldg(p + 2);
+        if (r + 3 < a.rows_per_sample) out.w = __ldg(p + 3);
+      }
     };
     auto derive = [&](Cur &c) {  // pointers and row count from (b, tis)
       const int r0 = c.tis * kTcTileM;
       c.rows_valid = min(kTcTileM, a.rows_per_sample - r0);
       const size_t row = (size_t)c.b * a.rows_per_sample + r0 + arow;
-      c.pa = a.A + row * a.lda + chunk * 4;
-      c.pr = a.R ? a.R + row * a.ldr + chunk * 4 : nullptr;
-      if (gath) {
+      if (gath) {                // (the dense pointers are not used by the gathered producer)
+        c.pa = a.A; c.pr = nullptr;
+        if (need_cidx) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c.pg[i] = cidx[i] >= 0 ? a.A + (size_t)cidx[i] * a.lda + chunk * 4 : nullptr;
+          for (int i = 0; i < 4; ++i) c.pg[i] = cidx[i] >= 0 ? a.A + (size_t)cidx[i] * a.lda + chunk * 4 : nullptr;
+        }
         c.p2 = a.A2 + row * a.lda2 + chunk * 4;
+      } else {
+        c.pa = a.A + row * a.lda + chunk * 4;
+        c.pr = a.R ? a.R + row * a.ldr + chunk * 4 : nullptr;
       }
     };
     auto advance = [&](Cur &c) {
@@ -326,14 +391,18 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       c.item += G;
       if (fast_adv) { c.tis += G; if (c.tis >= plan.tiles_per_sample) { c.tis -= plan.tiles_per_sample; ++c.b; } }
       else locate(c);
-      if (gath) {
+      if (gath && !is_loader) {
+        step_pos(ahead);
+        if (tg_warp) { g4c = g4n; fetch_g4(ahead, g4n); }
+        if (need_cidx) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cidx[i] = nidx[0][i];
+          for (int i = 0; i < 4; ++i) cidx[i] = nidx[0][i];
 #pragma unroll
-        for (int d = 0; d + 1 < kIdxAhead; ++d)
+          for (int d = 0; d + 1 < kIdxAhead; ++d)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) nidx[d][i] = nidx[d + 1][i];
-        fetch_idx(c.item + kIdxAhead * G, nidx[kIdxAhead - 1]);
+            for (int i = 0; i < 4; ++i) nidx[d][i] = nidx[d + 1][i];
+          fetch_idx(ahead, nidx[kIdxAhead - 1]);
+        }
       }
       derive(c);
     };
@@ -343,10 +412,14 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     const size_t w_step = (size_t)32 * a.ldw;
     Cur ci;
     ci.item = (int)blockIdx.x; ci.kc = 0;
+    static_assert(kIdxAhead == 1, "one look-ahead position");
     if (gath && !is_loader) {
-      fetch_idx(ci.item, cidx);
-#pragma unroll
-      for (int d = 0; d < kIdxAhead; ++d) fetch_idx(ci.item + (d + 1) * G, nidx[d]);
+      ahead.item = ci.item; locate_pos(ahead);
+      if (tg_warp) fetch_g4(ahead, g4c);
+      if (need_cidx) fetch_idx(ahead, cidx);
+      step_pos(ahead);
+      if (tg_warp) fetch_g4(ahead, g4n);
+      if (need_cidx) fetch_idx(ahead, nidx[0]);
     }
     locate(ci); derive(ci);
 
@@ -365,7 +438,13 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         // (K tail: this thread's 16-byte piece is either wholly inside K or wholly zero-filled)
         const int ksz = kin ? 16 : 0;
         if (gath) {
-          if (kofs + chunk * 4 < a.k_split) {          // feature part: one table row per grouped row
+          if (tg && kofs + kTcBK <= a.k_split) {       // a whole chunk of table columns: 32 gather4 copies, 4 per warp
+            if (tg_warp) {
+              mbar_expect_tx(&bar_full[stage], 512u);
+              tma_gather4(smem_u32(s_stages + (size_t)stage * kStageBytes) + (uint32_t)g4 * 512u, &tmap_a, kofs, g4c,
+                          &bar_full[stage]);
+            }
+          } else if (kofs + chunk * 4 < a.k_split) {   // feature part: one table row per grouped row
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float *p = c.pg[i];
@@ -1039,15 +1118,30 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
             uint32_t toff[8];
   #pragma unroll
             for (int k = 0; k < 8; ++k) toff[k] = tile + ((((uint32_t)lane >> 2) ^ (uint32_t)k) << 4) + ((uint32_t)lane & 3u) * 4u;
+            // two rows per step on packed fp32 pairs (add / fma.rn.f32x2): the epilogue warps are bound by instruction
+            // issue, and the even and the odd rows get one partial sum each, added at the end
+            unsigned long long s01 = 0ull, q01 = 0ull, r01 = 0ull, u01 = 0ull;
             auto rows_loop = [&](auto p_c, auto r_c, auto full_c) {
               constexpr bool P = decltype(p_c)::value, R = decltype(r_c)::value, FULL = decltype(full_c)::value;
   #pragma unroll
-              for (int r = 0; r < 32; ++r) {
+              for (int r = 0; r < 32; r += 2) {
                 if (!FULL && r >= wrows) break;
-                float t;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(toff[r & 7] + (uint32_t)r * 128u) : "memory");
-                if constexpr (P) { q0 += t; q1 = fmaf(t, t, q1); }
-                if constexpr (R) { const float p = fmaxf(t, 0.f); q2 += p; q3 = fmaf(p, p, q3); }
+                float t0, t1;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(toff[r & 7] + (uint32_t)r * 128u) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1) : "r"(toff[(r + 1) & 7] + (uint32_t)(r + 1) * 128u) : "memory");
+                if (!FULL && r + 1 >= wrows) t1 = 0.f;          // a row beyond the sample adds nothing to any of the sums
+                unsigned long long t2;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
+                if constexpr (P) {
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s01) : "l"(t2));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q01) : "l"(t2));
+                }
+                if constexpr (R) {
+                  unsigned long long p2;
+                  asm("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(fmaxf(t0, 0.f)), "f"(fmaxf(t1, 0.f)));
+                  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(r01) : "l"(p2));
+                  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(u01) : "l"(p2));
+                }
               }
             };
             using T = std::true_type; using F = std::false_type;
@@ -1057,6 +1151,13 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
               else if (needR) rows_loop(F{}, T{}, T{});
             } else {
               rows_loop(T{}, T{}, F{});
+            }
+            {
+              float lo, hi;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(s01)); q0 = lo + hi;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(q01)); q1 = lo + hi;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r01)); q2 = lo + hi;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(u01)); q3 = lo + hi;
             }
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_part_g + (uint32_t)((quarter * BN + cb + lane) * 16)),
                          "f"(q0), "f"(q1), "f"(q2), "f"(q3) : "memory");
@@ -1246,6 +1347,20 @@ int make_c_tensor_map(const PdrGemmArgs &a, CUtensorMap *tm) {
   return 0;
 }
 
+// the gathered table (PdrGemmArgs.A with a_rows) as a 2-D map for TMA tile::gather4: box = one 128-byte chunk of one row
+int make_table_tensor_map(const PdrGemmArgs &a, CUtensorMap *tm) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { set_error("gemm_tf32: cuTensorMapEncodeTiled is not available"); return PDR_ERR_UNSUPPORTED; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)(a.k_split / kTcBK * kTcBK), (cuuint64_t)a.table_rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)a.lda * 4u};
+  const cuuint32_t box[2] = {(cuuint32_t)kTcBK, 1u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)a.A, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tf32: cuTensorMapEncodeTiled (gathered table) failed (%d)", (int)r); return PDR_ERR_CUDA; }
+  return 0;
+}
 // PDR_GEMM_PROD_SLEEP=<ns>: back-off of the producers' empty-stage polls (0 = spin on try_wait)
 int producer_sleep_ns() {
   static int ns = -1;
@@ -1322,6 +1437,15 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
     const int rc = make_c_tensor_map(a, &tmap);
     if (rc != 0) return rc;
   }
+  CUtensorMap tmap_a;
+  memset(&tmap_a, 0, sizeof(tmap_a));
+  plan.tma_gather = 0;
+  if (a.a_rows && plan.direct && a.table_rows > 0 && a.k_split >= kTcBK &&
+      (reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && a.lda % 4 == 0) {
+    const int rc = make_table_tensor_map(a, &tmap_a);
+    if (rc != 0) return rc;
+    plan.tma_gather = 1;
+  }
   auto kern = vec == 3 ? gemm_tf32_persistent<BN, WRES, 3>
               : vec == 2 ? gemm_tf32_persistent<BN, WRES, 2>
                          : (vec == 1 ? gemm_tf32_persistent<BN, WRES, 1> : gemm_tf32_persistent<BN, WRES, 0>);
@@ -1335,7 +1459,7 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   const int sm_cap = (a.max_ctas > 0 && a.max_ctas < kNumSMs) ? a.max_ctas : kNumSMs;
   const int grid = plan.total_items < sm_cap ? plan.total_items : sm_cap;
   {
-    const cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, stream, a, plan, tmap);
+    const cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, stream, a, plan, tmap, tmap_a);
     if (e != cudaSuccess) { set_error("gemm_tf32_persistent: %s", cudaGetErrorString(e)); return PDR_ERR_CUDA; }
   }
   return check_launch("gemm_tf32_persistent");

@@ -58,7 +58,7 @@ class GemmArgs(ctypes.Structure):
                 ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
                 ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
                 ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int),
-                ("max_ctas", ctypes.c_int), ("w_static", ctypes.c_int)]
+                ("max_ctas", ctypes.c_int), ("w_static", ctypes.c_int), ("table_rows", ctypes.c_int)]
 
 
 GN_MAX_SOURCES = 4
@@ -84,6 +84,10 @@ _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
 # 1-32-CTA grids) back in line.  Default: it runs on a second stream next to the first encoder feature-mapper block, which only
 # needs the level-0 ball query; the kernels of that block leave 148 - PDR_GEOM_OVERLAP_CTAS SMs free (max_ctas): their CTAs own
 # a whole SM and would otherwise serialise against the 32-CTA FPS kernel.  Measured -0.27 ms / step (profiles/r02_experiments_ab.txt).
+# PDR_GEMM_TMA_GATHER=1: the 32-column chunks of a gathered feature table are fetched by TMA tile::gather4
+# (PdrGemmArgs.table_rows) instead of cp.async pieces.  Bit-identical; measured neutral (+0.2 % step,
+# profiles/r02_gather_producer_notes.txt), so off by default.
+_TMA_GATHER = os.environ.get("PDR_GEMM_TMA_GATHER", "0") == "1"
 _GEOM_OVERLAP = os.environ.get("PDR_GEOM_OVERLAP", "1") != "0"
 _GEOM_OVERLAP_CTAS = int(os.environ.get("PDR_GEOM_OVERLAP_CTAS", "116"))
 # PDR_ROUND_TABLES=0: the kernels that produce raw GEMM operands (feature tables, geometric channels) do not round them to TF32
@@ -300,6 +304,7 @@ class FusedDenoiser:
         if gathered is not None:
             g.a_rows, g.A2 = gathered.src_row.data_ptr(), gathered.geo.ptr
             g.lda2, g.k_split = gathered.geo.ld, gathered.Cp
+            g.table_rows = gathered.table.rows if _TMA_GATHER else 0
             self.keep.append(gathered)
         if tail is not None:
             g.tail_rows, g.T, g.ldt = tail.src_row.data_ptr(), tail.table.ptr, tail.table.ld

@@ -164,7 +164,7 @@ def test_gemm_stats_skip_hint(cuda_lib, case):
 
 
 @pytest.mark.parametrize("shape", [(2, 4096, 35, 9, 140, 3000), (3, 1000, 4, 9, 96, 700), (2, 2048, 160, 11, 428, 512),
-                                   (1, 8320, 320, 11, 588, 64), (2, 640, 32, 9, 32, 5000)])
+                                   (1, 8320, 320, 11, 588, 64), (2, 640, 32, 9, 32, 5000), (2, 1002, 64, 9, 64, 900)])
 def test_gemm_gathered_operand_equals_materialised(cuda_lib, shape):
     """PdrGemmArgs.a_rows: A assembled by the producers from (feature table, row index, geometric channels) gives
     bit for bit the GEMM over the materialised grouped tensor -- including rows whose index is -1 (zero features),
@@ -201,10 +201,15 @@ def test_gemm_gathered_operand_equals_materialised(cuda_lib, shape):
     a.stats, a.use_tf32 = stats.data_ptr(), 1
     a.a_rows, a.A2, a.lda2, a.k_split = src.data_ptr(), geo.data_ptr(), 12, Cp
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == 0, cuda_lib.pdr_last_error_string()
-    torch.cuda.synchronize()
-    assert torch.equal(Cg, C0)
-    assert torch.equal(stats.view(B, tiles, N, 4).sum(1), st0)
+    # table_rows = 0: the table part comes by cp.async pieces; > 0: whole 32-column chunks by TMA tile::gather4 (index -1 and
+    # the rows beyond a ragged tile read as zeros through the out-of-bounds fill)
+    for rows_known in (0, table_rows):
+        a.table_rows = rows_known
+        Cg.fill_(float("nan")); stats.zero_()
+        assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == 0, cuda_lib.pdr_last_error_string()
+        torch.cuda.synchronize()
+        assert torch.equal(Cg, C0), rows_known
+        assert torch.equal(stats.view(B, tiles, N, 4).sum(1), st0), rows_known
     a.use_tf32 = 0                                               # the fp32 SIMT path has no gathered operand
     assert cuda_lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(a)), stream) == -4
 
