@@ -184,6 +184,7 @@ struct TcPlan {
   int w_early;          // 1: the resident weight matrix is staged BEFORE the wait on the previous kernel (PdrGemmArgs.w_static)
   int tma_gather;       // 1: whole 32-column chunks of the gathered table come by TMA tile::gather4 (one warp, one
                         //    instruction per 4 rows) instead of 8 cp.async pieces per row with per-thread address arithmetic
+  int lean;             // 1: packed GroupNorm -> ReLU prologue (PDR_GEMM_LEAN=0: the generic clamp-fma-clamp, A/B)
   int pdl_late;         // 1: the MMA warp releases the dependent launch after its last MMA, 0: every thread at kernel start
 };
 
@@ -597,15 +598,27 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
       ct.item = (int)blockIdx.x; ct.kc = 0;
       locate(ct);
       const int k_pro = a.tail_rows ? a.k_pro : a.K;          // columns that get the prologue
+      // per-sample rows of the prologue constants (scale / shift / embedding), re-derived only when the sample changes:
+      // the transform warps are bound by instruction issue (ncu, profiles/r02_gather_producer_notes.txt), and three 64-bit
+      // multiply-adds per chunk for pointers that change every few hundred chunks were part of it
+      const bool has_pro = a.pro_mode != PDR_PRO_NONE, has_add = a.add != nullptr;
+      int cb_b = -1;
+      const float *psc = nullptr, *psh = nullptr, *pad = nullptr;
       auto fetch = [&](const Cur &c, float4 &s4, float4 &h4, float4 &e4) {
         const int k = c.kc * kTcBK + chunk * 4;
         s4 = make_float4(1.f, 1.f, 1.f, 1.f); h4 = make_float4(0.f, 0.f, 0.f, 0.f); e4 = h4;
+        if (c.b != cb_b) {
+          cb_b = c.b;
+          if (has_pro) { psc = a.sc + (size_t)c.b * a.ld_scsh + chunk * 4; psh = a.sh + (size_t)c.b * a.ld_scsh + chunk * 4; }
+          if (has_add) pad = a.add + (size_t)c.b * a.ld_add + chunk * 4;
+        }
         if (k < k_pro) {
-          if (a.pro_mode != PDR_PRO_NONE) {
-            s4 = __ldg(reinterpret_cast<const float4 *>(a.sc + (size_t)c.b * a.ld_scsh + k));
-            h4 = __ldg(reinterpret_cast<const float4 *>(a.sh + (size_t)c.b * a.ld_scsh + k));
+          const int kk = c.kc * kTcBK;
+          if (has_pro) {
+            s4 = __ldg(reinterpret_cast<const float4 *>(psc + kk));
+            h4 = __ldg(reinterpret_cast<const float4 *>(psh + kk));
           }
-          if (a.add) e4 = __ldg(reinterpret_cast<const float4 *>(a.add + (size_t)c.b * a.ld_add + k));
+          if (has_add) e4 = __ldg(reinterpret_cast<const float4 *>(pad + kk));
         }
       };
       float4 s4, h4, e4;
@@ -667,7 +680,38 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
         auto xf = [&](float x, float sc, float sh, float e) {
           return fmaxf(fmaf(fmaxf(x, lo1), sc, sh), lo2) + e;
         };
-        if (a.R) {
+        if (a.pro_mode == PDR_PRO_GN_RELU && !a.R && plan.lean) {
+          // the common flavour (GroupNorm -> ReLU [+ embedding]), on packed fp32 pairs: y = max(fma(x, sc, sh), 0) [+ e]; every
+          // operation is the .rn form of the scalar one in xf() (whose first clamp is the identity here), bit for bit
+          unsigned long long s01, s23, h01, h23, e01, e23;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(s01) : "f"(s4.x), "f"(s4.y));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(s23) : "f"(s4.z), "f"(s4.w));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(h01) : "f"(h4.x), "f"(h4.y));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(h23) : "f"(h4.z), "f"(h4.w));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(e01) : "f"(e4.x), "f"(e4.y));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(e23) : "f"(e4.z), "f"(e4.w));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 v = *reinterpret_cast<const float4 *>(sr + i * 4096);
+            unsigned long long v01, v23;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(v01) : "f"(v.x), "f"(v.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(v23) : "f"(v.z), "f"(v.w));
+            asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v01) : "l"(s01), "l"(h01));
+            asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v23) : "l"(s23), "l"(h23));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(v01));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(v23));
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            if (has_add) {
+              asm("mov.b64 %0, {%1, %2};" : "=l"(v01) : "f"(v.x), "f"(v.y));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(v23) : "f"(v.z), "f"(v.w));
+              asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v01) : "l"(e01));
+              asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v23) : "l"(e23));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(v01));
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(v23));
+            }
+            *reinterpret_cast<float4 *>(sa + i * 4096) = tf32x4(v);
+          }
+        } else if (a.R) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float4 v = *reinterpret_cast<const float4 *>(sr + i * 4096);
@@ -1394,6 +1438,11 @@ int launch_tc(const PdrGemmArgs &a, cudaStream_t stream) {
   plan.epi_alt = epilogue_alternates_tiles() ? 1 : 0;
   plan.prod_sleep_ns = producer_sleep_ns();
   plan.pdl_late = pdl_mode() == 2;
+  {
+    static int lean = -1;
+    if (lean < 0) { const char *e = getenv("PDR_GEMM_LEAN"); lean = !(e && e[0] == '0'); }
+    plan.lean = lean;
+  }
   plan.w_early = pdl_mode() != 0 && a.w_static;
   // epilogue flavour: pooling when asked for; float4 for the broadcast row-add on 32-column blocks; otherwise scalar, or
   // (PDR_GEMM_EPILOGUE=tma) the TMA-store flavour (row groups of at least 8 rows)
