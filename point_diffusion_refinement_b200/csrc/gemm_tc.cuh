@@ -414,7 +414,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     Cur ci;
     ci.item = (int)blockIdx.x; ci.kc = 0;
     static_assert(kIdxAhead == 1, "one look-ahead position");
-    if (gath && !is_loader) {
+    // the gathered operand without TMA has its own, lean, loop below
+    const bool lean_gather = plan.direct && gath && !tg;
+    if (gath && !is_loader && !lean_gather) {
       ahead.item = ci.item; locate_pos(ahead);
       if (tg_warp) fetch_g4(ahead, g4c);
       if (need_cidx) fetch_idx(ahead, cidx);
@@ -424,7 +426,80 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
     }
     locate(ci); derive(ci);
 
-    if (plan.direct) {
+    if (lean_gather) {
+      // ---- gathered A (feature-table rows picked by a_rows | dense geometric channels), no prologue.  ncu showed these
+      //      producers busy 95 % of the kernel at 170 - 200 warp-instructions per 16 KiB chunk in the general loop below
+      //      (kernel parameters re-read from the constant bank, cursor divisions, pointers derived per chunk, the W tile
+      //      behind two levels of predicates): profiles/r02_gather_producer_notes.txt.  Here everything that depends on the
+      //      item only is computed once per item -- 32-bit element offsets of my four table rows, validity masks, the W
+      //      row count -- and a chunk costs one 64-bit add per operand plus (IMAD.WIDE, LDGSTS) per copy. ----
+      if (!is_loader && my_items > 0) {
+        const int lda16 = a.lda >> 2, ksplit = a.k_split, Kk = a.K, rps = a.rows_per_sample;     // lda % 4 == 0
+        const size_t st2 = (size_t)32 * a.lda2 * sizeof(float);
+        const size_t wst = (size_t)32 * a.ldw * sizeof(float);
+        const char *const Abase = reinterpret_cast<const char *>(a.A + chunk * 4);
+        const int t_last = Kk - 4;                                // last 16-byte piece inside K (K % 4 == 0)
+        Pos cur;
+        cur.item = (int)blockIdx.x; locate_pos(cur);
+        ahead = cur; step_pos(ahead);
+        int ci4[4] = {-1, -1, -1, -1}, ni4[4] = {-1, -1, -1, -1};
+        fetch_idx(cur, ci4);
+        fetch_idx(ahead, ni4);
+        int stage = 0, phase = 0;
+        uint32_t sa = smem_u32(s_stages) + sw_off;
+        for (int it = 0; it < my_items; ++it) {
+          const int r0 = cur.tis * kTcTileM;
+          const int rows_valid = min(kTcTileM, rps - r0);
+          // geometric channels of my row arow (+ 32 i): column t - ksplit of piece t = kofs + chunk * 4
+          const char *const g0 = reinterpret_cast<const char *>(a.A2 + ((size_t)cur.b * rps + r0 + arow) * a.lda2);
+          int toff[4], tsz[4], gsz[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            toff[i] = ci4[i] < 0 ? 0 : ci4[i] * lda16;            // in 16-byte units: tables up to 32 GiB
+            tsz[i] = ci4[i] < 0 ? 0 : 16;
+            gsz[i] = arow + 32 * i < rows_valid ? 16 : 0;
+          }
+          const int n0 = cur.ct * bn;
+          const char *const w0 = reinterpret_cast<const char *>(a.W + (size_t)(n0 + arow) * a.ldw + chunk * 4);
+          const int w_rows = min(bn, a.N - n0) - arow;            // W rows n0 + arow + 32 i exist for 32 i < w_rows
+          // the next item's rows are requested now, a whole item ahead of their use
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ci4[i] = ni4[i];
+          step_pos(cur);
+          step_pos(ahead);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ni4[i] = -1;
+          fetch_idx(ahead, ni4);
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait_sleep(&bar_empty[stage], (uint32_t)(phase ^ 1), (uint32_t)plan.prod_sleep_ns);
+            const int kofs = kc * kTcBK, t = kofs + chunk * 4;
+            if (t < ksplit) {
+              const char *const ak = Abase + (size_t)kofs * sizeof(float);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cp_async16_sz(sa + i * 4096, ak + (long long)toff[i] * 16, tsz[i]);
+            } else {
+              const bool in = t < Kk;                              // beyond K: zeros (no bytes are read)
+              const char *const gk = g0 + (size_t)(min(t, t_last) - ksplit) * sizeof(float);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cp_async16_sz(sa + i * 4096, gsz[i] ? gk + i * st2 : Abase, in ? gsz[i] : 0);
+            }
+            if (!WRES) {
+              const bool in = t < Kk;
+              const char *const wk = w0 + (size_t)min(t, t_last) * sizeof(float) - (size_t)chunk * 4 * sizeof(float);
+#pragma unroll
+              for (int i = 0; i < kWLoads; ++i)
+                if (BN < 256 || i * 32 < bn) {
+                  const bool ok = in && 32 * i < w_rows;
+                  cp_async16_sz(sa + kATileBytes + i * 4096, ok ? wk + i * wst : Abase, ok ? 16 : 0);
+                }
+            }
+            cp_async_arrive_noinc(&bar_full[stage]);
+            sa += (uint32_t)kStageBytes;
+            if (++stage == S) { stage = 0; phase ^= 1; sa = smem_u32(s_stages) + sw_off; }
+          }
+        }
+      }
+    } else if (plan.direct) {
       // ---- no prologue: all 8 producer warps cp.async straight into the swizzled MMA stage.  Completion is
       //      signalled by cp.async.mbarrier.arrive (no wait_group, no fence: a fence.proxy.async compiles to
       //      MEMBAR.ALL.CTA, which also waits for the YOUNGER copies in flight and serialised the ring --
