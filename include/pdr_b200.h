@@ -231,6 +231,10 @@ typedef struct PdrGemmArgs {
   /* gathered A: number of rows of the table A (every a_rows[r] < table_rows).  > 0 lets the tensor-core kernel fetch whole
    * 32-column chunks of the table part with TMA tile::gather4; 0 = unknown (cp.async pieces). */
   int table_rows;
+  /* stats_skip per 32-column block of the output: bits 2 j, 2 j + 1 = the stats_skip bits of columns [32 j, 32 j + 32), j < 32
+   * (OR-ed with stats_skip; a merged GEMM whose column ranges feed different normalisations computes each pair only where
+   * some consumer reads it). */
+  unsigned long long stats_skip_blocks;
 } PdrGemmArgs;
 int pdr_gemm_tile_rows(void);            /* rows per tile (tiles_per_sample = ceil(rows_per_sample / this)) */
 int pdr_gemm_fused(const PdrGemmArgs *args, void *stream);

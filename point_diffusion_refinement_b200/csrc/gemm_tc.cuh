@@ -842,6 +842,11 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   } else {
     // =============================== EPILOGUE ================================================
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32)
+    // statistics pairs nobody reads in the 32-column block that starts at column n (PdrGemmArgs.stats_skip / stats_skip_blocks)
+    auto skip_of = [&](int n) {
+      const int blk = n >> 5;
+      return a.stats_skip | (blk < 32 ? (int)((a.stats_skip_blocks >> (2 * blk)) & 3ull) : 0);
+    };
     const int half = warp >> 2;                   // which of the two warps sharing this lane quarter
     constexpr bool VEC = EPI == 1, POOL = EPI == 2, TMA = EPI == 3;
     // epilogue block width: 32 columns; 16 for the narrowest tile so that all 8 warps have work there (the pooling
@@ -1057,7 +1062,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
             // specialised at compile time on what is needed: P = (sum, sum^2), R = the relu pair, AI = all four columns
             // of every lane are inside N (no select, packed bias add).  ~3-5 instructions per element.
             const bool all_in = __all_sync(0xffffffffu, in3);
-            const bool needP = a.stats && !(a.stats_skip & 1), needR = a.stats && !(a.stats_skip & 2);
+            const int sk = skip_of(n0 + cb);
+            const bool needP = a.stats && !(sk & 1), needR = a.stats && !(sk & 2);
             unsigned long long cur01, cur23;
             asm("mov.b64 %0, {%1, %2};" : "=l"(cur01) : "f"(cur.x), "f"(cur.y));
             asm("mov.b64 %0, {%1, %2};" : "=l"(cur23) : "f"(cur.z), "f"(cur.w));
@@ -1230,7 +1236,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (a.stats) {
-            const bool needP = !(a.stats_skip & 1), needR = !(a.stats_skip & 2);
+            const int sk = skip_of(n0 + cb);
+            const bool needP = !(sk & 1), needR = !(sk & 2);
             float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
             // element (r, c) sits at r * 128 + (((c >> 2) ^ (r & 7)) << 4) + (c & 3) * 4 bytes: 8 per-lane offsets, one
             // per value of r & 7, then immediates
@@ -1327,7 +1334,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
               }
             };
             using T = std::true_type; using F = std::false_type;
-            const bool needP = a.stats && !(a.stats_skip & 1), needR = a.stats && !(a.stats_skip & 2);
+            const int sk = skip_of(n0 + cb);
+            const bool needP = a.stats && !(sk & 1), needR = a.stats && !(sk & 2);
             if (needP && needR) rows_loop(T{}, T{});
             else if (needP) rows_loop(T{}, F{});
             else if (needR) rows_loop(F{}, T{});

@@ -58,7 +58,8 @@ class GemmArgs(ctypes.Structure):
                 ("pool_K", ctypes.c_int), ("pool_V", c_float_p), ("pool_ldv", ctypes.c_int),
                 ("pool_sc", c_float_p), ("pool_sh", c_float_p), ("pool_ld_scsh", ctypes.c_int),
                 ("pool_counts", c_float_p), ("pool_out", c_float_p), ("pool_ldo", ctypes.c_int),
-                ("max_ctas", ctypes.c_int), ("w_static", ctypes.c_int), ("table_rows", ctypes.c_int)]
+                ("max_ctas", ctypes.c_int), ("w_static", ctypes.c_int), ("table_rows", ctypes.c_int),
+                ("stats_skip_blocks", ctypes.c_uint64)]
 
 
 GN_MAX_SOURCES = 4
@@ -80,6 +81,7 @@ class GnArgs(ctypes.Structure):
 PRO_NONE, PRO_GN_RELU, PRO_RELU_GN = 0, 1, 2
 # A/B switch for profiling only: PDR_STATS_SKIP=0 makes every GEMM epilogue accumulate both statistics pairs
 _STATS_SKIP_HINT = os.environ.get("PDR_STATS_SKIP", "1") != "0"
+_STATS_SKIP_BLOCKS = os.environ.get("PDR_STATS_SKIP_BLOCKS", "1") != "0"   # 0: a pair one consumer reads is computed under every column (A/B)
 # PDR_GEOM_OVERLAP=0 puts the per-step geometry chain (FPS x4 -> centre gathers -> 8 of the 9 ball queries -> kNN x4; ~1.0 ms of
 # 1-32-CTA grids) back in line.  Default: it runs on a second stream next to the first encoder feature-mapper block, which only
 # needs the level-0 ball query; the kernels of that block leave 148 - PDR_GEOM_OVERLAP_CTAS SMs free (max_ctas): their CTAs own
@@ -344,7 +346,10 @@ class FusedDenoiser:
             tiles = (rows_per_sample + self.tile_rows - 1) // self.tile_rows
             st = Stats(self._zeros(batch * tiles, N, 4), tiles, N, rows_per_sample, g)
             g.stats = st.t.data_ptr()
-            g.stats_skip = 3 if _STATS_SKIP_HINT else 0     # until a consumer registers (gn)
+            # until consumers register (gn): nothing is needed.  Per 32-column block, so that a merged GEMM (first | key ...)
+            # computes the plain pair only under the columns a GroupNorm reads plain, the relu pair only under the others
+            g.stats_skip = 0
+            g.stats_skip_blocks = 0xFFFFFFFFFFFFFFFF if _STATS_SKIP_HINT else 0
         g.use_tf32 = self.use_tf32 if rows_per_sample * batch >= 512 else 0
         if g.use_tf32:
             W = tf32_round(W)
@@ -387,7 +392,10 @@ class FusedDenoiser:
             s.col0, s.ncols, s.out_col0 = col0, ncols, off
             s.use_relu, s.rows, s.mult = int(use_relu), st.rows, float(mult)
             if st.g is not None:
-                st.g.stats_skip &= ~(2 if use_relu else 1)
+                bit = 2 if use_relu else 1
+                blocks = range(col0 // 32, min((col0 + ncols - 1) // 32, 31) + 1) if _STATS_SKIP_BLOCKS else range(32)
+                for blk in blocks:
+                    st.g.stats_skip_blocks &= ~(bit << (2 * blk))
             off += rp(ncols)
         a.nsrc, a.batch, a.channels, a.gn_channels, a.groups = len(sources), batch, channels, gn_channels, groups
         gamma = gnm.weight.detach().float().contiguous()

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _run(lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32, want_stats=True, ldc=None, stats_skip=0):
+def _run(lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32, want_stats=True, ldc=None, stats_skip=0, stats_skip_blocks=0):
     from point_diffusion_refinement_b200.fused import GemmArgs
     M, K = A.shape
     ldc = ldc or (N + 3) // 4 * 4
@@ -33,6 +33,7 @@ def _run(lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32,
     g.stats = stats.data_ptr() if want_stats else None
     g.use_tf32 = int(use_tf32)
     g.stats_skip = stats_skip
+    g.stats_skip_blocks = stats_skip_blocks
     rc = lib.pdr_gemm_fused(ctypes.c_void_p(ctypes.addressof(g)), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.pdr_last_error_string()
     torch.cuda.synchronize()
@@ -161,6 +162,11 @@ def test_gemm_stats_skip_hint(cuda_lib, case):
     C3, _ = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True, stats_skip=3)
     assert torch.equal(C0, C1) and torch.equal(C0, C2) and torch.equal(C0, C3)
     assert torch.equal(st1[..., :2], st0[..., :2]) and torch.equal(st2[..., 2:], st0[..., 2:])
+    # per 32-column block (stats_skip_blocks): block 0 keeps the plain pair only, block 1 the relu pair only, the rest everything
+    C4, st4 = _run(cuda_lib, A, W, bias, B, rps, N, pro, sc, sh, add, R, rowadd, div, use_tf32=True, stats_skip_blocks=2 | (1 << 2))
+    assert torch.equal(C0, C4)
+    assert torch.equal(st4[:, :32, :2], st0[:, :32, :2]) and torch.equal(st4[:, 32:64, 2:], st0[:, 32:64, 2:])
+    assert torch.equal(st4[:, 64:], st0[:, 64:])
 
 
 @pytest.mark.parametrize("shape", [(2, 4096, 35, 9, 140, 3000), (3, 1000, 4, 9, 96, 700), (2, 2048, 160, 11, 428, 512),
