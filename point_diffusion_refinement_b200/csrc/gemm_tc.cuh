@@ -1209,18 +1209,23 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
           const uint32_t tile = s_tma + ((uint32_t)warp * (uint32_t)tma_bufs(BN) + tma_buf) * 4096u;
           if constexpr (tma_bufs(BN) == 2) tma_buf ^= 1u;
           {
-            const uint32_t trow = tile + (uint32_t)lane * 128u;
-            const uint32_t sw = (uint32_t)lane & 7u;
+            // chunk j of my row sits at row + ((j ^ (lane & 7)) << 4); the row start is 128-byte aligned, so that is
+            // (row | (lane & 7) << 4) ^ (j << 4): one LOP3 with an immediate per store.  The addends go on in packed pairs.
+            const uint32_t trow = (tile + (uint32_t)lane * 128u) | (((uint32_t)lane & 7u) << 4);
             float4 c4[4];
   #pragma unroll
             for (int j = 0; j < 4; ++j) c4[j] = *reinterpret_cast<const float4 *>(sadd + 16 + 4 * j);
   #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = j < 4 ? b4[j] : c4[j - 4];
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (((uint32_t)j ^ sw) << 4)),
-                           "f"(__uint_as_float(v[4 * j]) + b.x), "f"(__uint_as_float(v[4 * j + 1]) + b.y),
-                           "f"(__uint_as_float(v[4 * j + 2]) + b.z), "f"(__uint_as_float(v[4 * j + 3]) + b.w)
-                           : "memory");
+              unsigned long long y01, y23, b01, b23;
+              asm("mov.b64 %0, {%1, %2};" : "=l"(y01) : "r"(v[4 * j]), "r"(v[4 * j + 1]));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(y23) : "r"(v[4 * j + 2]), "r"(v[4 * j + 3]));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(b01) : "f"(b.x), "f"(b.y));
+              asm("mov.b64 %0, {%1, %2};" : "=l"(b23) : "f"(b.z), "f"(b.w));
+              asm("add.rn.f32x2 %0, %0, %1;" : "+l"(y01) : "l"(b01));
+              asm("add.rn.f32x2 %0, %0, %1;" : "+l"(y23) : "l"(b23));
+              asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(trow ^ ((uint32_t)j << 4)), "l"(y01), "l"(y23) : "memory");
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1243,7 +1248,8 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
             // per value of r & 7, then immediates
             uint32_t toff[8];
   #pragma unroll
-            for (int k = 0; k < 8; ++k) toff[k] = tile + ((((uint32_t)lane >> 2) ^ (uint32_t)k) << 4) + ((uint32_t)lane & 3u) * 4u;
+            for (int k = 0; k < 8; ++k)      // tile is 4 KiB aligned: (tile | chunk << 4 | word << 2) ^ (k << 4)
+              toff[k] = (tile | (((uint32_t)lane >> 2) << 4) | (((uint32_t)lane & 3u) << 2)) ^ ((uint32_t)k << 4);
             // two rows per step on packed fp32 pairs (add / fma.rn.f32x2): the epilogue warps are bound by instruction
             // issue, and the even and the odd rows get one partial sum each, added at the end
             unsigned long long s01 = 0ull, q01 = 0ull, r01 = 0ull, u01 = 0ull;
