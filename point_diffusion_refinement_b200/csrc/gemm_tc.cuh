@@ -230,7 +230,9 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   constexpr uint32_t kPartRegion = (uint32_t)(BN <= 128 ? 4 : 2) * 4u * BN * 16u;
   const uint32_t s_tma = s_part + kPartRegion;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (warp index through a shuffle from lane 0: nvcc then knows it is warp-uniform, keeps what derives from it in uniform registers
+  //  and issues UTMASTG / UTCHMMA / SYNCS operands without a per-lane R2UR loop)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int S = plan.stages, nk = plan.nk;
   if (!plan.pdl_late) pdl_launch_dependents();      // PDL (common.cuh): the next kernel's grid may be launched; it waits for this one
 
