@@ -256,7 +256,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem_base, 0);   // (uniform for ptxas, like the warp index)
   // barrier init and the TMEM allocation above overlap the tail of the previous kernel; from here on global memory is touched
   const bool stages_w_first = WRES && plan.w_early && warp >= kEpiWarps && warp < kEpiWarps + kProdWarps;
   if (!stages_w_first) pdl_wait();

@@ -243,7 +243,7 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
   __shared__ int s_mma_first[PDR_CHAIN_MAX_STEPS + 1];
   __shared__ EpiEntry s_epi[kMaxOps];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform for ptxas (gemm_tc.cuh)
   constexpr int wpg = WPG;
   const int n_epi_warps = 2 * wpg, mma_warp = n_epi_warps + kProdWarps;
   const int nthreads = (mma_warp + 1) * 32;
