@@ -483,7 +483,7 @@ gemm_tf32_persistent(const PdrGemmArgs a, const TcPlan plan, const __grid_consta
               const bool in = t < Kk;                              // beyond K: zeros (no bytes are read)
               const char *const gk = g0 + (size_t)(min(t, t_last) - ksplit) * sizeof(float);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) cp_async16_sz(sa + i * 4096, gsz[i] ? gk + i * st2 : Abase, in ? gsz[i] : 0);
+              for (int i = 0; i < 4; ++i) cp_async16_sz(sa + i * 4096, (in && gsz[i]) ? gk + i * st2 : Abase, in ? gsz[i] : 0);
             }
             if (!WRES) {
               const bool in = t < Kk;
