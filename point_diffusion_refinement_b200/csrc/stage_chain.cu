@@ -175,6 +175,15 @@ __device__ __forceinline__ void sts4(uint32_t a, float4 v) {
 }
 
 // one tcgen05.mma (one K step of 8) of the step program, everything precomputed but the tile group / X0 slot bases
+// A value every lane of the warp holds alike, made visibly so for ptxas (shuffle from lane 0): what derives from it lives in
+// uniform registers, and UTCHMMA / LDTM / STTM / SYNCS take it without an ELECT + R2UR.BROADCAST loop around each instruction
+// (the step tables below are read from shared memory, which ptxas must otherwise treat as per-lane data).
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t uni(uint64_t v) {
+  return ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(v >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (uint32_t)v, 0);
+}
+
 struct MmaEntry {
   uint64_t bdesc;        // complete shared-memory descriptor of the weight slice
   uint32_t d_col;        // accumulator column inside the group
@@ -387,17 +396,24 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
           first[g] = false;
           if (s == 0) mbar_wait(&bar_full[slot], slot_phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (lane == 0) {
+          {
+            // every lane reads the table entry (one broadcast LDS) and the fields are made uniform; lane 0 issues
             const uint32_t tg = tmem_base + (uint32_t)(g * kGroupCols);
             const uint64_t x0desc = make_desc(s_x0_u + (uint32_t)slot * slot_bytes);
-            const int m_end = s_mma_first[s + 1];
-            for (int m = s_mma_first[s]; m < m_end; ++m) {
+            const int m_end = uni(s_mma_first[s + 1]);
+            for (int m = uni(s_mma_first[s]); m < m_end; ++m) {
               const MmaEntry t = s_mma[m];
-              if (t.flags & 1u) umma_ts(tg + t.d_col, tg + t.a, t.bdesc, t.idesc, t.flags >> 1);
-              else umma_ss(tg + t.d_col, x0desc + (uint64_t)t.a, t.bdesc, t.idesc, t.flags >> 1);
+              const uint64_t bdesc = uni(t.bdesc);
+              const uint32_t d_col = uni(t.d_col), ta = uni(t.a), idesc = uni(t.idesc), flags = uni(t.flags);
+              if (lane == 0) {
+                if (flags & 1u) umma_ts(tg + d_col, tg + ta, bdesc, idesc, flags >> 1);
+                else umma_ss(tg + d_col, x0desc + (uint64_t)ta, bdesc, idesc, flags >> 1);
+              }
             }
-            umma_commit(&bar_mma_done[g]);
-            if (release_mask & (1u << s)) umma_commit(&bar_empty[slot]);
+            if (lane == 0) {
+              umma_commit(&bar_mma_done[g]);
+              if (release_mask & (1u << s)) umma_commit(&bar_empty[slot]);
+            }
           }
           __syncwarp();
         }
@@ -451,9 +467,11 @@ stage_chain_kernel(const __grid_constant__ PdrChainArgs a, const ChainPlan plan)
         bool wrote_tmem = false, did_stats = false;
         int unit = 0;
         for (int e = 0; e < n_epi; ++e) {
-          const EpiEntry opd = s_epi[s * PDR_CHAIN_MAX_EPI + e];
-          const int kind = opd.kind, d_col = opd.d_col, ncols = opd.ncols, pro_mode = opd.pro_mode;
-          const int nblk = opd.nblk;
+          EpiEntry opd = s_epi[s * PDR_CHAIN_MAX_EPI + e];
+          opd.a_col = uni(opd.a_col); opd.stat_col0 = uni(opd.stat_col0); opd.stat_skip = uni(opd.stat_skip);
+          opd.v_col = uni(opd.v_col); opd.cblk = uni(opd.cblk);
+          const int kind = uni(opd.kind), d_col = uni(opd.d_col), ncols = uni(opd.ncols), pro_mode = uni(opd.pro_mode);
+          const int nblk = uni(opd.nblk);
           const float *rowadd = opd.rowadd ? opd.rowadd + point * (size_t)opd.ld_rowadd : nullptr;
           const float *cop = cg + opd.cblk * 96;
           wrote_tmem |= kind == PDR_CHAIN_XFORM;
