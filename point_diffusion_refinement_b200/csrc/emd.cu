@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kEmdThreads)
 emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float *__restrict__ xyz2_all,
            float *__restrict__ match_all, float *temp_all, float *__restrict__ cost_out) {
   __shared__ float4 tile[kEmdTile];
+  __shared__ float tile_w1[kEmdTile];     // fused sweep: remainR of the staged points (the weight of the next level's pass 1)
   __shared__ float s_cost[kEmdThreads / 32];
   const int cloud = blockIdx.x / cs, rank = blockIdx.x % cs, tid = threadIdx.x;
   const float *xyz1 = xyz1_all + (size_t)cloud * n * 3;
@@ -123,6 +124,9 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
     level *= 1.4426950408889634f;
 #endif
     // ---- pass 1: ratioL[k] = remainL[k] / (1e-9 + sum_l e(k,l) * remainR[l]) ---------------------
+    // (first level only: for the later levels it rides in the previous level's pass 3 -- one sweep over the same pairs, one
+    //  distance evaluation for two exponentials; same operations in the same order per accumulator, bit-identical)
+    if (j == 7)
     for (int g = kb; g < ke; g += kEmdThreads * R) {
       float x[R], y[R], z[R], acc[R];
 #pragma unroll
@@ -175,7 +179,7 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
         if (k < ke) __stcg(ratioL + k, __ldcg(remainL + k) / acc[r]);
       }
     }
-    sync_all(cs);
+    if (j == 7) sync_all(cs);
     // ---- pass 2: columns.  sumr = remainR[l] * sum_k e * ratioL[k] ---------------------------------
     for (int g = lb; g < le; g += kEmdThreads * R) {
       float x[R], y[R], z[R], acc[R];
@@ -238,8 +242,15 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
     }
     sync_all(cs);
     // ---- pass 3: w = e * ratioL[k] * ratioR[l]; match += w; remainL[k] -= sum_l w; cost += d^2 w --
+    //      + pass 1 of the NEXT level in the same sweep: acc1[k] = 1e-9 + sum_l e'(k,l) * remainR[l] (remainR as pass 2 just
+    //      left it), ratioL[k] = remainL_new[k] / acc1[k]
+    const bool fuse_next = j > -2;
+    float level1 = (j - 1 == -2) ? 0.f : -powf(4.0f, (float)(j - 1));
+#ifndef PDR_EMD_EXACT_EXPF
+    level1 *= 1.4426950408889634f;
+#endif
     for (int g = kb; g < ke; g += kEmdThreads * R) {
-      float x[R], y[R], z[R], acc[R], rl[R];
+      float x[R], y[R], z[R], acc[R], rl[R], acc1[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int kr = g + r * kEmdThreads + tid;
@@ -247,30 +258,47 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
         x[r] = __ldg(xyz1 + k * 3); y[r] = __ldg(xyz1 + k * 3 + 1); z[r] = __ldg(xyz1 + k * 3 + 2);
         rl[r] = kr < ke ? __ldcg(ratioL + k) : 0.f;  // rows this CTA does not own contribute w = 0
         acc[r] = 0.f;
+        acc1[r] = 1e-9f;
       }
       for (int l0 = 0; l0 < m; l0 += kEmdTile) {
         const int cnt = min(kEmdTile, m - l0);
         __syncthreads();
         stage(tile, xyz2, ratioR, l0, cnt);
+        if (fuse_next)
+          for (int i = tid; i < cnt; i += kEmdThreads) tile_w1[i] = __ldcg(remainR + l0 + i);
         __syncthreads();
         if constexpr (R >= 2) {
-          f32x2 nx[R / 2], ny[R / 2], nz[R / 2], ac[R / 2], rl2[R / 2];
+          f32x2 nx[R / 2], ny[R / 2], nz[R / 2], ac[R / 2], rl2[R / 2], a1[R / 2];
 #pragma unroll
           for (int q = 0; q < R / 2; ++q) {
             nx[q] = pk2(-x[2 * q], -x[2 * q + 1]); ny[q] = pk2(-y[2 * q], -y[2 * q + 1]); nz[q] = pk2(-z[2 * q], -z[2 * q + 1]);
             ac[q] = pk2(acc[2 * q], acc[2 * q + 1]); rl2[q] = pk2(rl[2 * q], rl[2 * q + 1]);
+            a1[q] = pk2(acc1[2 * q], acc1[2 * q + 1]);
           }
-          const f32x2 lvl2 = pk2(level, level);
+          const f32x2 lvl2 = pk2(level, level), lvl1 = pk2(level1, level1);
 #pragma unroll 2
           for (int l = 0; l < cnt; ++l) {
             const float4 p = tile[l];
             const f32x2 pw = pk2(p.w, p.w);
+            const float w1s = fuse_next ? tile_w1[l] : 0.f;
+            const f32x2 pw1 = pk2(w1s, w1s);
 #pragma unroll
             for (int q = 0; q < R / 2; ++q) {
               f32x2 d, e;
               pair_d_e(p, nx[q], ny[q], nz[q], lvl2, d, e);
               const f32x2 w = mul2(mul2(e, rl2[q]), pw);
               ac[q] = add2(ac[q], w);
+              if (fuse_next) {
+                float b0, b1, e0, e1;
+                upk2(mul2(lvl1, d), b0, b1);
+#ifdef PDR_EMD_EXACT_EXPF
+                e0 = __expf(b0); e1 = __expf(b1);
+#else
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(b0));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(b1));
+#endif
+                a1[q] = fma2(pk2(e0, e1), pw1, a1[q]);
+              }
               if (ACC_COST || WRITE_MATCH) {
                 float d0, d1, w0, w1;
                 upk2(d, d0, d1); upk2(w, w0, w1);
@@ -287,16 +315,18 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
             }
           }
 #pragma unroll
-          for (int q = 0; q < R / 2; ++q) upk2(ac[q], acc[2 * q], acc[2 * q + 1]);
+          for (int q = 0; q < R / 2; ++q) { upk2(ac[q], acc[2 * q], acc[2 * q + 1]); upk2(a1[q], acc1[2 * q], acc1[2 * q + 1]); }
         } else {
 #pragma unroll 2
           for (int l = 0; l < cnt; ++l) {
             const float4 p = tile[l];
+            const float w1s = fuse_next ? tile_w1[l] : 0.f;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               const float d = dist2_ref(__fsub_rn(p.x, x[r]), __fsub_rn(p.y, y[r]), __fsub_rn(p.z, z[r]));
               const float w = emd_exp(level, d) * rl[r] * p.w;
               acc[r] += w;
+              if (fuse_next) acc1[r] = __fmaf_rn(emd_exp(level1, d), w1s, acc1[r]);
               if (ACC_COST) cost_acc = __fmaf_rn(d, w, cost_acc);
               if (WRITE_MATCH) {
                 const int k = g + r * kEmdThreads + tid;
@@ -312,7 +342,11 @@ emd_kernel(int n, int m, int cs, const float *__restrict__ xyz1_all, const float
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int k = g + r * kEmdThreads + tid;
-        if (k < ke) __stcg(remainL + k, fmaxf(0.0f, __ldcg(remainL + k) - acc[r]));
+        if (k < ke) {
+          const float left = fmaxf(0.0f, __ldcg(remainL + k) - acc[r]);
+          __stcg(remainL + k, left);
+          if (fuse_next) __stcg(ratioL + k, left / acc1[r]);
+        }
       }
     }
     sync_all(cs);
