@@ -227,6 +227,35 @@ def test_geometry_overlap_program_layout(cuda_lib, monkeypatch):
     assert all(g.max_ctas == 0 for g in off.keep if isinstance(g, fused.GemmArgs))
 
 
+def test_gemm_argument_flags_of_the_compiled_program(cuda_lib, monkeypatch):
+    """Launch hints the engine sets on every PdrGemmArgs: weights are static (the kernel may stage them before its
+    programmatic-dependency wait); the TMA gather of the table chunks is an opt-in (PDR_GEMM_TMA_GATHER); the statistics pairs are
+    requested per 32-column block -- a merged first GEMM computes the plain pair under the columns a GroupNorm->ReLU reads and the
+    relu pair under the ReLU->GroupNorm ones, never both under the same block unless two consumers overlap there."""
+    from point_diffusion_refinement_b200 import configs, fused
+    from point_diffusion_refinement_b200.pointnet2_with_pcld_condition import PointNet2CloudCondition
+    monkeypatch.setattr(fused, "_STAGE_CHAIN", False)
+    engines = {}
+    for tma in (False, True):
+        monkeypatch.setattr(fused, "_TMA_GATHER", tma)
+        eng = fused.FusedDenoiser(PointNet2CloudCondition(configs.tiny_pointnet_config()).eval(), 2, 256, use_tf32=True,
+                                  use_graph=False)
+        eng.build(384)
+        engines[tma] = [g for g in eng.keep if isinstance(g, fused.GemmArgs)]
+    off, on = engines[False], engines[True]
+    assert len(off) == len(on) and all(g.w_static == 1 for g in off)
+    assert all(g.table_rows == 0 for g in off)
+    assert all((g.table_rows > 0) == bool(g.a_rows) for g in on)
+    with_stats = [g for g in off if g.stats]
+    assert with_stats and all(g.stats_skip == 0 for g in with_stats)
+    mixed = 0
+    for g in with_stats:
+        bits = [(g.stats_skip_blocks >> (2 * b)) & 3 for b in range((g.N + 31) // 32)]
+        assert any(b != 3 for b in bits), (g.N, bits)                  # a statistics GEMM has at least one consumer
+        mixed += len(set(bits)) > 1
+    assert mixed >= 4                                                  # the merged first GEMMs of the grouped stages
+
+
 def test_builtin_hdf5_writer_is_readable_by_h5py(tmp_path):
     """the built-in HDF5 writer against the real library -- runs wherever h5py is installed (not in this image)."""
     h5py = pytest.importorskip("h5py")
