@@ -25,6 +25,15 @@
 //   When the whole weight matrix fits in shared memory next to the ring it is staged once per CTA (W-resident mode)
 //   and the ring carries A only.
 //
+// Round 2 (ncu role analysis in profiles/r02_gather_producer_notes.txt: these kernels are bound by instruction ISSUE, not by HBM):
+//   * the warp index comes through a shuffle from lane 0, so ptxas knows it is warp-uniform and keeps role / tile / barrier state in
+//     uniform registers (no ELECT + R2UR loop around every UTMASTG / UTCHMMA / SYNCS): -7 % step;
+//   * launched as a programmatic dependent (griddepcontrol.wait after the barrier / TMEM set-up; the MMA warp releases the next
+//     kernel after its last MMA; resident weights staged before the wait when PdrGemmArgs.w_static);
+//   * column tiles of the widest template are balanced (TcPlan.bn), short GEMMs take narrower tiles (gemm_tc.cu);
+//   * the gathered operand has its own lean producer loop (and an optional TMA tile::gather4 path), the GroupNorm -> ReLU
+//     prologue and the epilogue statistics / bias run on packed fp32 pairs.
+//
 // This header holds the kernel template and its launcher; gemm_tc_bn{32,64,128,256}.cu instantiate one column-tile
 // width each (so that nvcc compiles them in parallel), gemm_tc.cu picks the width.
 #pragma once
